@@ -1,0 +1,182 @@
+/*
+ * osteo_ddpm.h — C-ABI of the B200-native conditional-DDPM hot path.
+ *
+ * The reference (rare-resilience-ai/Osteosarcoma_DiffusionModel) is pure Python and has no
+ * FFI / plugin layer; its boundary for this path is the class
+ * `BiologyAwareDiffusionModel` (models/diffusion.py:259-449) and three validators
+ * (utils/validation.py:125-175, :177-223, :273-298).  Each entry point below names the
+ * reference interface it replaces.  The Python mirror of that class
+ * (osteosarcoma_diffusionmodel_b200/diffusion.py) binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain ints / floats / pointers; no torch types.
+ *   - every `*_dev` pointer is a DEVICE pointer (row-major, dense unless a pitch is given);
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - returns 0 on success, negative on error; osteo_last_error() gives the message.
+ *   - calls enqueue work on `stream` and do not synchronise unless stated.
+ *   - the library owns its workspace (repacked weights, activations, padded state);
+ *     it never allocates or frees caller-visible memory and never keeps caller pointers
+ *     beyond the call, except weights which are repacked (copied) in set_weights.
+ *   - there is NO CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef OSTEO_DDPM_H
+#define OSTEO_DDPM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct osteo_ddpm_ctx osteo_ddpm_ctx;
+
+/* Precision of the tensor-core contractions. */
+enum {
+    OSTEO_PREC_BF16 = 0,   /* bf16 operands, fp32 accumulate (throughput mode)                     */
+    OSTEO_PREC_FP32X3 = 1  /* split-bf16 hi/lo, 3 tcgen05 passes, ~fp32 accuracy (parity mode)     */
+};
+
+/* Number of weight tensors expected by osteo_ddpm_set_weights for `n_hidden` hidden dims:
+ * 4 (condition_embed) + 8 (input/cond/time/output proj) + 8 per block, blocks = 2*(n_hidden-1)+1. */
+int osteo_ddpm_num_weight_tensors(int n_hidden);
+
+const char* osteo_last_error(void);
+int osteo_version(void);
+/* Number of CUDA devices visible (0 when none; never fails). */
+int osteo_device_count(void);
+
+/* ---- model context: replaces BiologyAwareDiffusionModel.__init__ (models/diffusion.py:264-310)
+ * data_dim = mutation_dim + expression_dim + pathway_dim; cond_dim = condition_dim;
+ * time_dim = config.model.latent_dim; cond_embed_dim = 64 (models/diffusion.py:285);
+ * hidden_dims = config.model.hidden_dims (each a multiple of 128, <= 1024); num_steps = T. */
+int osteo_ddpm_create(osteo_ddpm_ctx** out, int device, int data_dim, int cond_dim, int time_dim,
+                      int cond_embed_dim, int n_hidden, const int* hidden_dims, int num_steps,
+                      float dropout_p, int precision);
+int osteo_ddpm_destroy(osteo_ddpm_ctx* ctx);
+
+/* Make room for `rows` patients in the workspace (grows only; synchronises the device). */
+int osteo_ddpm_reserve(osteo_ddpm_ctx* ctx, long long rows);
+long long osteo_ddpm_capacity(const osteo_ddpm_ctx* ctx);
+/* Bytes of device memory the context owns. */
+long long osteo_ddpm_workspace_bytes(const osteo_ddpm_ctx* ctx);
+/* Rows per internal pass (activations of one pass stay L2-resident). 0 = all rows at once. */
+int osteo_ddpm_set_chunk_rows(osteo_ddpm_ctx* ctx, int chunk_rows);
+int osteo_ddpm_set_precision(osteo_ddpm_ctx* ctx, int precision);
+
+/* ---- parameters: replaces nn.Module.load_state_dict / optimizer updates.
+ * `weights_dev[i]` are fp32 device tensors in state_dict order (SURVEY.md §8a layer table):
+ *   condition_embed.mlp.0.{weight,bias}, condition_embed.mlp.2.{weight,bias},
+ *   unet.input_proj.{weight,bias}, unet.cond_proj.{weight,bias}, unet.time_proj.{weight,bias},
+ *   for each block in encoder.0.., bottleneck, decoder.0..: {0.weight,0.bias,1.weight,1.bias,
+ *   4.weight,4.bias,5.weight,5.bias}, unet.output_proj.{weight,bias}.
+ * Repacks to bf16 [hi|lo], K padded to 64, rows padded to 128, and rebuilds the 1000x256
+ * time_proj table (models/diffusion.py:222-223 hoisted out of the loop). */
+int osteo_ddpm_set_weights(osteo_ddpm_ctx* ctx, const float* const* weights_dev, int n_tensors, void* stream);
+
+/* Schedule tables, all fp32 [num_steps] on the HOST (models/diffusion.py:299-310, :401-423):
+ * sqrt_ab / sqrt_1mab are the registered buffers; coef_x / coef_eps / sigma are the collapsed
+ * reverse-step coefficients derived from those buffers in fp64 by the host mirror. */
+int osteo_ddpm_set_schedule(osteo_ddpm_ctx* ctx, const float* sqrt_ab, const float* sqrt_1mab,
+                            const float* coef_x, const float* coef_eps, const float* sigma);
+/* Sinusoidal embedding table fp32 [num_steps, time_dim] on the HOST: TimeEmbedding.forward
+ * (models/diffusion.py:124-139) evaluated at t/num_steps for every integer t. */
+int osteo_ddpm_set_time_embedding(osteo_ddpm_ctx* ctx, const float* emb_host);
+
+/* ---- state I/O */
+/* x_dev [n, data_dim] fp32 -> internal padded fp32 state + bf16 shadow. */
+int osteo_ddpm_load_state(osteo_ddpm_ctx* ctx, const float* x_dev, long long n, void* stream);
+/* internal state -> out_dev [n, data_dim] fp32. */
+int osteo_ddpm_store_state(osteo_ddpm_ctx* ctx, float* out_dev, long long n, void* stream);
+/* x_T ~ N(0, I) from Philox4x32-10(seed; row_base + row, column): models/diffusion.py:443. */
+int osteo_ddpm_init_noise(osteo_ddpm_ctx* ctx, long long n, uint64_t seed, long long row_base, void* stream);
+/* ConditionalEmbedding + cond_proj hoisted out of the step loop (models/diffusion.py:107-114,
+ * :226, :395): cond_dev [n, cond_dim] fp32. */
+int osteo_ddpm_set_conditions(osteo_ddpm_ctx* ctx, const float* cond_dev, long long n, void* stream);
+
+/* ---- reverse process: replaces p_sample (models/diffusion.py:382-425) and the loop of sample (:446-447).
+ * One step at integer timestep t on the internal state. noise_dev: optional injected z [n, data_dim]
+ * (parity runs); NULL = in-kernel Philox keyed by (seed, row_base + row, t, column).
+ * eps_out_dev: optional fp32 [n, data_dim] copy of the predicted noise. */
+int osteo_ddpm_reverse_step(osteo_ddpm_ctx* ctx, long long n, int t, const float* noise_dev,
+                            float* eps_out_dev, uint64_t seed, long long row_base, void* stream);
+/* Steps t_start, t_start-1, ..., t_end (inclusive) with in-kernel noise; one CUDA graph per step shape,
+ * replayed. noise_dev: optional injected z for ALL steps, [t_start - t_end + 1, n, data_dim] in loop order
+ * (the z of step t == 0 is never read). */
+int osteo_ddpm_sample_loop(osteo_ddpm_ctx* ctx, long long n, int t_start, int t_end, const float* noise_dev,
+                           uint64_t seed, long long row_base, int use_graph, void* stream);
+
+/* ---- denoiser forward: replaces DiffusionUNet.forward via BiologyAwareDiffusionModel.forward(
+ * return_loss=False) (models/diffusion.py:210-256, :367-380) on caller data:
+ * xt_dev [n, data_dim] fp32, t_idx_dev [n] int32 (integer timesteps), conditions already set;
+ * eps_out_dev [n, data_dim] fp32. Eval mode (no dropout). */
+int osteo_ddpm_denoise(osteo_ddpm_ctx* ctx, const float* xt_dev, const int* t_idx_dev, long long n,
+                       float* eps_out_dev, void* stream);
+
+/* ---- forward process: replaces q_sample (models/diffusion.py:328-342).
+ * xt = sqrt_ab[t]*x0 + sqrt_1mab[t]*noise per row; noise_dev in/out: if gen_noise != 0 it is FILLED
+ * from Philox (stream QNOISE, step = `salt`) first. All [n, data_dim] fp32, t_idx_dev [n] int32. */
+int osteo_ddpm_q_sample(osteo_ddpm_ctx* ctx, const float* x0_dev, const int* t_idx_dev, float* noise_dev,
+                        float* xt_dev, long long n, int gen_noise, uint64_t seed, long long row_base,
+                        uint32_t salt, void* stream);
+
+/* ---- standalone elementwise reverse update (the epilogue of reverse_step as its own kernel):
+ * x <- coef_x[t]*x - coef_eps[t]*eps + sigma[t]*z, dense [n, data_dim] fp32 tensors. z_dev may be NULL
+ * (Philox). Replaces models/diffusion.py:400-423. */
+int osteo_ddpm_reverse_update(osteo_ddpm_ctx* ctx, float* x_dev, const float* eps_dev, const float* z_dev,
+                              long long n, int t, uint64_t seed, long long row_base, void* stream);
+
+/* ---- training step: replaces forward(return_loss=True) + loss.backward() (models/diffusion.py:344-378,
+ * utils/train.py:236-239).  x0_dev [n, data_dim], cond_dev [n, cond_dim] fp32.
+ * t_idx_dev / noise_dev / drop_masks_dev are optional injections (NULL = Philox streams keyed by seed).
+ * drop_masks_dev: array of n_blocks uint8 keep-masks [n, block_out_dim] (device pointers, host array).
+ * loss_dev: fp32 scalar on device. grads_dev: n_tensors fp32 device tensors shaped like the weights
+ * (overwritten, not accumulated); NULL = forward only. train != 0 enables dropout. */
+int osteo_ddpm_train_step(osteo_ddpm_ctx* ctx, const float* x0_dev, const float* cond_dev, long long n,
+                          const int* t_idx_dev, const float* noise_dev, const uint8_t* const* drop_masks_dev,
+                          int train, uint64_t seed, long long row_base, float* loss_dev,
+                          float* const* grads_dev, int n_tensors, void* stream);
+
+/* ---- diagnostics */
+/* Sticky kernel status word (0 = ok; see GemmError). Synchronises `stream`. */
+int osteo_ddpm_status(osteo_ddpm_ctx* ctx, void* stream);
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+long long osteo_ddpm_launch_count(const osteo_ddpm_ctx* ctx);
+
+/* ---- building blocks exposed for unit tests / the validators (context-free) */
+/* out[m, n] = a[m, :k] . w[n, :k] + bias[n]  on tcgen05; a, w fp32 device tensors (converted to bf16,
+ * or split-bf16 when precision = FP32X3). out fp32 [m, n]. */
+int osteo_linear_tc(const float* a_dev, const float* w_dev, const float* bias_dev, float* out_dev,
+                    int m, int n, int k, int precision, void* stream);
+/* Same contraction followed by GroupNorm(8) + affine + SiLU (n multiple of 128, n/8 in {16,32,64}). */
+int osteo_linear_gn_silu_tc(const float* a_dev, const float* w_dev, const float* bias_dev,
+                            const float* gamma_dev, const float* beta_dev, float* out_dev,
+                            int m, int n, int k, int precision, void* stream);
+/* Fill out[n, d] fp32 with Philox normals (stream id, step) — test hook for the RNG. */
+int osteo_philox_normal(float* out_dev, long long n, int d, uint64_t seed, long long row_base,
+                        uint32_t stream_id, uint32_t step, void* stream);
+/* Raw Philox words: out[n, 4*ncol4] uint32. */
+int osteo_philox_words(uint32_t* out_dev, long long n, int ncol4, uint64_t seed, long long row_base,
+                       uint32_t stream_id, uint32_t step, void* stream);
+
+/* ---- validators
+ * RBF-MMD partial sums: replaces the three cdist Grams of BiologicalValidator.compute_mmd
+ * (utils/validation.py:284-296).  x_dev [n, d], y_dev [m, d] fp32 device; this call handles Gram ROWS
+ * [row_begin, row_end) of K(X,X) and K(X,Y) and rows [yrow_begin, yrow_end) of K(Y,Y) (row sharding
+ * across GPUs) and writes sums_dev[3] = {sum Kxx, sum Kyy, sum Kxy} (fp64, device,
+ * overwritten).  Operands are centred by `center_dev` [d] (RBF is translation invariant). */
+int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long long m, int d, float gamma,
+                      const float* center_dev, long long row_begin, long long row_end,
+                      long long yrow_begin, long long yrow_end, int precision, double* sums_dev, void* stream);
+/* Column-gathered moment blocks for Pearson correlations: replaces DataFrame.corr / Series.corr
+ * (utils/validation.py:152,156,206).  data_dev [n, ld] fp32; cols_dev [k] int32 column indices (k <= 32);
+ * shift_dev [k] per-column shift (e.g. a first-row estimate; improves conditioning);
+ * out_dev fp64 [1 + k + k*k] = {count, sum (x-s), sum (x-s)(x-s)^T} over rows [row_begin,row_end),
+ * overwritten. */
+int osteo_corr_moments(const float* data_dev, long long n, int ld, const int* cols_dev, int k,
+                       const float* shift_dev, long long row_begin, long long row_end,
+                       double* out_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OSTEO_DDPM_H */

@@ -1,0 +1,59 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting,
+// TMA tensor-map construction (driver entry point fetched through the runtime,
+// so the library does not link against libcuda) and launch bookkeeping.
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace osteo {
+
+std::string& last_error_ref();
+int fail(const char* fmt, ...);
+
+#define OSTEO_CUDA(expr)                                                                              \
+    do {                                                                                              \
+        cudaError_t _e = (expr);                                                                      \
+        if (_e != cudaSuccess) return ::osteo::fail("%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define OSTEO_TRY(expr)            \
+    do {                           \
+        int _r = (expr);           \
+        if (_r != 0) return _r;    \
+    } while (0)
+
+inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+// bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns,
+// 128-byte swizzle (matches make_kmajor_sw128_desc). Out-of-bounds elements read as zero.
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
+int sm_count(int device);
+
+// Device buffer owned by the context.
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n) {
+        release();
+        if (n == 0) return 0;
+        OSTEO_CUDA(cudaMalloc(&p, n));
+        bytes = n;
+        return 0;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    ~DevBuf() { release(); }
+    template <class T>
+    T* as() const { return static_cast<T*>(p); }
+};
+
+
+}  // namespace osteo

@@ -1,0 +1,261 @@
+// Bandwidth-bound kernels around the GEMMs: operand repacking, state I/O, x_T fill,
+// q_sample, the standalone reverse update, the hoisted condition / time paths.
+// All are 128-bit vectorised along the feature axis; rows are independent.
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+#include "philox.cuh"
+
+namespace osteo {
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16r(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+// fp32 [rows, cols] (ld = src_ld) -> bf16 [dst_rows, dst_ld]: hi at column c, residual at c + lo_off
+// (lo_off = 0 skips the residual), zero padded. One thread per 4 destination columns of the hi half.
+__global__ void pack_bf16_hilo_kernel(const float* __restrict__ src, long long rows, int cols, long long src_ld,
+                                      __nv_bfloat16* __restrict__ dst, long long dst_rows, int kp, long long dst_ld, int lo_off) {
+    const long long total = dst_rows * (kp / 4);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / (kp / 4);
+        const int c = static_cast<int>(i % (kp / 4)) * 4;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (r < rows && c + j < cols) ? src[r * src_ld + c + j] : 0.0f;
+        uint2 hi = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+        *reinterpret_cast<uint2*>(dst + r * dst_ld + c) = hi;
+        if (lo_off > 0) {
+            uint2 lo = make_uint2(pack2(v[0] - bf16r(v[0]), v[1] - bf16r(v[1])), pack2(v[2] - bf16r(v[2]), v[3] - bf16r(v[3])));
+            *reinterpret_cast<uint2*>(dst + r * dst_ld + lo_off + c) = lo;
+        }
+    }
+}
+
+// Same, but the source is read transposed: dst[r, c] = src[c, r] (src is [cols, rows] with ld src_ld).
+// Used for the dgrad operand W^T. Tiled through shared memory so both sides are coalesced.
+__global__ void pack_bf16_hilo_transposed_kernel(const float* __restrict__ src, int rows, int cols, long long src_ld,
+                                                 __nv_bfloat16* __restrict__ dst, int dst_rows, int kp, long long dst_ld, int lo_off) {
+    __shared__ float tile[32][33];
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;   // src element (c, r)
+        tile[j][threadIdx.x] = (c < cols && r < rows) ? src[static_cast<long long>(c) * src_ld + r] : 0.0f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < dst_rows && c < kp) {
+            const float v = tile[threadIdx.x][j];
+            dst[static_cast<long long>(r) * dst_ld + c] = __float2bfloat16_rn(v);
+            if (lo_off > 0) dst[static_cast<long long>(r) * dst_ld + lo_off + c] = __float2bfloat16_rn(v - bf16r(v));
+        }
+    }
+}
+
+// Caller x [n, d] -> padded fp32 state [n, x_ld] + bf16 shadow [n, xb_ld] (hi | lo). One thread per 4 columns.
+__global__ void load_state_kernel(const float* __restrict__ src, long long n, int d, float* __restrict__ x, int x_ld,
+                                  __nv_bfloat16* __restrict__ xb, int xb_ld, int lo_off) {
+    const int q = x_ld / 4;
+    const long long total = n * q;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / q;
+        const int c = static_cast<int>(i % q) * 4;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (c + j < d) ? src[r * d + c + j] : 0.0f;
+        if (x) *reinterpret_cast<float4*>(x + r * x_ld + c) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint2*>(xb + r * xb_ld + c) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
+        if (lo_off > 0)
+            *reinterpret_cast<uint2*>(xb + r * xb_ld + lo_off + c) =
+                make_uint2(pack2(v[0] - bf16r(v[0]), v[1] - bf16r(v[1])), pack2(v[2] - bf16r(v[2]), v[3] - bf16r(v[3])));
+    }
+}
+
+__global__ void store_state_kernel(const float* __restrict__ x, int x_ld, float* __restrict__ dst, long long n, int d) {
+    const long long total = n * d;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / d;
+        const int c = static_cast<int>(i % d);
+        dst[i] = x[r * x_ld + c];
+    }
+}
+
+// x_T ~ N(0, I): models/diffusion.py:443. One Philox call per 4 columns.
+__global__ void init_noise_kernel(float* __restrict__ x, int x_ld, __nv_bfloat16* __restrict__ xb, int xb_ld, int lo_off, long long n, int d,
+                                  unsigned long long seed, long long row_base, uint32_t stream_id, uint32_t step) {
+    const int q = x_ld / 4;
+    const long long total = n * q;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / q;
+        const int c4 = static_cast<int>(i % q);
+        const int c = c4 * 4;
+        float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < d) {
+            z = philox_normal4(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), stream_id, step);
+            if (c + 1 >= d) z.y = 0.f;
+            if (c + 2 >= d) z.z = 0.f;
+            if (c + 3 >= d) z.w = 0.f;
+        }
+        *reinterpret_cast<float4*>(x + r * x_ld + c) = z;
+        if (xb) {
+            *reinterpret_cast<uint2*>(xb + r * xb_ld + c) = make_uint2(pack2(z.x, z.y), pack2(z.z, z.w));
+            if (lo_off > 0)
+                *reinterpret_cast<uint2*>(xb + r * xb_ld + lo_off + c) =
+                    make_uint2(pack2(z.x - bf16r(z.x), z.y - bf16r(z.y)), pack2(z.z - bf16r(z.z), z.w - bf16r(z.w)));
+        }
+    }
+}
+
+// Dense test hooks for the RNG.
+__global__ void philox_normal_kernel(float* __restrict__ out, long long n, int d, unsigned long long seed, long long row_base, uint32_t stream_id, uint32_t step) {
+    const int q = (d + 3) / 4;
+    const long long total = n * q;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / q;
+        const int c4 = static_cast<int>(i % q);
+        const float4 z = philox_normal4(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), stream_id, step);
+        const float zz[4] = {z.x, z.y, z.z, z.w};
+        for (int j = 0; j < 4; ++j)
+            if (c4 * 4 + j < d) out[r * d + c4 * 4 + j] = zz[j];
+    }
+}
+__global__ void philox_words_kernel(uint32_t* __restrict__ out, long long n, int ncol4, unsigned long long seed, long long row_base, uint32_t stream_id, uint32_t step) {
+    const long long total = n * ncol4;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / ncol4;
+        const int c4 = static_cast<int>(i % ncol4);
+        const uint4 w = philox_words(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), stream_id, step);
+        reinterpret_cast<uint4*>(out)[i] = w;
+    }
+}
+
+// q_sample (models/diffusion.py:337-340): xt = sqrt_ab[t_r]*x0 + sqrt_1mab[t_r]*noise, dense [n, d] tensors.
+// GEN: fill `noise` from Philox first (models/diffusion.py:335).
+template <bool GEN>
+__global__ void q_sample_kernel(const float* __restrict__ x0, const int* __restrict__ t_idx, float* __restrict__ noise, float* __restrict__ xt,
+                                long long n, int d, const float* __restrict__ sqrt_ab, const float* __restrict__ sqrt_1mab,
+                                unsigned long long seed, long long row_base, uint32_t salt) {
+    const int q = (d + 3) / 4;
+    const long long total = n * q;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / q;
+        const int c4 = static_cast<int>(i % q);
+        const int t = t_idx[r];
+        const float a = __ldg(sqrt_ab + t), b = __ldg(sqrt_1mab + t);
+        float z[4];
+        if (GEN) {
+            const float4 zz = philox_normal4(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), STREAM_QNOISE, salt);
+            z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c4 * 4 + j;
+            if (c < d) {
+                const long long o = r * d + c;
+                if (GEN) noise[o] = z[j]; else z[j] = noise[o];
+                xt[o] = a * x0[o] + b * z[j];
+            }
+        }
+    }
+}
+
+// Standalone reverse update on dense [n, d] tensors (models/diffusion.py:400-423 collapsed).
+__global__ void reverse_update_kernel(float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ z, long long n, int d,
+                                      float cx, float ce, float sg, unsigned long long seed, long long row_base, uint32_t t) {
+    const int q = (d + 3) / 4;
+    const long long total = n * q;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / q;
+        const int c4 = static_cast<int>(i % q);
+        float zz[4] = {0.f, 0.f, 0.f, 0.f};
+        if (sg != 0.0f && !z) {
+            const float4 g = philox_normal4(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), STREAM_REVERSE, t);
+            zz[0] = g.x; zz[1] = g.y; zz[2] = g.z; zz[3] = g.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c4 * 4 + j;
+            if (c < d) {
+                const long long o = r * d + c;
+                const float zv = (sg != 0.0f && z) ? z[o] : zz[j];
+                x[o] = fmaf(sg, zv, fmaf(cx, x[o], -ce * eps[o]));
+            }
+        }
+    }
+}
+
+// time_proj(time_embed(t / T)) for every integer t (models/diffusion.py:222-223): table[t, n] = emb[t, :] . W[n, :] + b[n].
+__global__ void time_table_kernel(const float* __restrict__ emb, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ table, int T, int td, int h0) {
+    const int t = blockIdx.x;
+    extern __shared__ float e[];
+    for (int k = threadIdx.x; k < td; k += blockDim.x) e[k] = emb[static_cast<long long>(t) * td + k];
+    __syncthreads();
+    for (int n = threadIdx.x; n < h0; n += blockDim.x) {
+        float acc = 0.0f;
+        const float* wr = w + static_cast<long long>(n) * td;
+        for (int k = 0; k < td; ++k) acc = fmaf(e[k], wr[k], acc);
+        table[static_cast<long long>(t) * h0 + n] = acc + b[n];
+    }
+}
+
+// ConditionalEmbedding (Linear C->E, SiLU, Linear E->E; models/diffusion.py:101-114) followed by
+// cond_proj (Linear E->h0; :226). fp32 on CUDA cores: runs once per sample() call. One block = 8 rows.
+// Optionally keeps the intermediate activations for the training backward.
+__global__ void cond_path_kernel(const float* __restrict__ cond, long long n, int C, int E, int h0,
+                                 const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2, const float* __restrict__ b2,
+                                 const float* __restrict__ wc, const float* __restrict__ bc, float* __restrict__ cproj,
+                                 float* __restrict__ save_pre0, float* __restrict__ save_emb) {
+    constexpr int R = 8;
+    extern __shared__ float sm[];
+    float* s_c = sm;                 // [R, C]
+    float* s_h = s_c + R * C;        // [R, E]
+    float* s_e = s_h + R * E;        // [R, E]
+    const long long r0 = static_cast<long long>(blockIdx.x) * R;
+    for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
+        const long long r = r0 + i / C;
+        s_c[i] = r < n ? cond[r * C + i % C] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * E; i += blockDim.x) {
+        const int rr = i / E, j = i % E;
+        float a = b0[j];
+        for (int k = 0; k < C; ++k) a = fmaf(s_c[rr * C + k], w0[j * C + k], a);
+        if (save_pre0 && r0 + rr < n) save_pre0[(r0 + rr) * E + j] = a;
+        s_h[i] = a / (1.0f + expf(-a));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * E; i += blockDim.x) {
+        const int rr = i / E, j = i % E;
+        float a = b2[j];
+        for (int k = 0; k < E; ++k) a = fmaf(s_h[rr * E + k], w2[j * E + k], a);
+        if (save_emb && r0 + rr < n) save_emb[(r0 + rr) * E + j] = a;
+        s_e[i] = a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * h0; i += blockDim.x) {
+        const int rr = i / h0, j = i % h0;
+        if (r0 + rr >= n) continue;
+        float a = bc[j];
+        for (int k = 0; k < E; ++k) a = fmaf(s_e[rr * E + k], wc[j * E + k], a);
+        cproj[(r0 + rr) * h0 + j] = a;
+    }
+}
+
+// bf16 [hi | lo] pair -> fp32 (hi + lo). Test helper for the GroupNorm epilogue.
+__global__ void unpack_hilo_kernel(const __nv_bfloat16* __restrict__ src, long long ld, int lo_off, float* __restrict__ dst, long long m, int n) {
+    const long long total = m * n;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / n;
+        const int c = static_cast<int>(i % n);
+        dst[i] = __bfloat162float(src[r * ld + c]) + __bfloat162float(src[r * ld + lo_off + c]);
+    }
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+__global__ void add_int_kernel(int* p, int v) { *p += v; }
+__global__ void finish_loss_kernel(const double* acc, float* out, double scale) { *out = static_cast<float>(*acc * scale); }
+
+}  // namespace osteo

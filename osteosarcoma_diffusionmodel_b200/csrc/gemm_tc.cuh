@@ -1,0 +1,564 @@
+// Persistent, warp-specialised tcgen05 GEMM for the denoiser's Linear layers
+// (reference: models/diffusion.py:198-208 blocks, :229-232 input_proj + embeddings,
+// :250 skip concat, :254 output_proj) with the layer's tail fused as the epilogue.
+//
+//   acc[m, n] = sum over K-segments s of  A_s[m, a_col_s : a_col_s + 64*nkb_s] . W[n, b_col_s : ...]
+//
+// A K-segment list expresses (i) the decoder's cat([h, skip]) as two segments
+// accumulated into one TMEM accumulator and (ii) the split-bf16 "fp32x3" mode
+// (hi*hi + hi*lo + lo*hi) as three segments over [hi | lo] operand buffers.
+//
+// Roles (384 threads, 1 CTA / SM, grid = min(#tiles, #SMs), static round-robin tiles):
+//   warp 0      TMA producer     A tile 128x64 bf16 + W tile 128x64 bf16 per k-block, 6-stage ring
+//   warp 1      MMA issuer       tcgen05.mma cta_group::1 kind::f16, M=128 N=128 K=16, fp32 accum in TMEM
+//   warp 2      TMEM allocator   512 columns = 4 accumulator stages of 128 columns
+//   warps 4-11  epilogue         thread <-> one accumulator row (TMEM lane), 64 columns per tile
+// Row-per-thread is what makes GroupNorm(8) a purely in-register reduction.
+#pragma once
+#include <cuda_bf16.h>
+#include "ptx.cuh"
+#include "philox.cuh"
+
+namespace osteo {
+
+constexpr int BM = 128;
+constexpr int BN = 128;
+constexpr int BK = 64;
+constexpr int STAGES = 6;
+constexpr int NUM_ACC = 4;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+constexpr int B_TILE_BYTES = BN * BK * 2;
+constexpr int GEMM_SMEM_BYTES = STAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int MAX_KSEG = 8;
+
+enum EpiKind : int {
+    EPI_LINEAR = 0,   // bias + table-row add + matrix add -> bf16 [hi|lo] and/or fp32
+    EPI_GN_SILU = 1,  // bias + GroupNorm(8) + affine + SiLU (+dropout) -> bf16 [hi|lo]
+    EPI_DDPM = 2,     // eps = acc + bias; x <- c_x*x - c_eps*eps + sigma*z ; xb <- bf16(x)
+    EPI_MSE = 3,      // eps = acc + bias; loss += sum (eps - noise)^2 ; grad <- scale*(eps - noise)
+    EPI_RBF = 4       // sum over tile of exp(-gamma*(na[m] + nb[n] - 2 acc))
+};
+
+enum GemmError : int { ERR_NONE = 0, ERR_PRODUCER_TIMEOUT = 1, ERR_MMA_TIMEOUT = 2, ERR_EPI_TIMEOUT = 3 };
+
+struct KSeg {
+    int a_sel;   // which A tensor map (0 / 1)
+    int a_col;   // first K column in A
+    int b_col;   // first K column in W
+    int nkb;     // number of 64-wide k-blocks
+};
+
+struct GemmParams {
+    CUtensorMap tma_a[2];
+    CUtensorMap tma_b;
+    int M, N;                 // valid rows / valid output columns
+    int m_tiles, n_tiles;     // tiles this launch covers: m blocks [m_tile0, m_tile0 + m_tiles)
+    int m_tile0;
+    int nseg;
+    KSeg seg[MAX_KSEG];
+    int* status;              // sticky error word (device)
+    long long row_base;       // global row index of row 0 (RNG keying under row sharding)
+
+    const float* bias;        // [N] or nullptr
+    // EPI_LINEAR
+    const float* add_tab;     // [rows, add_tab_ld] table; row = add_idx ? add_idx[m] : (step ? *step : 0)
+    const int* add_idx;
+    int add_tab_ld;
+    const float* add_mat;     // [M, add_mat_ld] or nullptr
+    int add_mat_ld;
+    float* out_f32;           // optional
+    int out_f32_ld;
+    __nv_bfloat16* out_bf;    // optional; hi at col, lo at col + out_lo_off when out_lo_off > 0
+    int out_bf_ld;
+    int out_lo_off;
+    // EPI_GN_SILU
+    const float* gamma;
+    const float* beta;
+    float gn_eps;
+    float drop_p;             // 0 = no dropout
+    const uint8_t* drop_mask; // optional injected keep-mask [M, N] (parity tests)
+    uint32_t drop_stream;
+    __nv_bfloat16* xhat_bf;   // optional: normalised pre-affine activations saved for backward
+    float* rstd_out;          // optional: [M, 8]
+    // EPI_DDPM / shared
+    const int* step;          // device-resident timestep (graph replay keeps the launch constant)
+    const float* coef_x;      // [T]
+    const float* coef_eps;    // [T]
+    const float* coef_sigma;  // [T]
+    float* x;                 // [M, x_ld] fp32 master state, updated in place
+    int x_ld;
+    __nv_bfloat16* xb;        // bf16 shadow [hi|lo] of x: next step's input_proj operand
+    int xb_ld;
+    int xb_lo_off;
+    const float* noise;       // injected z [M, noise_ld] (parity) or nullptr (Philox)
+    int noise_ld;
+    float* eps_out;           // optional fp32 eps [M, eps_ld]
+    int eps_ld;
+    unsigned long long seed;
+    // EPI_MSE
+    const float* target;      // noise [M, target_ld]
+    int target_ld;
+    float grad_scale;
+    double* loss_acc;
+    // EPI_RBF
+    const float* norm_a;      // [M]
+    const float* norm_b;      // [N]
+    float rbf_gamma;
+    int rbf_symmetric;        // 1: only tiles with n_blk >= m_blk, off-diagonal weighted 2x
+    double* rbf_acc;
+};
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
+
+// Store 32 consecutive values of this thread's row as bf16 (and the bf16 residual at +lo_off).
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float (&v)[32], int lo_off) {
+    uint4* d = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint4 w;
+        w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+        w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+        w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+        w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+        d[j] = w;
+    }
+    if (lo_off > 0) {
+        uint4* dl = reinterpret_cast<uint4*>(dst + lo_off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float r[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) r[i] = v[8 * j + i] - bf16_round(v[8 * j + i]);
+            uint4 w;
+            w.x = pack_bf16x2(r[0], r[1]);
+            w.y = pack_bf16x2(r[2], r[3]);
+            w.z = pack_bf16x2(r[4], r[5]);
+            w.w = pack_bf16x2(r[6], r[7]);
+            dl[j] = w;
+        }
+    }
+}
+
+__device__ __forceinline__ float silu_f(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
+
+// One epilogue pass over 32 columns [col, col+32) of row `row` held in v[].
+// GW = GroupNorm group width (16 / 32 / 64); a 64-wide group is handled by the caller
+// passing precomputed statistics (mean / rstd over both halves).
+template <int EPI>
+struct Epilogue;
+
+template <int EPI, int GW>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES));
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + NUM_ACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + NUM_ACC);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tma_a[0]);
+        tma_prefetch_desc(&p.tma_a[1]);
+        tma_prefetch_desc(&p.tma_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < NUM_ACC; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], NUM_EPI_WARPS);
+        }
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int num_tiles = p.m_tiles * p.n_tiles;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+                const int m_blk = p.m_tile0 + tile / p.n_tiles, n_blk = tile % p.n_tiles;
+                if (EPI == EPI_RBF && p.rbf_symmetric && n_blk < m_blk) continue;
+                for (int s = 0; s < p.nseg && ok; ++s) {
+                    const KSeg sg = p.seg[s];
+                    const CUtensorMap* ta = &p.tma_a[sg.a_sel];
+                    for (int kb = 0; kb < sg.nkb; ++kb) {
+                        if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; break; }
+                        mbar_arrive_expect_tx(&full_bar[stage], A_TILE_BYTES + B_TILE_BYTES);
+                        tma_load_2d(ta, smem_a + stage * A_TILE_BYTES, &full_bar[stage], sg.a_col + kb * BK, m_blk * BM);
+                        tma_load_2d(&p.tma_b, smem_b + stage * B_TILE_BYTES, &full_bar[stage], sg.b_col + kb * BK, n_blk * BN);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+            if (!ok) atomicExch(p.status, ERR_PRODUCER_TIMEOUT);
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            bool ok = true;
+            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+                if (EPI == EPI_RBF && p.rbf_symmetric && (tile % p.n_tiles) < (p.m_tile0 + tile / p.n_tiles)) continue;
+                const int acc = it % NUM_ACC;
+                const uint32_t acc_phase = static_cast<uint32_t>(it / NUM_ACC) & 1u;
+                ++it;
+                if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u)) { ok = false; break; }
+                tc_fence_after_sync();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+                uint32_t accumulate = 0;
+                for (int s = 0; s < p.nseg && ok; ++s) {
+                    const int nkb = p.seg[s].nkb;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (!mbar_wait(&full_bar[stage], phase)) { ok = false; break; }
+                        tc_fence_after_sync();
+                        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem_a + stage * A_TILE_BYTES));
+                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem_b + stage * B_TILE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // +32 B per UMMA_K step inside the 128-byte swizzle row (start-address field is >>4)
+                            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    }
+                }
+                if (ok) umma_commit(&tfull_bar[acc]);
+            }
+            if (!ok) atomicExch(p.status, ERR_MMA_TIMEOUT);
+        }
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue
+        const int q = warp & 3;                 // TMEM lane quadrant this warp may access
+        const int half = (warp - 4) >> 2;       // which 64-column half of the tile
+        int it = 0;
+        bool ok = true;
+        double thread_acc = 0.0;                // EPI_MSE / EPI_RBF partial sums
+        for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
+            const int m_blk = p.m_tile0 + tile / p.n_tiles, n_blk = tile % p.n_tiles;
+            if (EPI == EPI_RBF && p.rbf_symmetric && n_blk < m_blk) continue;
+            const int acc = it % NUM_ACC;
+            const uint32_t acc_phase = static_cast<uint32_t>(it / NUM_ACC) & 1u;
+            ++it;
+            if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
+            tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 64);
+            float v0[32], v1[32];
+            tmem_ld_32(taddr, v0);
+            tmem_ld_32(taddr + 32, v1);
+            // accumulator is in registers: hand the TMEM stage back to the MMA warp
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+
+            const int row = m_blk * BM + q * 32 + lane;
+            const int col = n_blk * BN + half * 64;
+            Epilogue<EPI>::template run<GW>(p, row, col, v0, v1, thread_acc);
+        }
+        if (EPI == EPI_MSE || EPI == EPI_RBF) {
+            // warp reduce then one atomic per warp
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) thread_acc += __shfl_xor_sync(0xffffffffu, thread_acc, o);
+            if (lane == 0 && thread_acc != 0.0) atomicAdd(EPI == EPI_MSE ? p.loss_acc : p.rbf_acc, thread_acc);
+        }
+        if (!ok && lane == 0) atomicExch(p.status, ERR_EPI_TIMEOUT);
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------ epilogues
+template <>
+struct Epilogue<EPI_LINEAR> {
+    template <int GW>
+    __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double&) {
+        if (row >= p.M) return;
+        const float* tab = nullptr;
+        if (p.add_tab) {
+            const int r = p.add_idx ? p.add_idx[row] : (p.step ? *p.step : 0);
+            tab = p.add_tab + static_cast<size_t>(r) * p.add_tab_ld;
+        }
+        const float* mat = p.add_mat ? p.add_mat + static_cast<size_t>(row) * p.add_mat_ld : nullptr;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float(&v)[32] = h ? v1 : v0;
+            const int c0 = col + 32 * h;
+            if (c0 >= p.N) break;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;
+                if (c < p.N) {
+                    float a = v[j];
+                    if (p.bias) a += __ldg(p.bias + c);
+                    if (tab) a += __ldg(tab + c);
+                    if (mat) a += __ldg(mat + c);
+                    v[j] = a;
+                } else {
+                    v[j] = 0.0f;
+                }
+            }
+            if (p.out_f32) {
+                float* o = p.out_f32 + static_cast<size_t>(row) * p.out_f32_ld + c0;
+                if (c0 + 32 <= p.N && (p.out_f32_ld & 3) == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(o)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c0 + j < p.N) o[j] = v[j];
+                }
+            }
+            if (p.out_bf) store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
+        }
+    }
+};
+
+template <>
+struct Epilogue<EPI_GN_SILU> {
+    // GroupNorm(8, N) -> group width GW = N / 8. Biased variance, eps inside the sqrt
+    // (torch.nn.GroupNorm, models/diffusion.py:202,206), then SiLU (:203,207) and the
+    // block's Dropout (:204) when drop_p > 0.
+    template <int GW>
+    __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double&) {
+        if (row >= p.M) return;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            v0[j] += __ldg(p.bias + col + j);
+            v1[j] += __ldg(p.bias + col + 32 + j);
+        }
+        float mean[64 / GW], rstd[64 / GW];
+        constexpr int NG = 64 / GW;   // groups inside this thread's 64 columns
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < GW; ++j) {
+                const int idx = g * GW + j;
+                s += (idx < 32) ? v0[idx & 31] : v1[idx & 31];
+            }
+            const float mu = s * (1.0f / GW);
+            float ss = 0.0f;
+#pragma unroll
+            for (int j = 0; j < GW; ++j) {
+                const int idx = g * GW + j;
+                const float d = ((idx < 32) ? v0[idx & 31] : v1[idx & 31]) - mu;
+                ss = fmaf(d, d, ss);
+            }
+            mean[g] = mu;
+            rstd[g] = rsqrtf(ss * (1.0f / GW) + p.gn_eps);
+        }
+        if (p.rstd_out) {
+            const int g0 = col / GW;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) p.rstd_out[static_cast<size_t>(row) * 8 + g0 + g] = rstd[g];
+        }
+        const float keep_scale = p.drop_p > 0.0f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float(&v)[32] = h ? v1 : v0;
+            const int c0 = col + 32 * h;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int g = (32 * h + j) / GW;
+                v[j] = (v[j] - mean[g]) * rstd[g];
+            }
+            if (p.xhat_bf) store_row32_bf16(p.xhat_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float y = fmaf(v[j], __ldg(p.gamma + c0 + j), __ldg(p.beta + c0 + j));
+                v[j] = silu_f(y);
+            }
+            if (p.drop_p > 0.0f) {
+                if (p.drop_mask) {
+                    const uint8_t* mk = p.drop_mask + static_cast<size_t>(row) * p.N + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = mk[j] ? v[j] * keep_scale : 0.0f;
+                } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const uint4 w = philox_words(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>((c0 >> 2) + j4), p.drop_stream, p.step ? static_cast<uint32_t>(*p.step) : 0u);
+                        v[4 * j4 + 0] = (u01(w.x) >= p.drop_p) ? v[4 * j4 + 0] * keep_scale : 0.0f;
+                        v[4 * j4 + 1] = (u01(w.y) >= p.drop_p) ? v[4 * j4 + 1] * keep_scale : 0.0f;
+                        v[4 * j4 + 2] = (u01(w.z) >= p.drop_p) ? v[4 * j4 + 2] * keep_scale : 0.0f;
+                        v[4 * j4 + 3] = (u01(w.w) >= p.drop_p) ? v[4 * j4 + 3] * keep_scale : 0.0f;
+                    }
+                }
+            }
+            store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
+        }
+    }
+};
+
+template <>
+struct Epilogue<EPI_DDPM> {
+    // Reverse step (models/diffusion.py:400-423) collapsed to
+    //   x <- c_x[t]*x - c_eps[t]*eps + sigma[t]*z ,  sigma[0] = 0 (the t == 0 branch returns x0_pred)
+    // with the three fp32 tables derived in fp64 from the reference's fp32 buffers.
+    template <int GW>
+    __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double&) {
+        if (row >= p.M) return;
+        const int t = *p.step;
+        const float cx = __ldg(p.coef_x + t), ce = __ldg(p.coef_eps + t), sg = __ldg(p.coef_sigma + t);
+        float* xrow = p.x + static_cast<size_t>(row) * p.x_ld;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float(&v)[32] = h ? v1 : v0;
+            const int c0 = col + 32 * h;
+            if (c0 >= p.N) break;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const int c = c0 + 4 * j4;
+                if (c >= p.N) break;
+                float e[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) e[i] = (c + i < p.N) ? v[4 * j4 + i] + __ldg(p.bias + c + i) : 0.0f;
+                if (p.eps_out) {
+                    float* eo = p.eps_out + static_cast<size_t>(row) * p.eps_ld + c;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        if (c + i < p.N) eo[i] = e[i];
+                }
+                const float4 xv = *reinterpret_cast<const float4*>(xrow + c);
+                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (sg != 0.0f) {
+                    if (p.noise) {
+                        const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c;
+                        z.x = nz[0];
+                        if (c + 1 < p.N) z.y = nz[1];
+                        if (c + 2 < p.N) z.z = nz[2];
+                        if (c + 3 < p.N) z.w = nz[3];
+                    } else {
+                        z = philox_normal4(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c >> 2), STREAM_REVERSE, static_cast<uint32_t>(t));
+                    }
+                }
+                float4 xn;
+                xn.x = fmaf(sg, z.x, fmaf(cx, xv.x, -ce * e[0]));
+                xn.y = (c + 1 < p.N) ? fmaf(sg, z.y, fmaf(cx, xv.y, -ce * e[1])) : 0.0f;
+                xn.z = (c + 2 < p.N) ? fmaf(sg, z.z, fmaf(cx, xv.z, -ce * e[2])) : 0.0f;
+                xn.w = (c + 3 < p.N) ? fmaf(sg, z.w, fmaf(cx, xv.w, -ce * e[3])) : 0.0f;
+                *reinterpret_cast<float4*>(xrow + c) = xn;
+                v[4 * j4 + 0] = xn.x;
+                v[4 * j4 + 1] = xn.y;
+                v[4 * j4 + 2] = xn.z;
+                v[4 * j4 + 3] = xn.w;
+            }
+            if (p.xb) {
+                // bf16 shadow, 8 elements (16 B) at a time; xb_ld >= round_up(N, 8)
+                __nv_bfloat16* xbrow = p.xb + static_cast<size_t>(row) * p.xb_ld + c0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (c0 + 8 * j >= p.N) break;
+                    float w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = (c0 + 8 * j + i < p.N) ? v[8 * j + i] : 0.0f;
+                    uint4 u;
+                    u.x = pack_bf16x2(w[0], w[1]);
+                    u.y = pack_bf16x2(w[2], w[3]);
+                    u.z = pack_bf16x2(w[4], w[5]);
+                    u.w = pack_bf16x2(w[6], w[7]);
+                    reinterpret_cast<uint4*>(xbrow)[j] = u;
+                    if (p.xb_lo_off > 0) {
+                        uint4 l;
+                        l.x = pack_bf16x2(w[0] - bf16_round(w[0]), w[1] - bf16_round(w[1]));
+                        l.y = pack_bf16x2(w[2] - bf16_round(w[2]), w[3] - bf16_round(w[3]));
+                        l.z = pack_bf16x2(w[4] - bf16_round(w[4]), w[5] - bf16_round(w[5]));
+                        l.w = pack_bf16x2(w[6] - bf16_round(w[6]), w[7] - bf16_round(w[7]));
+                        reinterpret_cast<uint4*>(xbrow + p.xb_lo_off)[j] = l;
+                    }
+                }
+            }
+        }
+    }
+};
+
+template <>
+struct Epilogue<EPI_MSE> {
+    // Training loss (models/diffusion.py:377): mean((eps_hat - noise)^2) over B*D; the epilogue
+    // accumulates the sum in fp64 and emits d(loss)/d(eps_hat) = grad_scale * (eps_hat - noise).
+    template <int GW>
+    __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double& acc) {
+        if (row >= p.M) return;
+        const float* trow = p.target + static_cast<size_t>(row) * p.target_ld;
+        float local = 0.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float(&v)[32] = h ? v1 : v0;
+            const int c0 = col + 32 * h;
+            if (c0 >= p.N) break;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;
+                float d = 0.0f;
+                if (c < p.N) {
+                    const float e = v[j] + __ldg(p.bias + c);
+                    if (p.eps_out) p.eps_out[static_cast<size_t>(row) * p.eps_ld + c] = e;
+                    d = e - trow[c];
+                    local = fmaf(d, d, local);
+                }
+                v[j] = d * p.grad_scale;
+            }
+            if (p.out_bf) store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
+        }
+        acc += static_cast<double>(local);
+    }
+};
+
+template <>
+struct Epilogue<EPI_RBF> {
+    // RBF Gram tile reduction (utils/validation.py:288-294): sum exp(-gamma * ||a - b||^2) with
+    // ||a - b||^2 = |a|^2 + |b|^2 - 2 a.b clamped at 0 (cdist never returns negatives).
+    template <int GW>
+    __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double& acc) {
+        if (row >= p.M) return;
+        const float na = p.norm_a[row];
+        const float ng = -p.rbf_gamma * 1.4426950408889634f;   // exp(x) = exp2(x * log2 e)
+        float local = 0.0f;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float(&v)[32] = h ? v1 : v0;
+            const int c0 = col + 32 * h;
+            if (c0 >= p.N) break;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const int c = c0 + j;
+                if (c < p.N) {
+                    const float d2 = fmaxf(na + __ldg(p.norm_b + c) - 2.0f * v[j], 0.0f);
+                    local += exp2f(ng * d2);
+                }
+            }
+        }
+        float w = 1.0f;
+        if (p.rbf_symmetric && (col / BN) != (row / BM)) w = 2.0f;
+        acc += static_cast<double>(local * w);
+    }
+};
+
+}  // namespace osteo

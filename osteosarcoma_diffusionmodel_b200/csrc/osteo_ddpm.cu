@@ -1,0 +1,793 @@
+// C-ABI of the B200-native DDPM hot path (see include/osteo_ddpm.h).
+// Context = repacked weights + workspace + prebuilt TMA descriptors; every compute entry
+// point enqueues hand-written sm_100a kernels on the caller's stream. No CPU fallback.
+#include <cstring>
+#include <memory>
+#include <vector>
+#include "../../include/osteo_ddpm.h"
+#include "common.cuh"
+#include "elem_kernels.cuh"
+#include "gemm_host.cuh"
+#include "train_kernels.cuh"
+#include "validators.cuh"
+
+namespace osteo {
+
+// ------------------------------------------------------------------ common.cuh impl
+std::string& last_error_ref() {
+    static thread_local std::string s;
+    return s;
+}
+int fail(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return -1;
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) return fail("tensor map operand not 16-byte aligned");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(BK), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu cols=%llu ld=%llu)", static_cast<int>(r),
+                                       static_cast<unsigned long long>(rows), static_cast<unsigned long long>(cols), static_cast<unsigned long long>(ld));
+    return 0;
+}
+
+int sm_count(int device) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
+    return n;
+}
+
+static inline int grid_for(long long work_items, int threads, int sms) {
+    long long g = (work_items + threads - 1) / threads;
+    const long long cap = static_cast<long long>(sms) * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return static_cast<int>(g);
+}
+
+// One Linear layer repacked for the tensor cores: W bf16 [np, 2*kp] = [hi | lo], zero padded.
+struct PackedLinear {
+    int n = 0, k = 0, np = 0, kp = 0;
+    DevBuf w, bias;     // bias fp32 [np]
+    DevBuf wt;          // W^T bf16 [kp128, 2*np] for dgrad (training only)
+    int ktp = 0;        // rows of wt (k rounded to 128)
+    CUtensorMap tmap, tmap_t;
+    int init(int n_, int k_) {
+        n = n_; k = k_;
+        np = static_cast<int>(round_up(n, BN));
+        kp = static_cast<int>(round_up(k, BK));
+        OSTEO_TRY(w.alloc(static_cast<size_t>(np) * 2 * kp * 2));
+        OSTEO_TRY(bias.alloc(static_cast<size_t>(np) * 4));
+        OSTEO_TRY(make_tmap_bf16(&tmap, w.p, np, 2 * kp, 2 * kp, BN));
+        return 0;
+    }
+    int init_transposed() {
+        ktp = static_cast<int>(round_up(k, BN));
+        OSTEO_TRY(wt.alloc(static_cast<size_t>(ktp) * 2 * np * 2));
+        OSTEO_TRY(make_tmap_bf16(&tmap_t, wt.p, ktp, 2 * np, 2 * np, BN));
+        return 0;
+    }
+    int upload(const float* w_dev, const float* b_dev, int sms, cudaStream_t s) {
+        const long long items = static_cast<long long>(np) * (kp / 4);
+        pack_bf16_hilo_kernel<<<grid_for(items, 256, sms), 256, 0, s>>>(w_dev, n, k, k, w.as<__nv_bfloat16>(), np, kp, 2LL * kp, kp);
+        OSTEO_CUDA(cudaGetLastError());
+        OSTEO_CUDA(cudaMemsetAsync(bias.p, 0, static_cast<size_t>(np) * 4, s));
+        OSTEO_CUDA(cudaMemcpyAsync(bias.p, b_dev, static_cast<size_t>(n) * 4, cudaMemcpyDeviceToDevice, s));
+        if (wt.p) {
+            dim3 grid((np + 31) / 32, (ktp + 31) / 32), block(32, 8);
+            // wt[r = k index, c = n index] = W[c, r]
+            pack_bf16_hilo_transposed_kernel<<<grid, block, 0, s>>>(w_dev, k, n, k, wt.as<__nv_bfloat16>(), ktp, np, 2LL * np, np);
+            OSTEO_CUDA(cudaGetLastError());
+        }
+        return 0;
+    }
+};
+
+// Activation buffer bf16 [cap, 2*width] = [hi | lo] with its A-operand tensor map.
+struct ActBuf {
+    int width = 0;
+    DevBuf buf;
+    CUtensorMap tmap;
+    int init(long long cap, int width_) {
+        width = width_;
+        OSTEO_TRY(buf.alloc(static_cast<size_t>(cap) * 2 * width * 2));
+        OSTEO_TRY(make_tmap_bf16(&tmap, buf.p, cap, 2 * width, 2 * width, BM));
+        return 0;
+    }
+    __nv_bfloat16* ptr() const { return buf.as<__nv_bfloat16>(); }
+};
+
+struct HalfBlock {
+    PackedLinear lin;
+    DevBuf gamma, beta;   // fp32 [n]
+    int gw = 0;
+    int src0 = -1, src1 = -1;   // activation indices feeding this Linear (src1 = concatenated skip)
+    int dst = -1;               // activation index written
+    bool dropout = false;       // first half of a block carries the Dropout
+    int block = 0;
+};
+
+}  // namespace osteo
+
+using namespace osteo;
+
+struct osteo_ddpm_ctx {
+    int device = 0, sms = 0;
+    int D = 0, C = 0, TD = 0, E = 0, T = 0;
+    std::vector<int> hidden;
+    float drop_p = 0.f;
+    int precision = OSTEO_PREC_BF16;
+    int DP = 0;                 // padded feature pitch (multiple of 64)
+    long long cap = 0;
+    int chunk_rows = 32768;
+    long long launches = 0;
+
+    // parameters
+    DevBuf ce_w0, ce_b0, ce_w2, ce_b2, cp_w, cp_b, tp_w, tp_b;   // fp32 copies of the small layers
+    PackedLinear in_proj, out_proj;
+    std::vector<std::unique_ptr<HalfBlock>> halves;
+    DevBuf emb_table, time_table;        // [T, TD], [T, h0] fp32
+    DevBuf sqrt_ab, sqrt_1mab, coef_x, coef_eps, coef_sigma;   // [T] fp32
+    std::vector<float> h_coef_x, h_coef_eps, h_coef_sigma;
+    bool have_weights = false, have_schedule = false, have_emb = false;
+
+    // workspace (capacity `cap` rows)
+    DevBuf x;                            // fp32 [cap, DP]
+    ActBuf xb;                           // bf16 [cap, 2*DP]
+    std::vector<std::unique_ptr<ActBuf>> acts;   // [0] = h0, then one per half block
+    DevBuf cproj;                        // fp32 [cap, h0]
+    DevBuf step_dev, status_dev;
+    DevBuf loss_acc;                     // fp64 scalar
+    TrainWorkspace train;
+
+    // graph cache for sample_loop
+    cudaGraphExec_t graph_exec = nullptr;
+    long long graph_n = -1;
+    unsigned long long graph_seed = 0;
+    long long graph_row_base = 0;
+    int graph_precision = -1, graph_chunk = -1;
+    long long graph_launches_per_step = 0;
+
+    bool x3() const { return precision == OSTEO_PREC_FP32X3; }
+    int h0() const { return hidden[0]; }
+    int lo(int width) const { return x3() ? width : 0; }
+    ~osteo_ddpm_ctx() {
+        if (graph_exec) cudaGraphExecDestroy(graph_exec);
+    }
+};
+
+namespace osteo {
+
+static int check_ctx(const osteo_ddpm_ctx* c) {
+    if (!c) return fail("null context");
+    return 0;
+}
+
+static void base_params(const osteo_ddpm_ctx* c, GemmParams& p) {
+    std::memset(&p, 0, sizeof p);
+    p.status = c->status_dev.as<int>();
+    p.step = c->step_dev.as<int>();
+    p.gn_eps = 1e-5f;
+}
+
+static void set_rows(GemmParams& p, long long row0, long long row1) {
+    p.M = static_cast<int>(row1);
+    p.m_tile0 = static_cast<int>(row0 / BM);
+    p.m_tiles = static_cast<int>((row1 - row0 + BM - 1) / BM);
+}
+
+// input_proj + time/cond embedding add (models/diffusion.py:229-232) for rows [row0, row1).
+static int launch_input_proj(osteo_ddpm_ctx* c, long long row0, long long row1, const int* t_idx, cudaStream_t s) {
+    GemmParams p;
+    base_params(c, p);
+    p.tma_a[0] = c->xb.tmap;
+    p.tma_a[1] = c->xb.tmap;
+    p.tma_b = c->in_proj.tmap;
+    OSTEO_TRY(add_segments(p, 0, 0, c->DP, 0, c->in_proj.kp, c->DP, c->x3()));
+    set_rows(p, row0, row1);
+    p.N = c->h0();
+    p.n_tiles = c->in_proj.np / BN;
+    p.bias = c->in_proj.bias.as<float>();
+    p.add_tab = c->time_table.as<float>();
+    p.add_tab_ld = c->h0();
+    p.add_idx = t_idx;
+    p.add_mat = c->cproj.as<float>();
+    p.add_mat_ld = c->h0();
+    p.out_bf = c->acts[0]->ptr();
+    p.out_bf_ld = 2 * c->h0();
+    p.out_lo_off = c->lo(c->h0());
+    ++c->launches;
+    return launch_gemm(EPI_LINEAR, 64, p, c->sms, s);
+}
+
+struct HalfOpts {
+    bool train = false;
+    const uint8_t* drop_mask = nullptr;
+    unsigned long long seed = 0;
+    long long row_base = 0;
+    bool save = false;
+};
+
+// Linear + GroupNorm + SiLU (+Dropout) half block (models/diffusion.py:201-207; concat at :250).
+static int launch_half(osteo_ddpm_ctx* c, int hi, long long row0, long long row1, const HalfOpts& o, cudaStream_t s) {
+    HalfBlock& hb = *c->halves[hi];
+    GemmParams p;
+    base_params(c, p);
+    const ActBuf& a0 = *c->acts[hb.src0];
+    p.tma_a[0] = a0.tmap;
+    p.tma_a[1] = a0.tmap;
+    p.tma_b = hb.lin.tmap;
+    if (c->x3()) {
+        // keep the three passes of each source adjacent: hi*hi, hi*lo, lo*hi
+        OSTEO_TRY(add_segments(p, 0, 0, a0.width, 0, hb.lin.kp, a0.width, true));
+        if (hb.src1 >= 0) {
+            const ActBuf& a1 = *c->acts[hb.src1];
+            p.tma_a[1] = a1.tmap;
+            OSTEO_TRY(add_segments(p, 1, 0, a1.width, a0.width, hb.lin.kp, a1.width, true));
+        }
+    } else {
+        OSTEO_TRY(add_segments(p, 0, 0, 0, 0, 0, a0.width, false));
+        if (hb.src1 >= 0) {
+            const ActBuf& a1 = *c->acts[hb.src1];
+            p.tma_a[1] = a1.tmap;
+            OSTEO_TRY(add_segments(p, 1, 0, 0, a0.width, 0, a1.width, false));
+        }
+    }
+    set_rows(p, row0, row1);
+    p.N = hb.lin.n;
+    p.n_tiles = hb.lin.np / BN;
+    p.bias = hb.lin.bias.as<float>();
+    p.gamma = hb.gamma.as<float>();
+    p.beta = hb.beta.as<float>();
+    ActBuf& dst = *c->acts[hb.dst];
+    p.out_bf = dst.ptr();
+    p.out_bf_ld = 2 * dst.width;
+    p.out_lo_off = c->lo(dst.width);
+    if (o.train && hb.dropout && c->drop_p > 0.f) {
+        p.drop_p = c->drop_p;
+        p.drop_mask = o.drop_mask;
+        p.drop_stream = STREAM_DROPOUT + static_cast<uint32_t>(hb.block);
+        p.seed = o.seed;
+        p.row_base = o.row_base;
+        p.step = nullptr;
+    }
+    if (o.save) {
+        p.xhat_bf = c->train.xhat[hi]->as<__nv_bfloat16>();
+        p.rstd_out = c->train.rstd[hi]->as<float>();
+    }
+    ++c->launches;
+    return launch_gemm(EPI_GN_SILU, hb.gw, p, c->sms, s);
+}
+
+static void out_proj_common(osteo_ddpm_ctx* c, GemmParams& p, long long row0, long long row1) {
+    base_params(c, p);
+    const ActBuf& a = *c->acts.back();
+    p.tma_a[0] = a.tmap;
+    p.tma_a[1] = a.tmap;
+    p.tma_b = c->out_proj.tmap;
+    add_segments(p, 0, 0, a.width, 0, c->out_proj.kp, a.width, c->x3());
+    set_rows(p, row0, row1);
+    p.N = c->D;
+    p.n_tiles = c->out_proj.np / BN;
+    p.bias = c->out_proj.bias.as<float>();
+}
+
+// output_proj with the reverse update as its epilogue (models/diffusion.py:254, :400-423).
+static int launch_output_ddpm(osteo_ddpm_ctx* c, long long row0, long long row1, const float* noise, float* eps_out,
+                              unsigned long long seed, long long row_base, cudaStream_t s) {
+    GemmParams p;
+    out_proj_common(c, p, row0, row1);
+    p.coef_x = c->coef_x.as<float>();
+    p.coef_eps = c->coef_eps.as<float>();
+    p.coef_sigma = c->coef_sigma.as<float>();
+    p.x = c->x.as<float>();
+    p.x_ld = c->DP;
+    p.xb = c->xb.ptr();
+    p.xb_ld = 2 * c->DP;
+    p.xb_lo_off = c->lo(c->DP);
+    p.noise = noise;
+    p.noise_ld = c->D;
+    p.eps_out = eps_out;
+    p.eps_ld = c->D;
+    p.seed = seed;
+    p.row_base = row_base;
+    ++c->launches;
+    return launch_gemm(EPI_DDPM, 64, p, c->sms, s);
+}
+
+// output_proj writing eps as a dense fp32 tensor (forward(return_loss=False)).
+static int launch_output_eps(osteo_ddpm_ctx* c, long long row0, long long row1, float* eps_out, cudaStream_t s) {
+    GemmParams p;
+    out_proj_common(c, p, row0, row1);
+    p.out_f32 = eps_out;
+    p.out_f32_ld = c->D;
+    ++c->launches;
+    return launch_gemm(EPI_LINEAR, 64, p, c->sms, s);
+}
+
+static long long chunk_of(const osteo_ddpm_ctx* c, long long n) {
+    long long ch = c->chunk_rows > 0 ? c->chunk_rows : n;
+    ch = round_up(ch, BM);
+    return ch < 1 ? BM : ch;
+}
+
+// Enqueue one full reverse step over rows [0, n); the timestep is read from the device word.
+static int enqueue_reverse_step(osteo_ddpm_ctx* c, long long n, const float* noise, float* eps_out, unsigned long long seed, long long row_base, cudaStream_t s) {
+    const long long ch = chunk_of(c, n);
+    HalfOpts o;
+    for (long long r0 = 0; r0 < n; r0 += ch) {
+        const long long r1 = r0 + ch < n ? r0 + ch : n;
+        OSTEO_TRY(launch_input_proj(c, r0, r1, nullptr, s));
+        for (size_t i = 0; i < c->halves.size(); ++i) OSTEO_TRY(launch_half(c, static_cast<int>(i), r0, r1, o, s));
+        OSTEO_TRY(launch_output_ddpm(c, r0, r1, noise, eps_out, seed, row_base, s));
+    }
+    return 0;
+}
+
+static int require_ready(const osteo_ddpm_ctx* c, long long n) {
+    if (!c->have_weights) return fail("weights not set (osteo_ddpm_set_weights)");
+    if (!c->have_schedule) return fail("schedule not set (osteo_ddpm_set_schedule)");
+    if (!c->have_emb) return fail("time embedding not set (osteo_ddpm_set_time_embedding)");
+    if (n <= 0) return fail("row count must be positive");
+    if (n > c->cap) return fail("%lld rows exceed the reserved capacity %lld (osteo_ddpm_reserve)", n, c->cap);
+    return 0;
+}
+
+static int rebuild_time_table(osteo_ddpm_ctx* c, cudaStream_t s) {
+    if (!c->have_weights || !c->have_emb) return 0;
+    time_table_kernel<<<c->T, 256, c->TD * sizeof(float), s>>>(c->emb_table.as<float>(), c->tp_w.as<float>(), c->tp_b.as<float>(),
+                                                                c->time_table.as<float>(), c->T, c->TD, c->h0());
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+}  // namespace osteo
+
+// ====================================================================== C-ABI
+extern "C" {
+
+const char* osteo_last_error(void) { return last_error_ref().c_str(); }
+int osteo_version(void) { return 100; }
+int osteo_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int osteo_ddpm_num_weight_tensors(int n_hidden) { return 4 + 8 + 8 * (2 * (n_hidden - 1) + 1); }
+
+int osteo_ddpm_create(osteo_ddpm_ctx** out, int device, int data_dim, int cond_dim, int time_dim, int cond_embed_dim, int n_hidden,
+                      const int* hidden_dims, int num_steps, float dropout_p, int precision) {
+    if (!out) return fail("null output pointer");
+    *out = nullptr;
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (data_dim <= 0 || cond_dim <= 0 || time_dim <= 0 || cond_embed_dim <= 0 || num_steps <= 0 || num_steps > 65535) return fail("invalid dimensions");
+    if (n_hidden < 2) return fail("hidden_dims needs at least 2 entries (models/diffusion.py:171-193)");
+    for (int i = 0; i < n_hidden; ++i)
+        if (hidden_dims[i] % 128 != 0 || hidden_dims[i] > 512 || hidden_dims[i] < 128)
+            return fail("hidden dim %d unsupported: the tcgen05 path needs multiples of 128 in [128, 512]", hidden_dims[i]);
+    if (time_dim % 2 != 0) return fail("time_dim must be even");
+    if (dropout_p < 0.f || dropout_p >= 1.f) return fail("dropout must be in [0, 1)");
+    OSTEO_CUDA(cudaSetDevice(device));
+    std::unique_ptr<osteo_ddpm_ctx> c(new osteo_ddpm_ctx);
+    c->device = device;
+    c->sms = sm_count(device);
+    if (c->sms <= 0) return fail("cannot query SM count");
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10) return fail("device compute capability %d.x: kernels are built for sm_100a only", major);
+    c->D = data_dim; c->C = cond_dim; c->TD = time_dim; c->E = cond_embed_dim; c->T = num_steps;
+    c->hidden.assign(hidden_dims, hidden_dims + n_hidden);
+    c->drop_p = dropout_p;
+    c->precision = precision;
+    c->DP = static_cast<int>(round_up(data_dim, BK));
+    const int h0 = c->h0();
+
+    OSTEO_TRY(c->ce_w0.alloc(sizeof(float) * c->E * c->C));
+    OSTEO_TRY(c->ce_b0.alloc(sizeof(float) * c->E));
+    OSTEO_TRY(c->ce_w2.alloc(sizeof(float) * c->E * c->E));
+    OSTEO_TRY(c->ce_b2.alloc(sizeof(float) * c->E));
+    OSTEO_TRY(c->cp_w.alloc(sizeof(float) * h0 * c->E));
+    OSTEO_TRY(c->cp_b.alloc(sizeof(float) * h0));
+    OSTEO_TRY(c->tp_w.alloc(sizeof(float) * h0 * c->TD));
+    OSTEO_TRY(c->tp_b.alloc(sizeof(float) * h0));
+    OSTEO_TRY(c->emb_table.alloc(sizeof(float) * c->T * c->TD));
+    OSTEO_TRY(c->time_table.alloc(sizeof(float) * c->T * h0));
+    for (DevBuf* b : {&c->sqrt_ab, &c->sqrt_1mab, &c->coef_x, &c->coef_eps, &c->coef_sigma}) OSTEO_TRY(b->alloc(sizeof(float) * c->T));
+    OSTEO_TRY(c->step_dev.alloc(sizeof(int)));
+    OSTEO_TRY(c->status_dev.alloc(sizeof(int)));
+    OSTEO_TRY(c->loss_acc.alloc(sizeof(double)));
+    OSTEO_CUDA(cudaMemset(c->step_dev.p, 0, sizeof(int)));
+    OSTEO_CUDA(cudaMemset(c->status_dev.p, 0, sizeof(int)));
+
+    OSTEO_TRY(c->in_proj.init(h0, data_dim));
+    OSTEO_TRY(c->out_proj.init(data_dim, h0));
+
+    // Block structure of DiffusionUNet.__init__ (models/diffusion.py:171-193). Activation 0 = h0.
+    int act_count = 1;
+    int block_id = 0;
+    auto add_block = [&](int in0_act, int in0_dim, int in1_act, int in1_dim, int out_dim) -> int {
+        for (int half = 0; half < 2; ++half) {
+            std::unique_ptr<HalfBlock> hb(new HalfBlock);
+            const int k = half == 0 ? in0_dim + in1_dim : out_dim;
+            OSTEO_TRY(hb->lin.init(out_dim, k));
+            OSTEO_TRY(hb->gamma.alloc(sizeof(float) * out_dim));
+            OSTEO_TRY(hb->beta.alloc(sizeof(float) * out_dim));
+            hb->gw = out_dim / 8;
+            hb->src0 = half == 0 ? in0_act : act_count - 1;
+            hb->src1 = half == 0 ? in1_act : -1;
+            hb->dst = act_count++;
+            hb->dropout = half == 0;
+            hb->block = block_id;
+            c->halves.push_back(std::move(hb));
+        }
+        ++block_id;
+        return 0;
+    };
+    std::vector<int> skip_act;
+    int cur_act = 0, cur_dim = h0;
+    for (int i = 1; i < n_hidden; ++i) {
+        OSTEO_TRY(add_block(cur_act, cur_dim, -1, 0, c->hidden[i]));
+        cur_act = act_count - 1;
+        cur_dim = c->hidden[i];
+        skip_act.push_back(cur_act);
+    }
+    OSTEO_TRY(add_block(cur_act, cur_dim, -1, 0, cur_dim));
+    cur_act = act_count - 1;
+    for (int i = n_hidden - 2; i >= 0; --i) {
+        const int sk = skip_act.back();
+        skip_act.pop_back();
+        const int skip_dim = c->hidden[i + 1];
+        OSTEO_TRY(add_block(cur_act, cur_dim, sk, skip_dim, c->hidden[i]));
+        cur_act = act_count - 1;
+        cur_dim = c->hidden[i];
+    }
+    if (cur_dim != h0) return fail("internal: decoder does not end at hidden_dims[0]");
+    *out = c.release();
+    return 0;
+}
+
+int osteo_ddpm_destroy(osteo_ddpm_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    delete ctx;
+    return 0;
+}
+
+long long osteo_ddpm_capacity(const osteo_ddpm_ctx* ctx) { return ctx ? ctx->cap : 0; }
+long long osteo_ddpm_launch_count(const osteo_ddpm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+long long osteo_ddpm_workspace_bytes(const osteo_ddpm_ctx* c) {
+    if (!c) return 0;
+    size_t b = c->x.bytes + c->xb.buf.bytes + c->cproj.bytes + c->in_proj.w.bytes + c->out_proj.w.bytes;
+    for (auto& a : c->acts) b += a->buf.bytes;
+    for (auto& h : c->halves) b += h->lin.w.bytes + h->lin.wt.bytes;
+    b += c->train.bytes();
+    return static_cast<long long>(b);
+}
+
+int osteo_ddpm_set_chunk_rows(osteo_ddpm_ctx* c, int chunk_rows) {
+    OSTEO_TRY(check_ctx(c));
+    if (chunk_rows < 0) return fail("chunk_rows must be >= 0");
+    c->chunk_rows = chunk_rows;
+    return 0;
+}
+int osteo_ddpm_set_precision(osteo_ddpm_ctx* c, int precision) {
+    OSTEO_TRY(check_ctx(c));
+    if (precision != OSTEO_PREC_BF16 && precision != OSTEO_PREC_FP32X3) return fail("unknown precision %d", precision);
+    c->precision = precision;
+    return 0;
+}
+
+int osteo_ddpm_reserve(osteo_ddpm_ctx* c, long long rows) {
+    OSTEO_TRY(check_ctx(c));
+    if (rows <= c->cap) return 0;
+    OSTEO_CUDA(cudaSetDevice(c->device));
+    OSTEO_CUDA(cudaDeviceSynchronize());
+    if (c->graph_exec) {
+        cudaGraphExecDestroy(c->graph_exec);
+        c->graph_exec = nullptr;
+        c->graph_n = -1;
+    }
+    const long long cap = round_up(rows, BM);
+    OSTEO_TRY(c->x.alloc(static_cast<size_t>(cap) * c->DP * 4));
+    OSTEO_CUDA(cudaMemset(c->x.p, 0, c->x.bytes));
+    OSTEO_TRY(c->xb.init(cap, c->DP));
+    OSTEO_CUDA(cudaMemset(c->xb.buf.p, 0, c->xb.buf.bytes));
+    OSTEO_TRY(c->cproj.alloc(static_cast<size_t>(cap) * c->h0() * 4));
+    OSTEO_CUDA(cudaMemset(c->cproj.p, 0, c->cproj.bytes));
+    c->acts.clear();
+    {
+        std::unique_ptr<ActBuf> a(new ActBuf);
+        OSTEO_TRY(a->init(cap, c->h0()));
+        c->acts.push_back(std::move(a));
+    }
+    for (auto& hb : c->halves) {
+        std::unique_ptr<ActBuf> a(new ActBuf);
+        OSTEO_TRY(a->init(cap, hb->lin.n));
+        OSTEO_CUDA(cudaMemset(a->buf.p, 0, a->buf.bytes));
+        c->acts.push_back(std::move(a));
+    }
+    c->train.release();
+    c->cap = cap;
+    return 0;
+}
+
+int osteo_ddpm_set_weights(osteo_ddpm_ctx* c, const float* const* w, int n_tensors, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    const int expect = osteo_ddpm_num_weight_tensors(static_cast<int>(c->hidden.size()));
+    if (n_tensors != expect) return fail("expected %d weight tensors, got %d", expect, n_tensors);
+    for (int i = 0; i < n_tensors; ++i)
+        if (!w[i]) return fail("weight tensor %d is null", i);
+    OSTEO_CUDA(cudaSetDevice(c->device));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    auto copy = [&](DevBuf& dst, const float* src) -> int {
+        OSTEO_CUDA(cudaMemcpyAsync(dst.p, src, dst.bytes, cudaMemcpyDeviceToDevice, s));
+        return 0;
+    };
+    OSTEO_TRY(copy(c->ce_w0, w[0]));
+    OSTEO_TRY(copy(c->ce_b0, w[1]));
+    OSTEO_TRY(copy(c->ce_w2, w[2]));
+    OSTEO_TRY(copy(c->ce_b2, w[3]));
+    OSTEO_TRY(c->in_proj.upload(w[4], w[5], c->sms, s));
+    OSTEO_TRY(copy(c->cp_w, w[6]));
+    OSTEO_TRY(copy(c->cp_b, w[7]));
+    OSTEO_TRY(copy(c->tp_w, w[8]));
+    OSTEO_TRY(copy(c->tp_b, w[9]));
+    int idx = 10;
+    for (auto& hb : c->halves) {
+        OSTEO_TRY(hb->lin.upload(w[idx], w[idx + 1], c->sms, s));
+        OSTEO_TRY(copy(hb->gamma, w[idx + 2]));
+        OSTEO_TRY(copy(hb->beta, w[idx + 3]));
+        idx += 4;
+    }
+    OSTEO_TRY(c->out_proj.upload(w[idx], w[idx + 1], c->sms, s));
+    c->launches += 2 + static_cast<long long>(c->halves.size());
+    c->have_weights = true;
+    return rebuild_time_table(c, s);
+}
+
+int osteo_ddpm_set_schedule(osteo_ddpm_ctx* c, const float* sqrt_ab, const float* sqrt_1mab, const float* coef_x, const float* coef_eps, const float* sigma) {
+    OSTEO_TRY(check_ctx(c));
+    OSTEO_CUDA(cudaSetDevice(c->device));
+    const size_t b = sizeof(float) * c->T;
+    OSTEO_CUDA(cudaMemcpy(c->sqrt_ab.p, sqrt_ab, b, cudaMemcpyHostToDevice));
+    OSTEO_CUDA(cudaMemcpy(c->sqrt_1mab.p, sqrt_1mab, b, cudaMemcpyHostToDevice));
+    OSTEO_CUDA(cudaMemcpy(c->coef_x.p, coef_x, b, cudaMemcpyHostToDevice));
+    OSTEO_CUDA(cudaMemcpy(c->coef_eps.p, coef_eps, b, cudaMemcpyHostToDevice));
+    OSTEO_CUDA(cudaMemcpy(c->coef_sigma.p, sigma, b, cudaMemcpyHostToDevice));
+    c->h_coef_x.assign(coef_x, coef_x + c->T);
+    c->h_coef_eps.assign(coef_eps, coef_eps + c->T);
+    c->h_coef_sigma.assign(sigma, sigma + c->T);
+    c->have_schedule = true;
+    return 0;
+}
+
+int osteo_ddpm_set_time_embedding(osteo_ddpm_ctx* c, const float* emb_host) {
+    OSTEO_TRY(check_ctx(c));
+    OSTEO_CUDA(cudaSetDevice(c->device));
+    OSTEO_CUDA(cudaMemcpy(c->emb_table.p, emb_host, sizeof(float) * c->T * c->TD, cudaMemcpyHostToDevice));
+    c->have_emb = true;
+    OSTEO_TRY(rebuild_time_table(c, nullptr));
+    OSTEO_CUDA(cudaDeviceSynchronize());
+    return 0;
+}
+
+int osteo_ddpm_load_state(osteo_ddpm_ctx* c, const float* x_dev, long long n, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    if (n <= 0 || n > c->cap) return fail("load_state: %lld rows outside (0, capacity %lld]", n, c->cap);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long items = n * (c->DP / 4);
+    load_state_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(x_dev, n, c->D, c->x.as<float>(), c->DP, c->xb.ptr(), 2 * c->DP, c->lo(c->DP));
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+int osteo_ddpm_store_state(osteo_ddpm_ctx* c, float* out_dev, long long n, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    if (n <= 0 || n > c->cap) return fail("store_state: %lld rows outside (0, capacity %lld]", n, c->cap);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    store_state_kernel<<<grid_for(n * c->D, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->DP, out_dev, n, c->D);
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+int osteo_ddpm_init_noise(osteo_ddpm_ctx* c, long long n, uint64_t seed, long long row_base, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    if (n <= 0 || n > c->cap) return fail("init_noise: %lld rows outside (0, capacity %lld]", n, c->cap);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long items = n * (c->DP / 4);
+    init_noise_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->DP, c->xb.ptr(), 2 * c->DP, c->lo(c->DP), n, c->D, seed, row_base,
+                                                                  STREAM_XT, 0u);
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+int osteo_ddpm_set_conditions(osteo_ddpm_ctx* c, const float* cond_dev, long long n, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    if (!c->have_weights) return fail("weights not set");
+    if (n <= 0 || n > c->cap) return fail("set_conditions: %lld rows outside (0, capacity %lld]", n, c->cap);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const size_t smem = sizeof(float) * 8 * (c->C + 2 * c->E);
+    cond_path_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, s>>>(cond_dev, n, c->C, c->E, c->h0(), c->ce_w0.as<float>(), c->ce_b0.as<float>(),
+                                                                         c->ce_w2.as<float>(), c->ce_b2.as<float>(), c->cp_w.as<float>(), c->cp_b.as<float>(),
+                                                                         c->cproj.as<float>(), nullptr, nullptr);
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+int osteo_ddpm_reverse_step(osteo_ddpm_ctx* c, long long n, int t, const float* noise_dev, float* eps_out_dev, uint64_t seed, long long row_base, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    OSTEO_TRY(require_ready(c, n));
+    if (t < 0 || t >= c->T) return fail("timestep %d outside [0, %d)", t, c->T);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    set_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), t);
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return enqueue_reverse_step(c, n, noise_dev, eps_out_dev, seed, row_base, s);
+}
+
+int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_end, const float* noise_dev, uint64_t seed, long long row_base, int use_graph,
+                           void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    OSTEO_TRY(require_ready(c, n));
+    if (t_start >= c->T || t_end < 0 || t_end > t_start) return fail("bad step range [%d, %d]", t_start, t_end);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int steps = t_start - t_end + 1;
+    set_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), t_start);
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    if (noise_dev || !use_graph) {
+        for (int i = 0; i < steps; ++i) {
+            const float* nz = noise_dev ? noise_dev + static_cast<size_t>(i) * n * c->D : nullptr;
+            OSTEO_TRY(enqueue_reverse_step(c, n, nz, nullptr, seed, row_base, s));
+            add_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), -1);
+            OSTEO_CUDA(cudaGetLastError());
+            ++c->launches;
+        }
+        return 0;
+    }
+    // One step captured once, replayed `steps` times; the device-resident step word is the only thing that changes.
+    const bool reuse = c->graph_exec && c->graph_n == n && c->graph_seed == seed && c->graph_row_base == row_base &&
+                       c->graph_precision == c->precision && c->graph_chunk == c->chunk_rows;
+    const long long before = c->launches;
+    if (!reuse) {
+        if (c->graph_exec) {
+            cudaGraphExecDestroy(c->graph_exec);
+            c->graph_exec = nullptr;
+        }
+        cudaStream_t cs;
+        OSTEO_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        OSTEO_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_reverse_step(c, n, nullptr, nullptr, seed, row_base, cs);
+        if (rc == 0) {
+            add_int_kernel<<<1, 1, 0, cs>>>(c->step_dev.as<int>(), -1);
+            ++c->launches;
+        }
+        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+        cudaStreamDestroy(cs);
+        if (rc != 0) {
+            if (graph) cudaGraphDestroy(graph);
+            return rc;
+        }
+        if (ce != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
+        c->graph_n = n;
+        c->graph_seed = seed;
+        c->graph_row_base = row_base;
+        c->graph_precision = c->precision;
+        c->graph_chunk = c->chunk_rows;
+    }
+    if (!reuse) {
+        c->graph_launches_per_step = c->launches - before;
+        c->launches = before;   // capture enqueued nothing; the replays below are what runs
+    }
+    for (int i = 0; i < steps; ++i) OSTEO_CUDA(cudaGraphLaunch(c->graph_exec, s));
+    c->launches += c->graph_launches_per_step * steps;
+    return 0;
+}
+
+int osteo_ddpm_denoise(osteo_ddpm_ctx* c, const float* xt_dev, const int* t_idx_dev, long long n, float* eps_out_dev, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    OSTEO_TRY(require_ready(c, n));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long items = n * (c->DP / 4);
+    load_state_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(xt_dev, n, c->D, nullptr, c->DP, c->xb.ptr(), 2 * c->DP, c->lo(c->DP));
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    const long long ch = chunk_of(c, n);
+    HalfOpts o;
+    for (long long r0 = 0; r0 < n; r0 += ch) {
+        const long long r1 = r0 + ch < n ? r0 + ch : n;
+        OSTEO_TRY(launch_input_proj(c, r0, r1, t_idx_dev, s));
+        for (size_t i = 0; i < c->halves.size(); ++i) OSTEO_TRY(launch_half(c, static_cast<int>(i), r0, r1, o, s));
+        OSTEO_TRY(launch_output_eps(c, r0, r1, eps_out_dev, s));
+    }
+    return 0;
+}
+
+int osteo_ddpm_q_sample(osteo_ddpm_ctx* c, const float* x0_dev, const int* t_idx_dev, float* noise_dev, float* xt_dev, long long n, int gen_noise,
+                        uint64_t seed, long long row_base, uint32_t salt, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    if (!c->have_schedule) return fail("schedule not set");
+    if (n <= 0) return fail("row count must be positive");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long items = n * ((c->D + 3) / 4);
+    const int grid = grid_for(items, 256, c->sms);
+    if (gen_noise)
+        q_sample_kernel<true><<<grid, 256, 0, s>>>(x0_dev, t_idx_dev, noise_dev, xt_dev, n, c->D, c->sqrt_ab.as<float>(), c->sqrt_1mab.as<float>(), seed, row_base, salt);
+    else
+        q_sample_kernel<false><<<grid, 256, 0, s>>>(x0_dev, t_idx_dev, noise_dev, xt_dev, n, c->D, c->sqrt_ab.as<float>(), c->sqrt_1mab.as<float>(), seed, row_base, salt);
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+int osteo_ddpm_reverse_update(osteo_ddpm_ctx* c, float* x_dev, const float* eps_dev, const float* z_dev, long long n, int t, uint64_t seed, long long row_base,
+                              void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    if (!c->have_schedule) return fail("schedule not set");
+    if (t < 0 || t >= c->T) return fail("timestep %d outside [0, %d)", t, c->T);
+    if (n <= 0) return fail("row count must be positive");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long items = n * ((c->D + 3) / 4);
+    reverse_update_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(x_dev, eps_dev, z_dev, n, c->D, c->h_coef_x[t], c->h_coef_eps[t], c->h_coef_sigma[t], seed,
+                                                                      row_base, static_cast<uint32_t>(t));
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+int osteo_ddpm_status(osteo_ddpm_ctx* c, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    int h = 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OSTEO_CUDA(cudaMemcpyAsync(&h, c->status_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    OSTEO_CUDA(cudaStreamSynchronize(s));
+    if (h != 0) return fail("kernel pipeline reported error %d (1 = TMA producer, 2 = MMA issuer, 3 = epilogue wait timed out)", h);
+    return 0;
+}
+
+}  // extern "C"
+
+#include "api_train.inl"
+#include "api_ops.inl"

@@ -1,0 +1,60 @@
+// Counter-based RNG for the DDPM noise: Philox4x32-10 keyed by the sampling seed,
+// counter = (column/4, global_row_lo, global_row_hi, stream<<16 | step), so a
+// row's noise is independent of how rows are sharded over GPUs.
+// The numpy restatement lives in oracle/philox_oracle.py and is compared bit-exactly
+// (uint32 words) and within 2e-6 (Box-Muller normals) in tests/test_philox.py.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace osteo {
+
+enum PhiloxStream : uint32_t {
+    STREAM_REVERSE = 0,   // z in the reverse update (models/diffusion.py:409)
+    STREAM_XT = 1,        // x_T = randn (models/diffusion.py:443)
+    STREAM_QNOISE = 2,    // q_sample noise (models/diffusion.py:335)
+    STREAM_DROPOUT = 3,   // + block index: dropout masks (models/diffusion.py:204)
+    STREAM_TIMESTEP = 16  // randint t (models/diffusion.py:361)
+};
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
+        const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += W0;
+        k.y += W1;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint4 philox_words(uint64_t seed, uint64_t row, uint32_t col4, uint32_t stream, uint32_t step) {
+    const uint4 ctr = make_uint4(col4, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), (stream << 16) | (step & 0xFFFFu));
+    const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    return philox4x32_10(ctr, key);
+}
+
+// 24-bit uniform strictly inside (0,1): exactly representable in fp32.
+__device__ __forceinline__ float u01(uint32_t w) { return static_cast<float>(w >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f; }
+
+// Box-Muller on hardware approximations (lg2 / sqrt / sin / cos MUFU ops).
+__device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, float& z1) {
+    const float u1 = u01(w0), u2 = u01(w1);
+    const float r = __fsqrt_rn(-1.3862943611198906f * __log2f(u1));   // sqrt(-2 ln u1)
+    float s, c;
+    __sincosf(6.283185307179586f * u2, &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t row, uint32_t col4, uint32_t stream, uint32_t step) {
+    const uint4 w = philox_words(seed, row, col4, stream, step);
+    float4 z;
+    box_muller(w.x, w.y, z.x, z.y);
+    box_muller(w.z, w.w, z.z, z.w);
+    return z;
+}
+
+}  // namespace osteo
