@@ -1,0 +1,62 @@
+"""ORACLE — numpy restatement of the in-kernel counter RNG (csrc/philox.cuh); test infrastructure.
+
+Philox4x32-10 (Salmon et al., SC'11; same constants as Random123 / cuRAND) with
+counter = (col4, row_lo, row_hi, stream << 16 | step), key = (seed_lo, seed_hi).  The reference has
+no counterpart (it calls torch.randn, models/diffusion.py:335,409,443); this is pinned by the
+Random123 known-answer vectors in tests/test_philox.py.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+M0, M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
+W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
+MASK = np.uint64(0xFFFFFFFF)
+
+
+def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
+    """ctr [..., 4] uint32, key [..., 2] uint32 (broadcastable) -> [..., 4] uint32."""
+    c = [ctr[..., i].astype(np.uint64) for i in range(4)]
+    k0 = np.asarray(key[..., 0], dtype=np.uint32).copy()
+    k1 = np.asarray(key[..., 1], dtype=np.uint32).copy()
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = M0 * c[0]
+            p1 = M1 * c[2]
+            hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
+            hi1, lo1 = p1 >> np.uint64(32), p1 & MASK
+            c = [hi1 ^ c[1] ^ k0.astype(np.uint64), lo1, hi0 ^ c[3] ^ k1.astype(np.uint64), lo0]
+            k0 = (k0 + W0).astype(np.uint32)
+            k1 = (k1 + W1).astype(np.uint32)
+    return np.stack([x.astype(np.uint32) for x in c], axis=-1)
+
+
+def words(seed: int, rows: np.ndarray, ncol4: int, stream: int, step: int) -> np.ndarray:
+    """uint32 [len(rows), ncol4, 4] exactly as osteo_philox_words writes them."""
+    rows = np.asarray(rows, dtype=np.uint64)
+    n = rows.shape[0]
+    ctr = np.zeros((n, ncol4, 4), dtype=np.uint32)
+    ctr[..., 0] = np.arange(ncol4, dtype=np.uint32)[None, :]
+    ctr[..., 1] = (rows & MASK).astype(np.uint32)[:, None]
+    ctr[..., 2] = (rows >> np.uint64(32)).astype(np.uint32)[:, None]
+    ctr[..., 3] = np.uint32(((stream & 0xFFFF) << 16) | (step & 0xFFFF))
+    key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
+    return philox4x32_10(ctr, key)
+
+
+def u01(w: np.ndarray) -> np.ndarray:
+    """24-bit uniform in (0, 1), exact in fp32 (csrc/philox.cuh u01)."""
+    return ((w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24) + np.float32(2.0 ** -25)).astype(np.float32)
+
+
+def normals(seed: int, rows: np.ndarray, d: int, stream: int, step: int) -> np.ndarray:
+    """fp64-evaluated Box-Muller on the same words: float64 [len(rows), d]."""
+    ncol4 = (d + 3) // 4
+    w = words(seed, rows, ncol4, stream, step)
+    u = u01(w).astype(np.float64)
+    r0 = np.sqrt(-2.0 * np.log(u[..., 0]))
+    r1 = np.sqrt(-2.0 * np.log(u[..., 2]))
+    t0 = 2.0 * np.pi * u[..., 1]
+    t1 = 2.0 * np.pi * u[..., 3]
+    z = np.stack([r0 * np.cos(t0), r0 * np.sin(t0), r1 * np.cos(t1), r1 * np.sin(t1)], axis=-1)
+    return z.reshape(len(rows), ncol4 * 4)[:, :d]
