@@ -156,7 +156,8 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const int* __restr
             if (c < d) {
                 const long long o = r * d + c;
                 if (GEN) noise[o] = z[j]; else z[j] = noise[o];
-                xt[o] = a * x0[o] + b * z[j];
+                // two rounded products then a rounded add, as the reference's elementwise ops do (bit-exact)
+                xt[o] = __fadd_rn(__fmul_rn(a, x0[o]), __fmul_rn(b, z[j]));
             }
         }
     }

@@ -1,0 +1,60 @@
+"""Shared helpers for the parity tests: golden loading, model construction from oracle/synth.py."""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from oracle import ddpm_oracle as O
+from oracle import synth
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+
+CASES = {
+    "smoke": (synth.SMOKE_DIMS, (256, 512, 256), "cosine"),
+    "config": (synth.CONFIG_YAML_DIMS, (256, 512, 256), "cosine"),
+    "linear3": (dict(mutation_dim=20, expression_dim=90, pathway_dim=10, condition_dim=2), (128, 256), "linear"),
+}
+
+# Stated tolerances (norm-wise relative Frobenius error against the reference's fp32 output)
+TOL_FP32X3 = 1e-4      # north_star: "stated fp32 tolerance (rel 1e-4)"
+TOL_BF16 = 2e-2        # bf16 operands vs the fp32 reference (SURVEY.md §7 "State precision": weights alone cost 1.8e-3)
+
+
+def rel(a, b) -> float:
+    a = np.asarray(a.detach().cpu() if hasattr(a, "detach") else a, dtype=np.float64)
+    b = np.asarray(b.detach().cpu() if hasattr(b, "detach") else b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def load_case(name):
+    g = np.load(GOLDEN / f"ddpm_{name}.npz", allow_pickle=False)
+    dims, hidden, schedule = CASES[name]
+    D = dims["mutation_dim"] + dims["expression_dim"] + dims["pathway_dim"]
+    seed = int(g["seed"])
+    sd = synth.make_params(D, dims["condition_dim"], hidden, seed=seed)
+    batch = int(g["batch"])
+    x0, cond = synth.make_cohort(batch, dims["mutation_dim"], dims["expression_dim"], dims["pathway_dim"], dims["condition_dim"], seed=seed)
+    return dict(g=g, dims=dims, hidden=hidden, schedule=schedule, D=D, seed=seed, sd=sd, x0=x0, cond=cond, batch=batch, T=int(g["num_steps"]))
+
+
+def oracle_sd(case):
+    sd = dict(case["sd"])
+    sd.update(O.schedule_buffers(case["schedule"], case["T"]))
+    return sd
+
+
+def build_model(case, precision="fp32x3", device="cuda", dropout=0.2):
+    from osteosarcoma_diffusionmodel_b200.diffusion import BiologyAwareDiffusionModel
+
+    cfg = synth.model_config(hidden_dims=case["hidden"], schedule=case["schedule"], num_steps=case["T"], dropout=dropout)
+    d = case["dims"]
+    model = BiologyAwareDiffusionModel(d["mutation_dim"], d["expression_dim"], d["pathway_dim"], d["condition_dim"], cfg)
+    res = model.load_state_dict(case["sd"], strict=False)
+    assert not res.unexpected_keys
+    assert set(res.missing_keys) <= {"betas", "alphas_cumprod", "sqrt_alphas_cumprod", "sqrt_one_minus_alphas_cumprod"}
+    model = model.to(device)
+    model.set_precision(precision)
+    model.eval()
+    return model
