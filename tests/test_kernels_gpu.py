@@ -76,7 +76,10 @@ def test_philox_normals_match_oracle_and_moments(lib):
     out = torch.zeros(n, d, device="cuda")
     _lib.check(lib.osteo_philox_normal(out.data_ptr(), n, d, seed, 7, 0, 123, None))
     ref = P.normals(seed, np.arange(n, dtype=np.uint64) + np.uint64(7), d, 0, 123)
-    assert np.abs(out.cpu().numpy().astype(np.float64) - ref).max() < 5e-6     # MUFU lg2 / sin / cos approximations
+    # Stated tolerance 2e-4 absolute on N(0,1) draws: the MUFU lg2 has ~2^-22 ABSOLUTE error, i.e. a relative error in
+    # -ln(u1) that grows as u1 -> 1 (tiny radii); measured worst case 7e-5, typical 1e-7.
+    err = np.abs(out.cpu().numpy().astype(np.float64) - ref)
+    assert err.max() < 2e-4 and np.median(err) < 5e-7
     big = torch.zeros(4096, 2048, device="cuda")
     _lib.check(lib.osteo_philox_normal(big.data_ptr(), 4096, 2048, 1, 0, 1, 0, None))
     assert abs(big.mean().item()) < 2e-3 and abs(big.var().item() - 1.0) < 3e-3
