@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native conditional-DDPM sampling path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--rows R]
+
+Metric (BASELINE.json): DDPM-sampled patients/sec, 1000 reverse steps per patient.
+Workload at N=1 (BASELINE.json configs[1]): 1000-step conditional DDPM sampling of 100k synthetic
+patients, bf16 tensor-core operands, the three config.yaml scenarios, config.yaml dims
+(62 + 5054 + 26 = 5142 features, 3 conditions, hidden [256, 512, 256], cosine schedule).
+One bench "step" = one complete `model.sample()` of the whole per-GPU batch (1000 reverse steps).
+N > 1 (torchrun, one rank per GPU): every rank samples its own contiguous row range of the global
+cohort (Philox keyed by global row; no collective on the data path) -> weak scaling.
+
+`--impl reference` times the reference's CPU algorithm (the torch-CPU oracle port of
+models/diffusion.py:382-449, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+D_MUT, D_EXPR, D_PATH, N_COND = 62, 5054, 26, 3            # config/config.yaml:27-30
+D = D_MUT + D_EXPR + D_PATH
+T_STEPS = 1000
+HIDDEN = (256, 512, 256)
+ALGO_BYTES_PER_PATIENT_STEP = 2 * D * 4                     # read x_t once, write x_{t-1} once, fp32 state
+ALGO_FLOPS_PER_PATIENT_STEP = 2 * 4_205_568                 # 12 core GEMMs
+METRIC = "ddpm_sampled_patients_per_sec_1000_steps"
+UNIT = "patients/s"
+
+
+def read_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.lines = []
+        self.proc = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+
+        def pump():
+            for line in self.proc.stdout:
+                self.lines.append(line.strip())
+
+        self.thread = threading.Thread(target=pump, daemon=True)
+        self.thread.start()
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(smax), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_rate(rows: int, steps: int, repeats: int = 1):
+    """patients/s of the reference's CPU algorithm: `steps` reverse steps on `rows` rows (torch CPU, all threads),
+    scaled to the 1000 steps a patient needs. Noise is drawn inside the timed region as the reference does."""
+    import torch
+    from oracle import ddpm_oracle as O
+    from oracle import synth
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.make_params(D, N_COND, HIDDEN, seed=0)
+    sd.update(O.schedule_buffers("cosine", T_STEPS))
+    cond = synth.scenario_conditions(rows, N_COND)
+    x = torch.randn(rows, D)
+    best = None
+    for _ in range(repeats):
+        xx = x.clone()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            t = T_STEPS - 1 - i
+            xx = O.p_sample(sd, xx, t, cond, torch.randn_like(xx), T_STEPS)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    per_step = best / steps
+    return rows / (per_step * T_STEPS), per_step, torch.get_num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    rows, sub_steps = 1024, 20
+    vals = []
+    ms = []
+    for _ in range(args.warmup):
+        cpu_reference_rate(rows, 2)
+    for _ in range(args.steps):
+        v, per_step, threads = cpu_reference_rate(rows, sub_steps)
+        vals.append(v)
+        ms.append(per_step * T_STEPS * 1e3)
+    value = statistics.mean(vals)
+    sample = f"{rows} rows x {sub_steps} of {T_STEPS} reverse steps per bench step, scaled to {T_STEPS} steps (B=1024 is the reference's CPU throughput peak, BASELINE.md §2)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": statistics.mean(ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.rows),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def workload_config(args, rows_per_gpu):
+    return {"workload": "1000-step conditional DDPM sampling, config.yaml dims (5142 features, 3 conditions, hidden [256,512,256], cosine), "
+                        "three config.yaml scenarios in equal thirds (BASELINE.json configs[1])",
+            "patients_per_gpu": rows_per_gpu, "num_steps": T_STEPS, "precision": args.precision,
+            "rng": "in-kernel Philox4x32-10 keyed by (seed, global row, t, column)", "weights": "random init (oracle/synth.py seed 0)",
+            "l2_policy": "state (fp32 x + bf16 shadow = 3.1 GB per 100k patients) is larger than L2; no flush needed",
+            "sharding": "contiguous global-row ranges per rank, no data-path collective"}
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device. The product path has no CPU fallback; use --impl reference for the CPU arm.")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    from osteosarcoma_diffusionmodel_b200 import build
+    from osteosarcoma_diffusionmodel_b200.diffusion import BiologyAwareDiffusionModel
+    from osteosarcoma_diffusionmodel_b200 import _lib
+    from oracle import synth   # deterministic synthetic weights / cohort generator only (no compute)
+
+    build.build()
+    rows = args.rows
+    cfg = synth.model_config(hidden_dims=HIDDEN)
+    model = BiologyAwareDiffusionModel(D_MUT, D_EXPR, D_PATH, N_COND, cfg)
+    model.load_state_dict(synth.make_params(D, N_COND, HIDDEN, seed=0), strict=False)
+    model = model.to(dev).eval()
+    model.set_precision(args.precision)
+    if args.chunk_rows is not None:
+        model.set_chunk_rows(args.chunk_rows)
+    row_base = rank * rows
+    cond_host = synth.scenario_conditions(rows, N_COND).pin_memory()
+    cond_dev = cond_host.to(dev)
+    out_host = torch.empty((rows, D), dtype=torch.float32).pin_memory() if not args.no_e2e else None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(seed):
+        return model.sample(cond_dev, rows, seed=seed, row_base=row_base)
+
+    for i in range(args.warmup):
+        one_step(1000 + i)
+    model.check_status()
+
+    # ---- kernel-resident timing: inputs already in HBM, result left in HBM
+    sampler = ClockSampler(local_rank)
+    launches0 = model.launch_count()
+    barrier()
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        one_step(i)
+    ev1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    barrier()
+    launches = model.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    if dist is not None:
+        tt = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_total = tt.item()
+    model.check_status()
+    value = rows * world * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public API: pinned host conditions in, samples out to pinned host memory
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step(seed):
+            c = cond_host.to(dev, non_blocking=True)
+            s = model.sample(c, rows, seed=seed, row_base=row_base)
+            out_host.copy_(s, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        e2e_step(77)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(100 + i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms_e2e = e0.elapsed_time(e1)
+        if dist is not None:
+            tt = torch.tensor([ms_e2e], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms_e2e = tt.item()
+        e2e = {"value": rows * world * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(cond_host.numel() * 4),
+               "d2h_bytes_per_step": int(rows * D * 4)}
+
+    # ---- live per-kernel timing of one reverse step (CUDA events after every launch on the launch stream)
+    roofline = None
+    kernels = None
+    hbm_peak, tf_peak, peak_src = read_peaks()
+    if rank == 0:
+        import ctypes as C
+
+        lib = _lib.load()
+        buf = (C.c_float * 4096)()
+        per = []
+        for rep in range(5):
+            n_l = lib.osteo_ddpm_profile_step(model._ctx, rows, 500, 9, row_base, buf, 4096, _lib.stream_handle())
+            if n_l < 0:
+                _lib.check(n_l)
+            per.append([buf[i] for i in range(n_l)])
+        per = np.array(per[1:]).mean(axis=0)            # drop the first repetition
+        n_chunks = max(1, len(per) // 12)
+        names = ["input_proj+emb_add"] + [f"linear_gn_silu_{i}" for i in range(10)] + ["output_proj+reverse_update"]
+        by_kernel = {}
+        for i, ms in enumerate(per):
+            by_kernel.setdefault(names[i % 12], []).append(float(ms))
+        step_ms = float(per.sum())
+        kernels = {k: {"ms_per_step": sum(v), "share": sum(v) / step_ms} for k, v in by_kernel.items()}
+        dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
+        launches_of_dom = len(by_kernel[dom])
+        dom_ms = kernels[dom]["ms_per_step"] / launches_of_dom
+        rows_per_launch = rows / launches_of_dom
+        if dom == "output_proj+reverse_update":
+            algo = ALGO_BYTES_PER_PATIENT_STEP * rows_per_launch
+            ach = algo / (dom_ms / 1e3) / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                        "algorithmic_bytes_per_launch": algo, "avg_launch_ms": dom_ms, "peak_source": peak_src}
+        elif dom == "input_proj+emb_add":
+            algo = D * 4 * rows_per_launch      # one read of the state row (fp32-equivalent algorithmic bytes)
+            ach = algo / (dom_ms / 1e3) / 1e9
+            roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                        "algorithmic_bytes_per_launch": algo, "avg_launch_ms": dom_ms, "peak_source": peak_src}
+        else:
+            flops = ALGO_FLOPS_PER_PATIENT_STEP * rows_per_launch / 12
+            ach = flops / (dom_ms / 1e3) / 1e12
+            roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+                        "avg_launch_ms": dom_ms, "peak_source": peak_src}
+        prof = ROOT / "profiles" / "traffic.json"
+        if prof.exists():
+            try:
+                roofline["traffic"] = json.loads(prof.read_text()).get(dom)
+            except Exception:
+                pass
+        # whole reverse step against both ceilings of SURVEY.md §8(d)
+        gemm_ms = sum(v["ms_per_step"] for k, v in kernels.items())
+        roofline["step"] = {"ms_per_reverse_step": step_ms, "hbm_frac_of_algorithmic": ALGO_BYTES_PER_PATIENT_STEP * rows / (step_ms / 1e3) / 1e9 / hbm_peak,
+                            "tensor_frac": ALGO_FLOPS_PER_PATIENT_STEP * rows / (gemm_ms / 1e3) / 1e12 / tf_peak}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, per_step, threads = cpu_reference_rate(1024, 20)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"1024 rows x 20 of {T_STEPS} reverse steps of the torch-CPU oracle port (oracle/ddpm_oracle.py), scaled to {T_STEPS} steps"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split-bf16, fp32-equivalent)", "data": "synthetic",
+            "config": workload_config(args, rows), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--rows", type=int, default=100_000, help="patients per GPU (BASELINE.json configs[1]: 100k)")
+    ap.add_argument("--precision", choices=["bf16", "fp32x3"], default="bf16")
+    ap.add_argument("--chunk-rows", type=int, default=None)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3          # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -137,6 +137,12 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* ctx, const float* x0_dev, const float*
                           float* const* grads_dev, int n_tensors, void* stream);
 
 /* ---- diagnostics */
+/* One reverse step (in-kernel noise) with a CUDA event recorded on `stream` after every GEMM launch.
+ * Writes the per-launch durations in ms to ms_out_host[0..] in launch order (per row chunk: input_proj,
+ * the 2*blocks Linear+GroupNorm+SiLU launches, output_proj+update) and RETURNS the number of launches
+ * (>= 0) or a negative error. Synchronises `stream`. Used by bench.py for the live roofline numbers. */
+int osteo_ddpm_profile_step(osteo_ddpm_ctx* ctx, long long n, int t, uint64_t seed, long long row_base,
+                            float* ms_out_host, int max_out, void* stream);
 /* Sticky kernel status word (0 = ok; see GemmError). Synchronises `stream`. */
 int osteo_ddpm_status(osteo_ddpm_ctx* ctx, void* stream);
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */

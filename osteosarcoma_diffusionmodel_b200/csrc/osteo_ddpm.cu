@@ -175,6 +175,7 @@ struct osteo_ddpm_ctx {
     long long graph_row_base = 0;
     int graph_precision = -1, graph_chunk = -1;
     long long graph_launches_per_step = 0;
+    std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every GEMM launch
 
     bool x3() const { return precision == OSTEO_PREC_FP32X3; }
     int h0() const { return hidden[0]; }
@@ -196,6 +197,17 @@ static void base_params(const osteo_ddpm_ctx* c, GemmParams& p) {
     p.status = c->status_dev.as<int>();
     p.step = c->step_dev.as<int>();
     p.gn_eps = 1e-5f;
+}
+
+static int after_launch(osteo_ddpm_ctx* c, int rc, cudaStream_t s) {
+    ++c->launches;
+    if (rc == 0 && c->prof) {
+        cudaEvent_t e;
+        OSTEO_CUDA(cudaEventCreate(&e));
+        OSTEO_CUDA(cudaEventRecord(e, s));
+        c->prof->push_back(e);
+    }
+    return rc;
 }
 
 static void set_rows(GemmParams& p, long long row0, long long row1) {
@@ -224,8 +236,7 @@ static int launch_input_proj(osteo_ddpm_ctx* c, long long row0, long long row1, 
     p.out_bf = c->acts[0]->ptr();
     p.out_bf_ld = 2 * c->h0();
     p.out_lo_off = c->lo(c->h0());
-    ++c->launches;
-    return launch_gemm(EPI_LINEAR, 64, p, c->sms, s);
+    return after_launch(c, launch_gemm(EPI_LINEAR, 64, p, c->sms, s), s);
 }
 
 struct HalfOpts {
@@ -283,8 +294,7 @@ static int launch_half(osteo_ddpm_ctx* c, int hi, long long row0, long long row1
         p.xhat_bf = c->train.xhat[hi]->as<__nv_bfloat16>();
         p.rstd_out = c->train.rstd[hi]->as<float>();
     }
-    ++c->launches;
-    return launch_gemm(EPI_GN_SILU, hb.gw, p, c->sms, s);
+    return after_launch(c, launch_gemm(EPI_GN_SILU, hb.gw, p, c->sms, s), s);
 }
 
 static void out_proj_common(osteo_ddpm_ctx* c, GemmParams& p, long long row0, long long row1) {
@@ -319,8 +329,7 @@ static int launch_output_ddpm(osteo_ddpm_ctx* c, long long row0, long long row1,
     p.eps_ld = c->D;
     p.seed = seed;
     p.row_base = row_base;
-    ++c->launches;
-    return launch_gemm(EPI_DDPM, 64, p, c->sms, s);
+    return after_launch(c, launch_gemm(EPI_DDPM, 64, p, c->sms, s), s);
 }
 
 // output_proj writing eps as a dense fp32 tensor (forward(return_loss=False)).
@@ -329,8 +338,7 @@ static int launch_output_eps(osteo_ddpm_ctx* c, long long row0, long long row1, 
     out_proj_common(c, p, row0, row1);
     p.out_f32 = eps_out;
     p.out_f32_ld = c->D;
-    ++c->launches;
-    return launch_gemm(EPI_LINEAR, 64, p, c->sms, s);
+    return after_launch(c, launch_gemm(EPI_LINEAR, 64, p, c->sms, s), s);
 }
 
 static long long chunk_of(const osteo_ddpm_ctx* c, long long n) {
@@ -775,6 +783,32 @@ int osteo_ddpm_reverse_update(osteo_ddpm_ctx* c, float* x_dev, const float* eps_
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     return 0;
+}
+
+int osteo_ddpm_profile_step(osteo_ddpm_ctx* c, long long n, int t, uint64_t seed, long long row_base, float* ms_out, int max_out, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    OSTEO_TRY(require_ready(c, n));
+    if (t < 0 || t >= c->T) return fail("timestep %d outside [0, %d)", t, c->T);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    set_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), t);
+    OSTEO_CUDA(cudaGetLastError());
+    std::vector<cudaEvent_t> ev;
+    cudaEvent_t e0;
+    OSTEO_CUDA(cudaEventCreate(&e0));
+    OSTEO_CUDA(cudaEventRecord(e0, s));
+    ev.push_back(e0);
+    c->prof = &ev;
+    const int rc = enqueue_reverse_step(c, n, nullptr, nullptr, seed, row_base, s);
+    c->prof = nullptr;
+    int count = -1;
+    if (rc == 0 && cudaStreamSynchronize(s) == cudaSuccess) {
+        count = static_cast<int>(ev.size()) - 1;
+        for (int i = 0; i < count && i < max_out; ++i) cudaEventElapsedTime(&ms_out[i], ev[i], ev[i + 1]);
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (rc != 0) return rc;
+    if (count < 0) return fail("profile_step: stream synchronisation failed");
+    return count;
 }
 
 int osteo_ddpm_status(osteo_ddpm_ctx* c, void* stream) {
