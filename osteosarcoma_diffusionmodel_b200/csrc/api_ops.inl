@@ -36,7 +36,8 @@ static int linear_tc_impl(const float* a_dev, const float* w_dev, const float* b
     std::memset(&p, 0, sizeof p);
     OSTEO_TRY(make_tmap_bf16(&p.tma_a[0], a_bf.p, mp, 2 * kp, 2 * kp, BM));
     p.tma_a[1] = p.tma_a[0];
-    OSTEO_TRY(make_tmap_bf16(&p.tma_b, w_bf.p, np, 2 * kp, 2 * kp, BN));
+    OSTEO_TRY(make_tmap_bf16(&p.tma_b[0], w_bf.p, np, 2 * kp, 2 * kp, BN));
+    p.tma_b[1] = p.tma_b[0];
     OSTEO_TRY(add_segments(p, 0, 0, kp, 0, kp, kp, x3));
     p.M = m;
     p.N = n;

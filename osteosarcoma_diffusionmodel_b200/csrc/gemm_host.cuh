@@ -45,7 +45,7 @@ inline int add_segments(GemmParams& p, int a_sel, int a_col0, int a_lo_off, int 
     const int nkb = k / BK;
     auto push = [&](int ac, int bc) -> int {
         if (p.nseg >= MAX_KSEG) return fail("too many K segments");
-        p.seg[p.nseg++] = KSeg{a_sel, ac, bc, nkb};
+        p.seg[p.nseg++] = KSeg{a_sel, ac, bc, nkb, 0, 0};
         return 0;
     };
     OSTEO_TRY(push(a_col0, b_col0));

@@ -38,21 +38,25 @@ enum EpiKind : int {
     EPI_GN_SILU = 1,  // bias + GroupNorm(8) + affine + SiLU (+dropout) -> bf16 [hi|lo]
     EPI_DDPM = 2,     // eps = acc + bias; x <- c_x*x - c_eps*eps + sigma*z ; xb <- bf16(x)
     EPI_MSE = 3,      // eps = acc + bias; loss += sum (eps - noise)^2 ; grad <- scale*(eps - noise)
-    EPI_RBF = 4       // sum over tile of exp(-gamma*(na[m] + nb[n] - 2 acc))
+    EPI_RBF = 4,      // sum over tile of exp(-gamma*(na[m] + nb[n] - 2 acc))
+    EPI_GN_BWD = 5,   // acc = d(block output): dropout/SiLU/GroupNorm backward -> d(pre-norm) bf16 + column partials
+    EPI_WGRAD = 6     // acc = dY^T X (both operands MN-major, split over the batch): fp32 atomic accumulate
 };
 
 enum GemmError : int { ERR_NONE = 0, ERR_PRODUCER_TIMEOUT = 1, ERR_MMA_TIMEOUT = 2, ERR_EPI_TIMEOUT = 3 };
 
 struct KSeg {
     int a_sel;   // which A tensor map (0 / 1)
-    int a_col;   // first K column in A
-    int b_col;   // first K column in W
-    int nkb;     // number of 64-wide k-blocks
+    int a_col;   // first K column in A            (MN-major mode: first feature column of the A operand)
+    int b_col;   // first K column in W            (MN-major mode: first feature column of the B operand)
+    int nkb;     // number of 64-wide k-blocks     (MN-major mode: unused, the k range is the launch's row split)
+    int b_sel;   // which B tensor map (0 / 1)
+    int b_row0;  // row of W holding output column 0 (dgrad through a concatenated input reads a row range of W^T)
 };
 
 struct GemmParams {
     CUtensorMap tma_a[2];
-    CUtensorMap tma_b;
+    CUtensorMap tma_b[2];
     int M, N;                 // valid rows / valid output columns
     int m_tiles, n_tiles;     // tiles this launch covers: m blocks [m_tile0, m_tile0 + m_tiles)
     int m_tile0;
@@ -102,6 +106,16 @@ struct GemmParams {
     int target_ld;
     float grad_scale;
     double* loss_acc;
+    // EPI_GN_BWD (reads gamma / beta / drop_* above)
+    const __nv_bfloat16* xhat_in;   // saved normalised activations [M, xhat_ld] (hi at col, lo at col + xhat_lo_off)
+    int xhat_ld;
+    int xhat_lo_off;
+    const float* rstd_in;     // [M, 8]
+    float* col_partials;      // [ceil(M/32), n_partials, N] fp32 column sums over 32-row slabs (dgamma, dbeta, dbias | dbias)
+    // EPI_WGRAD
+    int k_rows;               // contraction length (batch rows)
+    int splits;               // row splits; tiles = splits * m_tiles * n_tiles
+    int kb_per_split;
     // EPI_RBF
     const float* norm_a;      // [M]
     const float* norm_b;      // [N]
@@ -153,7 +167,28 @@ __device__ __forceinline__ float silu_f(float y) { return __fdividef(y, 1.0f + _
 template <int EPI>
 struct Epilogue;
 
-template <int EPI, int GW>
+// Tile decode shared by the three roles. K-major mode: tile -> (m_blk, n_blk), the k range is the segment list.
+// MN-major (wgrad) mode: tile -> (split, m_blk, n_blk), the k range is this split's slice of the batch rows.
+struct TileInfo {
+    int m_blk, n_blk, kb0, kb1;
+    bool skip;
+};
+template <int EPI, bool MN>
+__device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
+    TileInfo t;
+    const int per = p.m_tiles * p.n_tiles;
+    const int split = MN ? tile / per : 0;
+    const int r = MN ? tile % per : tile;
+    t.m_blk = p.m_tile0 + r / p.n_tiles;
+    t.n_blk = r % p.n_tiles;
+    t.kb0 = split * p.kb_per_split;
+    const int total_kb = (p.k_rows + BK - 1) / BK;
+    t.kb1 = t.kb0 + p.kb_per_split < total_kb ? t.kb0 + p.kb_per_split : total_kb;
+    t.skip = (EPI == EPI_RBF) && p.rbf_symmetric && t.n_blk < t.m_blk;
+    return t;
+}
+
+template <int EPI, int GW, bool MN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -171,7 +206,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tma_a[0]);
         tma_prefetch_desc(&p.tma_a[1]);
-        tma_prefetch_desc(&p.tma_b);
+        tma_prefetch_desc(&p.tma_b[0]);
+        tma_prefetch_desc(&p.tma_b[1]);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -190,7 +226,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = p.m_tiles * p.n_tiles;
+    const int num_tiles = (MN ? p.splits : 1) * p.m_tiles * p.n_tiles;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -199,16 +235,28 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             uint32_t phase = 0;
             bool ok = true;
             for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                const int m_blk = p.m_tile0 + tile / p.n_tiles, n_blk = tile % p.n_tiles;
-                if (EPI == EPI_RBF && p.rbf_symmetric && n_blk < m_blk) continue;
+                const TileInfo ti = decode_tile<EPI, MN>(p, tile);
+                if (ti.skip) continue;
                 for (int s = 0; s < p.nseg && ok; ++s) {
                     const KSeg sg = p.seg[s];
                     const CUtensorMap* ta = &p.tma_a[sg.a_sel];
-                    for (int kb = 0; kb < sg.nkb; ++kb) {
+                    const CUtensorMap* tb = &p.tma_b[sg.b_sel];
+                    const int kb_begin = MN ? ti.kb0 : 0, kb_end = MN ? ti.kb1 : sg.nkb;
+                    for (int kb = kb_begin; kb < kb_end; ++kb) {
                         if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; break; }
                         mbar_arrive_expect_tx(&full_bar[stage], A_TILE_BYTES + B_TILE_BYTES);
-                        tma_load_2d(ta, smem_a + stage * A_TILE_BYTES, &full_bar[stage], sg.a_col + kb * BK, m_blk * BM);
-                        tma_load_2d(&p.tma_b, smem_b + stage * B_TILE_BYTES, &full_bar[stage], sg.b_col + kb * BK, n_blk * BN);
+                        uint8_t* sa = smem_a + stage * A_TILE_BYTES;
+                        uint8_t* sb = smem_b + stage * B_TILE_BYTES;
+                        if (MN) {
+                            // operand tile = two boxes of [64 batch rows][64 features]; features are the MN dimension
+                            tma_load_2d(ta, sa, &full_bar[stage], sg.a_col + ti.m_blk * BM, kb * BK);
+                            tma_load_2d(ta, sa + A_TILE_BYTES / 2, &full_bar[stage], sg.a_col + ti.m_blk * BM + 64, kb * BK);
+                            tma_load_2d(tb, sb, &full_bar[stage], sg.b_col + ti.n_blk * BN, kb * BK);
+                            tma_load_2d(tb, sb + B_TILE_BYTES / 2, &full_bar[stage], sg.b_col + ti.n_blk * BN + 64, kb * BK);
+                        } else {
+                            tma_load_2d(ta, sa, &full_bar[stage], sg.a_col + kb * BK, ti.m_blk * BM);
+                            tma_load_2d(tb, sb, &full_bar[stage], sg.b_col + kb * BK, sg.b_row0 + ti.n_blk * BN);
+                        }
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -218,13 +266,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MN ? 1 : 0, MN ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
             bool ok = true;
             for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                if (EPI == EPI_RBF && p.rbf_symmetric && (tile % p.n_tiles) < (p.m_tile0 + tile / p.n_tiles)) continue;
+                const TileInfo ti = decode_tile<EPI, MN>(p, tile);
+                if (ti.skip) continue;
                 const int acc = it % NUM_ACC;
                 const uint32_t acc_phase = static_cast<uint32_t>(it / NUM_ACC) & 1u;
                 ++it;
@@ -233,17 +282,30 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
                 uint32_t accumulate = 0;
                 for (int s = 0; s < p.nseg && ok; ++s) {
-                    const int nkb = p.seg[s].nkb;
-                    for (int kb = 0; kb < nkb; ++kb) {
+                    const int kb_begin = MN ? ti.kb0 : 0, kb_end = MN ? ti.kb1 : p.seg[s].nkb;
+                    for (int kb = kb_begin; kb < kb_end; ++kb) {
                         if (!mbar_wait(&full_bar[stage], phase)) { ok = false; break; }
                         tc_fence_after_sync();
-                        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem_a + stage * A_TILE_BYTES));
-                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem_b + stage * B_TILE_BYTES));
+                        const uint32_t a_addr = smem_u32(smem_a + stage * A_TILE_BYTES);
+                        const uint32_t b_addr = smem_u32(smem_b + stage * B_TILE_BYTES);
+                        if (MN) {
+                            const uint64_t adesc = make_mnmajor_sw128_desc(a_addr, A_TILE_BYTES / 2);
+                            const uint64_t bdesc = make_mnmajor_sw128_desc(b_addr, B_TILE_BYTES / 2);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            // +32 B per UMMA_K step inside the 128-byte swizzle row (start-address field is >>4)
-                            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accumulate);
-                            accumulate = 1;
+                            for (int k = 0; k < BK / 16; ++k) {
+                                // 16 batch rows per UMMA_K step = 16 * 128 B inside each box
+                                umma_bf16(d_tmem, adesc + 128u * k, bdesc + 128u * k, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                        } else {
+                            const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+                            const uint64_t bdesc = make_kmajor_sw128_desc(b_addr);
+#pragma unroll
+                            for (int k = 0; k < BK / 16; ++k) {
+                                // +32 B per UMMA_K step inside the 128-byte swizzle row (start-address field is >>4)
+                                umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accumulate);
+                                accumulate = 1;
+                            }
                         }
                         umma_commit(&empty_bar[stage]);
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -261,8 +323,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         bool ok = true;
         double thread_acc = 0.0;                // EPI_MSE / EPI_RBF partial sums
         for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-            const int m_blk = p.m_tile0 + tile / p.n_tiles, n_blk = tile % p.n_tiles;
-            if (EPI == EPI_RBF && p.rbf_symmetric && n_blk < m_blk) continue;
+            const TileInfo ti = decode_tile<EPI, MN>(p, tile);
+            if (ti.skip) continue;
             const int acc = it % NUM_ACC;
             const uint32_t acc_phase = static_cast<uint32_t>(it / NUM_ACC) & 1u;
             ++it;
@@ -277,8 +339,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
 
-            const int row = m_blk * BM + q * 32 + lane;
-            const int col = n_blk * BN + half * 64;
+            const int row = ti.m_blk * BM + q * 32 + lane;
+            const int col = ti.n_blk * BN + half * 64;
             Epilogue<EPI>::template run<GW>(p, row, col, v0, v1, thread_acc);
         }
         if (EPI == EPI_MSE || EPI == EPI_RBF) {
@@ -293,6 +355,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Column sums over the 32 rows a warp holds: each lane contributes v[0..31] (its row's 32 columns); after the
+// butterfly (16+8+4+2+1 = 31 shuffles) lane L holds the total of column L. Rows that must not count pass zeros.
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        const bool upper = (lane & w) != 0;
+#pragma unroll
+        for (int j = 0; j < w; ++j) {
+            // keep the half of the columns whose bit `w` matches this lane's bit, send the other half across
+            const float keep = upper ? v[j + w] : v[j];
+            const float send = upper ? v[j] : v[j + w];
+            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+        }
+    }
+    return v[0];
 }
 
 // ------------------------------------------------------------------ epilogues
@@ -558,6 +637,159 @@ struct Epilogue<EPI_RBF> {
         float w = 1.0f;
         if (p.rbf_symmetric && (col / BN) != (row / BM)) w = 2.0f;
         acc += static_cast<double>(local * w);
+    }
+};
+
+template <>
+struct Epilogue<EPI_GN_BWD> {
+    // Backward of Linear -> GroupNorm(8) -> SiLU (-> Dropout) for one row held by this thread.
+    //   acc = dL/d(block output); ds = acc * mask / (1 - p); z = gamma * xhat + beta; dz = ds * silu'(z);
+    //   dgamma += dz * xhat; dbeta += dz; dxhat = dz * gamma;
+    //   dy = rstd * (dxhat - mean_g(dxhat) - xhat * mean_g(dxhat * xhat));  dbias += dy
+    // (autograd of models/diffusion.py:201-207 with torch's native_group_norm_backward formulas).
+    // dy goes out as bf16 [hi|lo]: the A operand of the next dgrad and the MN-major operand of this layer's wgrad.
+    template <int GW>
+    __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double&) {
+        const bool live = row < p.M;
+        const int lane = threadIdx.x & 31;
+        constexpr int NG = 64 / GW;
+        float xh0[32], xh1[32];
+        if (live) {
+            const __nv_bfloat16* xr = p.xhat_in + static_cast<size_t>(row) * p.xhat_ld + col;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float(&xh)[32] = h ? xh1 : xh0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 w = reinterpret_cast<const uint4*>(xr + 32 * h)[j];
+                    const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[i]);
+                        xh[8 * j + 2 * i] = __low2float(b2);
+                        xh[8 * j + 2 * i + 1] = __high2float(b2);
+                    }
+                }
+                if (p.xhat_lo_off > 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint4 w = reinterpret_cast<const uint4*>(xr + p.xhat_lo_off + 32 * h)[j];
+                        const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const __nv_bfloat162 b2 = *reinterpret_cast<const __nv_bfloat162*>(&ww[i]);
+                            xh[8 * j + 2 * i] += __low2float(b2);
+                            xh[8 * j + 2 * i + 1] += __high2float(b2);
+                        }
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { xh0[j] = 0.f; xh1[j] = 0.f; v0[j] = 0.f; v1[j] = 0.f; }
+        }
+        // dropout of the block output
+        if (live && p.drop_p > 0.0f) {
+            const float keep_scale = 1.0f / (1.0f - p.drop_p);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                float(&v)[32] = h ? v1 : v0;
+                const int c0 = col + 32 * h;
+                if (p.drop_mask) {
+                    const uint8_t* mk = p.drop_mask + static_cast<size_t>(row) * p.N + c0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) v[j] = mk[j] ? v[j] * keep_scale : 0.0f;
+                } else {
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const uint4 w = philox_words(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>((c0 >> 2) + j4), p.drop_stream, 0u);
+                        v[4 * j4 + 0] = (u01(w.x) >= p.drop_p) ? v[4 * j4 + 0] * keep_scale : 0.0f;
+                        v[4 * j4 + 1] = (u01(w.y) >= p.drop_p) ? v[4 * j4 + 1] * keep_scale : 0.0f;
+                        v[4 * j4 + 2] = (u01(w.z) >= p.drop_p) ? v[4 * j4 + 2] * keep_scale : 0.0f;
+                        v[4 * j4 + 3] = (u01(w.w) >= p.drop_p) ? v[4 * j4 + 3] * keep_scale : 0.0f;
+                    }
+                }
+            }
+        }
+        // dz, then the two parameter-gradient column sums (dgamma, dbeta) over this warp's 32 rows
+        const int slab = row >> 5;
+        float* part = p.col_partials ? p.col_partials + static_cast<size_t>(slab) * 3 * p.N : nullptr;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float(&v)[32] = h ? v1 : v0;
+            float(&xh)[32] = h ? xh1 : xh0;
+            const int c0 = col + 32 * h;
+            float t0[32], t1[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float g = __ldg(p.gamma + c0 + j);
+                const float z = fmaf(xh[j], g, __ldg(p.beta + c0 + j));
+                const float sg = __fdividef(1.0f, 1.0f + __expf(-z));
+                const float dz = live ? v[j] * sg * fmaf(z, 1.0f - sg, 1.0f) : 0.0f;
+                t0[j] = dz * xh[j];
+                t1[j] = dz;
+                v[j] = dz * g;     // dxhat
+            }
+            const float sg_ = warp_column_sums(t0, lane);
+            const float sb_ = warp_column_sums(t1, lane);
+            if (part) {
+                part[c0 + lane] = sg_;
+                part[p.N + c0 + lane] = sb_;
+            }
+        }
+        // GroupNorm backward within each group of this row
+        const float* rs = p.rstd_in + static_cast<size_t>(live ? row : 0) * 8 + col / GW;
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            float m1 = 0.0f, m2 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < GW; ++j) {
+                const int idx = g * GW + j;
+                const float dx = (idx < 32) ? v0[idx & 31] : v1[idx & 31];
+                const float x = (idx < 32) ? xh0[idx & 31] : xh1[idx & 31];
+                m1 += dx;
+                m2 = fmaf(dx, x, m2);
+            }
+            m1 *= (1.0f / GW);
+            m2 *= (1.0f / GW);
+            const float r = live ? rs[g] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < GW; ++j) {
+                const int idx = g * GW + j;
+                if (idx < 32) v0[idx & 31] = r * (v0[idx & 31] - m1 - xh0[idx & 31] * m2);
+                else v1[idx & 31] = r * (v1[idx & 31] - m1 - xh1[idx & 31] * m2);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float(&v)[32] = h ? v1 : v0;
+            const int c0 = col + 32 * h;
+            if (live) store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
+            float t[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = v[j];
+            const float sdy = warp_column_sums(t, lane);
+            if (part) part[2 * p.N + c0 + lane] = sdy;
+        }
+    }
+};
+
+template <>
+struct Epilogue<EPI_WGRAD> {
+    // dW[row = output feature, col = input feature] += acc. One launch may split the batch rows over several CTAs.
+    template <int GW>
+    __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double&) {
+        if (row >= p.M) return;
+        float* o = p.out_f32 + static_cast<size_t>(row) * p.out_f32_ld;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float(&v)[32] = h ? v1 : v0;
+            const int c0 = col + 32 * h;
+            if (c0 >= p.N) break;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < p.N) atomicAdd(o + c0 + j, v[j]);
+        }
     }
 };
 

@@ -222,7 +222,7 @@ static int launch_input_proj(osteo_ddpm_ctx* c, long long row0, long long row1, 
     base_params(c, p);
     p.tma_a[0] = c->xb.tmap;
     p.tma_a[1] = c->xb.tmap;
-    p.tma_b = c->in_proj.tmap;
+    p.tma_b[0] = p.tma_b[1] = c->in_proj.tmap;
     OSTEO_TRY(add_segments(p, 0, 0, c->DP, 0, c->in_proj.kp, c->DP, c->x3()));
     set_rows(p, row0, row1);
     p.N = c->h0();
@@ -255,7 +255,7 @@ static int launch_half(osteo_ddpm_ctx* c, int hi, long long row0, long long row1
     const ActBuf& a0 = *c->acts[hb.src0];
     p.tma_a[0] = a0.tmap;
     p.tma_a[1] = a0.tmap;
-    p.tma_b = hb.lin.tmap;
+    p.tma_b[0] = p.tma_b[1] = hb.lin.tmap;
     if (c->x3()) {
         // keep the three passes of each source adjacent: hi*hi, hi*lo, lo*hi
         OSTEO_TRY(add_segments(p, 0, 0, a0.width, 0, hb.lin.kp, a0.width, true));
@@ -302,7 +302,7 @@ static void out_proj_common(osteo_ddpm_ctx* c, GemmParams& p, long long row0, lo
     const ActBuf& a = *c->acts.back();
     p.tma_a[0] = a.tmap;
     p.tma_a[1] = a.tmap;
-    p.tma_b = c->out_proj.tmap;
+    p.tma_b[0] = p.tma_b[1] = c->out_proj.tmap;
     add_segments(p, 0, 0, a.width, 0, c->out_proj.kp, a.width, c->x3());
     set_rows(p, row0, row1);
     p.N = c->D;
