@@ -136,6 +136,10 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* ctx, const float* x0_dev, const float*
                           int train, uint64_t seed, long long row_base, float* loss_dev,
                           float* const* grads_dev, int n_tensors, void* stream);
 
+/* Allocate the transposed weight copies the backward pass contracts against. Must be followed by
+ * osteo_ddpm_set_weights (which fills them) before osteo_ddpm_train_step is asked for gradients. */
+int osteo_ddpm_enable_training(osteo_ddpm_ctx* ctx, int enable);
+
 /* ---- diagnostics */
 /* One reverse step (in-kernel noise) with a CUDA event recorded on `stream` after every GEMM launch.
  * Writes the per-launch durations in ms to ms_out_host[0..] in launch order (per row chunk: input_proj,
@@ -157,6 +161,11 @@ int osteo_linear_tc(const float* a_dev, const float* w_dev, const float* bias_de
 int osteo_linear_gn_silu_tc(const float* a_dev, const float* w_dev, const float* bias_dev,
                             const float* gamma_dev, const float* beta_dev, float* out_dev,
                             int m, int n, int k, int precision, void* stream);
+/* dw[n_out, k_in] = dy^T x over `rows` batch rows (dy fp32 [rows, n_out], x fp32 [rows, k_in]) on tcgen05 with
+ * both operands MN-major and the batch split over CTAs — the weight-gradient contraction of train_step.
+ * Synchronises `stream`. */
+int osteo_wgrad_tc(const float* dy_dev, const float* x_dev, float* dw_dev, long long rows, int n_out, int k_in,
+                   int precision, void* stream);
 /* Fill out[n, d] fp32 with Philox normals (stream id, step) — test hook for the RNG. */
 int osteo_philox_normal(float* out_dev, long long n, int d, uint64_t seed, long long row_base,
                         uint32_t stream_id, uint32_t step, void* stream);

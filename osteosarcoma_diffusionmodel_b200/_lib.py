@@ -50,11 +50,13 @@ SIGNATURES = {
     "osteo_ddpm_q_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _u64, _ll, _u32, _vp]),
     "osteo_ddpm_reverse_update": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _u64, _ll, _vp]),
     "osteo_ddpm_train_step": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, C.POINTER(_vp), _i, _u64, _ll, _vp, C.POINTER(_vp), _i, _vp]),
+    "osteo_ddpm_enable_training": (_i, [_vp, _i]),
     "osteo_ddpm_profile_step": (_i, [_vp, _ll, _i, _u64, _ll, _vp, _i, _vp]),
     "osteo_ddpm_status": (_i, [_vp, _vp]),
     "osteo_ddpm_launch_count": (_ll, [_vp]),
     "osteo_linear_tc": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "osteo_linear_gn_silu_tc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "osteo_wgrad_tc": (_i, [_vp, _vp, _vp, _ll, _i, _i, _i, _vp]),
     "osteo_philox_normal": (_i, [_vp, _ll, _i, _u64, _ll, _u32, _u32, _vp]),
     "osteo_philox_words": (_i, [_vp, _ll, _i, _u64, _ll, _u32, _u32, _vp]),
     "osteo_mmd_partial": (_i, [_vp, _ll, _vp, _ll, _i, _f, _vp, _ll, _ll, _ll, _ll, _i, _vp, _vp]),

@@ -87,6 +87,30 @@ int osteo_linear_gn_silu_tc(const float* a_dev, const float* w_dev, const float*
     return linear_tc_impl(a_dev, w_dev, bias_dev, gamma_dev, beta_dev, out_dev, m, n, k, precision, true, static_cast<cudaStream_t>(stream));
 }
 
+int osteo_wgrad_tc(const float* dy_dev, const float* x_dev, float* dw_dev, long long rows, int n_out, int k_in, int precision, void* stream) {
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (rows <= 0 || n_out <= 0 || k_in <= 0) return fail("wgrad_tc: bad shape");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int sms = current_sms();
+    const bool x3 = precision == OSTEO_PREC_FP32X3;
+    const int np = static_cast<int>(round_up(n_out, 64)), kp = static_cast<int>(round_up(k_in, 64));
+    DevBuf dy_bf, x_bf, status;
+    OSTEO_TRY(dy_bf.alloc(static_cast<size_t>(rows) * 2 * np * 2));
+    OSTEO_TRY(x_bf.alloc(static_cast<size_t>(rows) * 2 * kp * 2));
+    OSTEO_TRY(status.alloc(sizeof(int)));
+    OSTEO_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), s));
+    pack_bf16_hilo_kernel<<<grid_for(rows * (np / 4), 256, sms), 256, 0, s>>>(dy_dev, rows, n_out, n_out, dy_bf.as<__nv_bfloat16>(), rows, np, 2LL * np, np);
+    pack_bf16_hilo_kernel<<<grid_for(rows * (kp / 4), 256, sms), 256, 0, s>>>(x_dev, rows, k_in, k_in, x_bf.as<__nv_bfloat16>(), rows, kp, 2LL * kp, kp);
+    OSTEO_CUDA(cudaGetLastError());
+    OSTEO_CUDA(cudaMemsetAsync(dw_dev, 0, static_cast<size_t>(n_out) * k_in * sizeof(float), s));
+    OSTEO_TRY(launch_wgrad(dy_bf.as<__nv_bfloat16>(), 2 * np, np, n_out, x_bf.as<__nv_bfloat16>(), 2 * kp, 0, kp, k_in, dw_dev, k_in, rows, x3, status.as<int>(), sms, s));
+    int h = 0;
+    OSTEO_CUDA(cudaMemcpyAsync(&h, status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    OSTEO_CUDA(cudaStreamSynchronize(s));
+    if (h != 0) return fail("tcgen05 pipeline error %d in wgrad", h);
+    return 0;
+}
+
 int osteo_philox_normal(float* out_dev, long long n, int d, uint64_t seed, long long row_base, uint32_t stream_id, uint32_t step, void* stream) {
     if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
     if (n <= 0 || d <= 0) return fail("philox_normal: bad shape");

@@ -5,17 +5,17 @@
 
 namespace osteo {
 
-template <int EPI, int GW>
+template <int EPI, int GW, bool MN = false>
 int launch_gemm_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        OSTEO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        OSTEO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, GW, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
         configured = true;
     }
-    const int tiles = p.m_tiles * p.n_tiles;
+    const int tiles = (MN ? p.splits : 1) * p.m_tiles * p.n_tiles;
     if (tiles <= 0) return 0;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<EPI, GW><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    gemm_tc_kernel<EPI, GW, MN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
     OSTEO_CUDA(cudaGetLastError());
     return 0;
 }
@@ -33,6 +33,14 @@ inline int launch_gemm(int epi, int gw, const GemmParams& p, int num_sms, cudaSt
                 case 64: return launch_gemm_inst<EPI_GN_SILU, 64>(p, num_sms, stream);
                 default: return fail("GroupNorm group width %d not supported (need 16, 32 or 64)", gw);
             }
+        case EPI_GN_BWD:
+            switch (gw) {
+                case 16: return launch_gemm_inst<EPI_GN_BWD, 16>(p, num_sms, stream);
+                case 32: return launch_gemm_inst<EPI_GN_BWD, 32>(p, num_sms, stream);
+                case 64: return launch_gemm_inst<EPI_GN_BWD, 64>(p, num_sms, stream);
+                default: return fail("GroupNorm group width %d not supported (need 16, 32 or 64)", gw);
+            }
+        case EPI_WGRAD: return launch_gemm_inst<EPI_WGRAD, 64, true>(p, num_sms, stream);
         default: return fail("unknown epilogue %d", epi);
     }
 }
@@ -54,6 +62,40 @@ inline int add_segments(GemmParams& p, int a_sel, int a_col0, int a_lo_off, int 
         OSTEO_TRY(push(a_col0 + a_lo_off, b_col0));
     }
     return 0;
+}
+
+// dW[n_out, k_in] (+)= dY^T X over `rows` batch rows, both operands read MN-major straight from their row-major
+// [rows, ld] bf16 [hi|lo] buffers (no transposed copies). dW must be zero-initialised: row splits accumulate atomically.
+inline int launch_wgrad(const __nv_bfloat16* dy, int dy_ld, int dy_lo_off, int n_out, const __nv_bfloat16* x, int x_ld, int x_col0, int x_lo_off, int k_in,
+                        float* dw, int dw_ld, long long rows, bool x3, int* status, int num_sms, cudaStream_t stream) {
+    GemmParams p;
+    std::memset(&p, 0, sizeof p);
+    OSTEO_TRY(make_tmap_bf16(&p.tma_a[0], dy, rows, dy_ld, dy_ld, 64));
+    p.tma_a[1] = p.tma_a[0];
+    OSTEO_TRY(make_tmap_bf16(&p.tma_b[0], x, rows, x_ld, x_ld, 64));
+    p.tma_b[1] = p.tma_b[0];
+    p.seg[p.nseg++] = KSeg{0, 0, x_col0, 0, 0, 0};
+    if (x3) {
+        p.seg[p.nseg++] = KSeg{0, 0, x_col0 + x_lo_off, 0, 0, 0};
+        p.seg[p.nseg++] = KSeg{0, dy_lo_off, x_col0, 0, 0, 0};
+    }
+    p.M = n_out;
+    p.N = k_in;
+    p.m_tile0 = 0;
+    p.m_tiles = (n_out + BM - 1) / BM;
+    p.n_tiles = (k_in + BN - 1) / BN;
+    p.k_rows = static_cast<int>(rows);
+    const int total_kb = static_cast<int>((rows + BK - 1) / BK);
+    const int mn = p.m_tiles * p.n_tiles;
+    int splits = (2 * num_sms + mn - 1) / mn;
+    if (splits > total_kb) splits = total_kb;
+    if (splits < 1) splits = 1;
+    p.kb_per_split = (total_kb + splits - 1) / splits;
+    p.splits = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+    p.out_f32 = dw;
+    p.out_f32_ld = dw_ld;
+    p.status = status;
+    return launch_gemm(EPI_WGRAD, 64, p, num_sms, stream);
 }
 
 }  // namespace osteo

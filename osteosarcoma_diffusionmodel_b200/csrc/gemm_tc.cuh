@@ -111,7 +111,7 @@ struct GemmParams {
     int xhat_ld;
     int xhat_lo_off;
     const float* rstd_in;     // [M, 8]
-    float* col_partials;      // [ceil(M/32), n_partials, N] fp32 column sums over 32-row slabs (dgamma, dbeta, dbias | dbias)
+    float* col_partials;      // [ceil(M/32), nq, N] fp32 column sums over 32-row slabs; nq = 3 (dgamma, dbeta, dbias) for GN_BWD, 1 (dbias) otherwise
     // EPI_WGRAD
     int k_rows;               // contraction length (batch rows)
     int splits;               // row splits; tiles = splits * m_tiles * n_tiles
@@ -379,13 +379,15 @@ template <>
 struct Epilogue<EPI_LINEAR> {
     template <int GW>
     __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double&) {
-        if (row >= p.M) return;
+        const bool live = row < p.M;
+        if (!live && !p.col_partials) return;      // warp-uniform only when partials are off; otherwise every lane continues
+        const int lane = threadIdx.x & 31;
         const float* tab = nullptr;
-        if (p.add_tab) {
+        if (live && p.add_tab) {
             const int r = p.add_idx ? p.add_idx[row] : (p.step ? *p.step : 0);
             tab = p.add_tab + static_cast<size_t>(r) * p.add_tab_ld;
         }
-        const float* mat = p.add_mat ? p.add_mat + static_cast<size_t>(row) * p.add_mat_ld : nullptr;
+        const float* mat = (live && p.add_mat) ? p.add_mat + static_cast<size_t>(row) * p.add_mat_ld : nullptr;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             float(&v)[32] = h ? v1 : v0;
@@ -394,7 +396,7 @@ struct Epilogue<EPI_LINEAR> {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int c = c0 + j;
-                if (c < p.N) {
+                if (live && c < p.N) {
                     float a = v[j];
                     if (p.bias) a += __ldg(p.bias + c);
                     if (tab) a += __ldg(tab + c);
@@ -404,7 +406,7 @@ struct Epilogue<EPI_LINEAR> {
                     v[j] = 0.0f;
                 }
             }
-            if (p.out_f32) {
+            if (live && p.out_f32) {
                 float* o = p.out_f32 + static_cast<size_t>(row) * p.out_f32_ld + c0;
                 if (c0 + 32 <= p.N && (p.out_f32_ld & 3) == 0) {
 #pragma unroll
@@ -415,7 +417,11 @@ struct Epilogue<EPI_LINEAR> {
                         if (c0 + j < p.N) o[j] = v[j];
                 }
             }
-            if (p.out_bf) store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
+            if (live && p.out_bf) store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
+            if (p.col_partials) {
+                const float sum = warp_column_sums(v, lane);
+                if (c0 + lane < p.N) p.col_partials[static_cast<size_t>(row >> 5) * p.N + c0 + lane] = sum;
+            }
         }
     }
 };
@@ -581,22 +587,24 @@ struct Epilogue<EPI_DDPM> {
 template <>
 struct Epilogue<EPI_MSE> {
     // Training loss (models/diffusion.py:377): mean((eps_hat - noise)^2) over B*D; the epilogue
-    // accumulates the sum in fp64 and emits d(loss)/d(eps_hat) = grad_scale * (eps_hat - noise).
+    // accumulates the sum in fp64 and emits d(loss)/d(eps_hat) = grad_scale * (eps_hat - noise)
+    // plus its column sums over 32-row slabs (d(loss)/d(output_proj.bias)).
     template <int GW>
     __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double& acc) {
-        if (row >= p.M) return;
-        const float* trow = p.target + static_cast<size_t>(row) * p.target_ld;
+        const bool live = row < p.M;
+        const int lane = threadIdx.x & 31;
+        const float* trow = p.target + static_cast<size_t>(live ? row : 0) * p.target_ld;
         float local = 0.0f;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             float(&v)[32] = h ? v1 : v0;
             const int c0 = col + 32 * h;
-            if (c0 >= p.N) break;
+            if (c0 >= p.N) break;      // warp-uniform
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 const int c = c0 + j;
                 float d = 0.0f;
-                if (c < p.N) {
+                if (live && c < p.N) {
                     const float e = v[j] + __ldg(p.bias + c);
                     if (p.eps_out) p.eps_out[static_cast<size_t>(row) * p.eps_ld + c] = e;
                     d = e - trow[c];
@@ -604,7 +612,11 @@ struct Epilogue<EPI_MSE> {
                 }
                 v[j] = d * p.grad_scale;
             }
-            if (p.out_bf) store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
+            if (live && p.out_bf) store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
+            if (p.col_partials) {
+                const float sum = warp_column_sums(v, lane);
+                if (c0 + lane < p.N) p.col_partials[static_cast<size_t>(row >> 5) * p.N + c0 + lane] = sum;
+            }
         }
         acc += static_cast<double>(local);
     }
@@ -719,23 +731,25 @@ struct Epilogue<EPI_GN_BWD> {
             float(&v)[32] = h ? v1 : v0;
             float(&xh)[32] = h ? xh1 : xh0;
             const int c0 = col + 32 * h;
-            float t0[32], t1[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                const float g = __ldg(p.gamma + c0 + j);
-                const float z = fmaf(xh[j], g, __ldg(p.beta + c0 + j));
+                const float z = fmaf(xh[j], __ldg(p.gamma + c0 + j), __ldg(p.beta + c0 + j));
                 const float sg = __fdividef(1.0f, 1.0f + __expf(-z));
-                const float dz = live ? v[j] * sg * fmaf(z, 1.0f - sg, 1.0f) : 0.0f;
-                t0[j] = dz * xh[j];
-                t1[j] = dz;
-                v[j] = dz * g;     // dxhat
+                v[j] = live ? v[j] * sg * fmaf(z, 1.0f - sg, 1.0f) : 0.0f;     // dz
             }
-            const float sg_ = warp_column_sums(t0, lane);
-            const float sb_ = warp_column_sums(t1, lane);
+            float t[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = v[j] * xh[j];
+            const float sg_ = warp_column_sums(t, lane);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) t[j] = v[j];
+            const float sb_ = warp_column_sums(t, lane);
             if (part) {
                 part[c0 + lane] = sg_;
                 part[p.N + c0 + lane] = sb_;
             }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= __ldg(p.gamma + c0 + j);      // dxhat
         }
         // GroupNorm backward within each group of this row
         const float* rs = p.rstd_in + static_cast<size_t>(live ? row : 0) * 8 + col / GW;

@@ -1,25 +1,181 @@
-// Training-step workspace and kernels (backward of the denoiser). See api_train.inl.
+// Training-step workspace and the CUDA-core kernels of the backward pass that are not GEMMs:
+// q_sample fused with operand packing, column-partial reduction, and the backward of the tiny
+// condition / time embedding paths. The heavy lifting (dgrad / wgrad / GroupNorm backward) is
+// in gemm_tc.cuh; the orchestration is api_train.inl.
 #pragma once
 #include <memory>
 #include <vector>
 #include "common.cuh"
+#include "elem_kernels.cuh"
 
 namespace osteo {
 
-// Tensors saved by the training forward for the backward pass, one entry per half block:
-// normalised pre-affine activations x_hat (bf16 [cap, 2*n] = [hi|lo]) and 1/sigma per (row, group).
+// Tensors saved by the training forward for the backward pass.
 struct TrainWorkspace {
-    std::vector<std::unique_ptr<DevBuf>> xhat, rstd;
+    long long cap = 0;
+    // per half block
+    std::vector<std::unique_ptr<DevBuf>> xhat;   // bf16 [cap, 2*n]  normalised pre-affine activations [hi|lo]
+    std::vector<std::unique_ptr<DevBuf>> rstd;   // fp32 [cap, 8]
+    std::vector<std::unique_ptr<DevBuf>> dy;     // bf16 [cap, 2*n]  d(loss)/d(pre-norm Linear output) [hi|lo]
+    std::vector<CUtensorMap> dy_tmap;            // K-major A-operand maps of dy (dgrad)
+    DevBuf dh0_bf, dh0_f32;                      // d(loss)/d(h0): bf16 [cap, 2*h0], fp32 [cap, h0]
+    DevBuf deps;                                 // bf16 [cap, 2*DP]  d(loss)/d(eps_hat)
+    CUtensorMap deps_tmap;
+    DevBuf pre0, cemb, h1, dcemb, dpre0;         // fp32 [cap, E] each: condition-embedding forward saves / backward temporaries
+    DevBuf partials;                             // fp32 [cap/32, 3, max_width]
+    DevBuf colsum_tmp;                           // fp32 [E] scratch
     size_t bytes() const {
-        size_t b = 0;
+        size_t b = dh0_bf.bytes + dh0_f32.bytes + deps.bytes + pre0.bytes + cemb.bytes + h1.bytes + dcemb.bytes + dpre0.bytes + partials.bytes;
         for (auto& p : xhat) b += p->bytes;
         for (auto& p : rstd) b += p->bytes;
+        for (auto& p : dy) b += p->bytes;
         return b;
     }
     void release() {
         xhat.clear();
         rstd.clear();
+        dy.clear();
+        dy_tmap.clear();
+        for (DevBuf* b : {&dh0_bf, &dh0_f32, &deps, &pre0, &cemb, &h1, &dcemb, &dpre0, &partials, &colsum_tmp}) b->release();
+        cap = 0;
     }
 };
+
+// q_sample (models/diffusion.py:337-340) fused with the packing the GEMMs need:
+//   noise (injected, or Philox when noise_in == nullptr) -> fp32 [n, ld] (target of the MSE epilogue)
+//   x_t = sqrt_ab[t]*x0 + sqrt_1mab[t]*noise            -> bf16 [hi|lo] shadow (A operand of input_proj)
+__global__ void train_prepare_kernel(const float* __restrict__ x0, const float* __restrict__ noise_in, const int* __restrict__ t_idx, long long n, int d,
+                                     const float* __restrict__ sqrt_ab, const float* __restrict__ sqrt_1mab, float* __restrict__ noise_out, int ld,
+                                     __nv_bfloat16* __restrict__ xb, int xb_ld, int lo_off, unsigned long long seed, long long row_base) {
+    const int q = ld / 4;
+    const long long total = n * q;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / q;
+        const int c4 = static_cast<int>(i % q);
+        const int c = c4 * 4;
+        const int t = t_idx[r];
+        const float a = __ldg(sqrt_ab + t), b = __ldg(sqrt_1mab + t);
+        float z[4] = {0.f, 0.f, 0.f, 0.f}, xt[4] = {0.f, 0.f, 0.f, 0.f};
+        if (c < d) {
+            if (!noise_in) {
+                const float4 g = philox_normal4(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), STREAM_QNOISE, 0u);
+                z[0] = g.x; z[1] = g.y; z[2] = g.z; z[3] = g.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (c + j < d) {
+                    if (noise_in) z[j] = noise_in[r * d + c + j];
+                    xt[j] = __fadd_rn(__fmul_rn(a, x0[r * d + c + j]), __fmul_rn(b, z[j]));
+                } else {
+                    z[j] = 0.f;
+                }
+            }
+        }
+        *reinterpret_cast<float4*>(noise_out + r * ld + c) = make_float4(z[0], z[1], z[2], z[3]);
+        *reinterpret_cast<uint2*>(xb + r * xb_ld + c) = make_uint2(pack2(xt[0], xt[1]), pack2(xt[2], xt[3]));
+        if (lo_off > 0)
+            *reinterpret_cast<uint2*>(xb + r * xb_ld + lo_off + c) =
+                make_uint2(pack2(xt[0] - bf16r(xt[0]), xt[1] - bf16r(xt[1])), pack2(xt[2] - bf16r(xt[2]), xt[3] - bf16r(xt[3])));
+    }
+}
+
+// out_q[c] = sum over slabs of part[slab, q, c]. grid = (ceil(N/32), nq), block = (32, 8).
+__global__ void partials_finish_kernel(const float* __restrict__ part, int slabs, int nq, int N, float* out0, float* out1, float* out2) {
+    __shared__ float red[8][33];
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int q = blockIdx.y;
+    float acc = 0.0f;
+    if (c < N)
+        for (int s = threadIdx.y; s < slabs; s += 8) acc += part[(static_cast<size_t>(s) * nq + q) * N + c];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < N) {
+        float t = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        float* out = q == 0 ? out0 : (q == 1 ? out1 : out2);
+        if (out) out[c] = t;
+    }
+}
+
+// Column sums of a dense fp32 matrix g [n, m] -> out[m] (atomic accumulate; out zeroed by the caller).
+__global__ void colsum_f32_kernel(const float* __restrict__ g, long long n, int m, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const long long rows_per = (n + gridDim.y - 1) / gridDim.y;
+    const long long r0 = blockIdx.y * rows_per, r1 = r0 + rows_per < n ? r0 + rows_per : n;
+    float acc = 0.0f;
+    for (long long r = r0; r < r1; ++r) acc += g[r * m + c];
+    atomicAdd(out + c, acc);
+}
+
+// dW[gm, xk] += G^T X over rows: G fp32 [n, gm], X fp32 [n_x, xk] read through an optional row index (time table
+// gather). One block = 64 rows staged in shared memory; each thread owns a strided set of dW entries.
+__global__ void outer_accum_kernel(const float* __restrict__ G, int gm, const float* __restrict__ X, int xk, const int* __restrict__ x_idx, long long n,
+                                   float* __restrict__ dW) {
+    constexpr int R = 64;
+    extern __shared__ float sm[];
+    float* sg = sm;             // [R, gm]
+    float* sx = sm + R * gm;    // [R, xk]
+    const long long r0 = static_cast<long long>(blockIdx.x) * R;
+    const int rows = static_cast<int>((n - r0) < R ? (n - r0) : R);
+    for (int i = threadIdx.x; i < R * gm; i += blockDim.x) {
+        const int rr = i / gm;
+        sg[i] = rr < rows ? G[(r0 + rr) * gm + i % gm] : 0.0f;
+    }
+    for (int i = threadIdx.x; i < R * xk; i += blockDim.x) {
+        const int rr = i / xk;
+        float v = 0.0f;
+        if (rr < rows) {
+            const long long xr = x_idx ? x_idx[r0 + rr] : (r0 + rr);
+            v = X[xr * xk + i % xk];
+        }
+        sx[i] = v;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < gm * xk; e += blockDim.x) {
+        const int a = e / xk, b = e % xk;
+        float acc = 0.0f;
+#pragma unroll 8
+        for (int rr = 0; rr < R; ++rr) acc = fmaf(sg[rr * gm + a], sx[rr * xk + b], acc);
+        atomicAdd(dW + e, acc);
+    }
+}
+
+// Per-row backward through cond_proj and ConditionalEmbedding (models/diffusion.py:101-114, :226):
+//   dcemb = dh0 . Wc ; h1 = silu(pre0) ; dh1 = dcemb . W2 ; dpre0 = dh1 * silu'(pre0).  One block = 8 rows.
+__global__ void cond_bwd_rows_kernel(const float* __restrict__ dh0, long long n, int h0, int E, const float* __restrict__ wc, const float* __restrict__ w2,
+                                     const float* __restrict__ pre0, float* __restrict__ dcemb, float* __restrict__ h1, float* __restrict__ dpre0) {
+    constexpr int R = 8;
+    extern __shared__ float sm[];
+    float* s_d = sm;              // [R, h0]
+    float* s_e = s_d + R * h0;    // [R, E]
+    const long long r0 = static_cast<long long>(blockIdx.x) * R;
+    for (int i = threadIdx.x; i < R * h0; i += blockDim.x) {
+        const long long r = r0 + i / h0;
+        s_d[i] = r < n ? dh0[r * h0 + i % h0] : 0.0f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * E; i += blockDim.x) {
+        const int rr = i / E, j = i % E;
+        float a = 0.0f;
+        for (int k = 0; k < h0; ++k) a = fmaf(s_d[rr * h0 + k], wc[k * E + j], a);   // Wc is [h0, E]
+        s_e[i] = a;
+        if (r0 + rr < n) dcemb[(r0 + rr) * E + j] = a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * E; i += blockDim.x) {
+        const int rr = i / E, j = i % E;
+        if (r0 + rr >= n) continue;
+        float a = 0.0f;
+        for (int k = 0; k < E; ++k) a = fmaf(s_e[rr * E + k], w2[k * E + j], a);     // W2 is [E_out, E_in]: dh1[j] = sum_k dcemb[k] W2[k, j]
+        const float p0 = pre0[(r0 + rr) * E + j];
+        const float sg = 1.0f / (1.0f + expf(-p0));
+        h1[(r0 + rr) * E + j] = p0 * sg;
+        dpre0[(r0 + rr) * E + j] = a * sg * (1.0f + p0 * (1.0f - sg));
+    }
+}
+
+__global__ void zero_double_kernel(double* p) { *p = 0.0; }
 
 }  // namespace osteo

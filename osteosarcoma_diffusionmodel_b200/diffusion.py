@@ -146,6 +146,7 @@ class BiologyAwareDiffusionModel(nn.Module):
         self._ctx_device = None
         self._weights_sig = None
         self._schedule_sig = None
+        self._train_enabled = False
         self._inject: Optional[dict] = None   # test hook: {"t":..., "noise":..., "masks":[...]} consumed by forward()
 
     # ------------------------------------------------------------------ schedule (models/diffusion.py:312-326)
@@ -220,7 +221,7 @@ class BiologyAwareDiffusionModel(nn.Module):
         ps += [u.output_proj.weight, u.output_proj.bias]
         return ps
 
-    def _ensure_ctx(self, rows: int):
+    def _ensure_ctx(self, rows: int, train: bool = False):
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError("BiologyAwareDiffusionModel (B200-native) computes only on a CUDA device: move the model with "
@@ -235,11 +236,16 @@ class BiologyAwareDiffusionModel(nn.Module):
                                              len(self._hidden_dims), hid, self.num_steps, self._dropout, _PRECISIONS[self._precision]))
             self._ctx, self._ctx_device = handle, index
             self._weights_sig = self._schedule_sig = None
+            self._train_enabled = False
             _lib.check(lib.osteo_ddpm_set_chunk_rows(self._ctx, self._chunk_rows))
             emb = self.unet.time_embed.table(self.num_steps).numpy()
             _lib.check(lib.osteo_ddpm_set_time_embedding(self._ctx, emb.ctypes.data))
         if rows > lib.osteo_ddpm_capacity(self._ctx):
             _lib.check(lib.osteo_ddpm_reserve(self._ctx, int(rows)))
+        if train and not self._train_enabled:
+            _lib.check(lib.osteo_ddpm_enable_training(self._ctx, 1))
+            self._train_enabled = True
+            self._weights_sig = None
         self._sync_schedule()
         self._sync_weights()
         return lib
@@ -282,7 +288,7 @@ class BiologyAwareDiffusionModel(nn.Module):
     def __getstate__(self):
         # the C context is per-object device state: copies / pickles start without one
         state = self.__dict__.copy()
-        state.update(_ctx=None, _ctx_device=None, _weights_sig=None, _schedule_sig=None, _inject=None)
+        state.update(_ctx=None, _ctx_device=None, _weights_sig=None, _schedule_sig=None, _inject=None, _train_enabled=False)
         return state
 
     def check_status(self) -> None:
@@ -342,7 +348,7 @@ class BiologyAwareDiffusionModel(nn.Module):
 
     def _run_train_step(self, x_0, conditions, inject, want_grads: bool):
         n = x_0.shape[0]
-        lib = self._ensure_ctx(n)
+        lib = self._ensure_ctx(n, train=want_grads)
         dev = self._device()
         t = self._draw_t(n, inject).to(torch.int32).contiguous()
         noise = None
