@@ -130,12 +130,78 @@ int osteo_philox_words(uint32_t* out_dev, long long n, int ncol4, uint64_t seed,
 
 int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long long m, int d, float gamma, const float* center_dev, long long row_begin,
                       long long row_end, long long yrow_begin, long long yrow_end, int precision, double* sums_dev, void* stream) {
-    return fail("osteo_mmd_partial: not built yet");
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (n <= 0 || m <= 0 || d <= 0) return fail("mmd_partial: bad shape");
+    if (row_begin < 0 || row_end > n || row_begin > row_end || yrow_begin < 0 || yrow_end > m || yrow_begin > yrow_end) return fail("mmd_partial: bad row range");
+    if (row_begin % BM != 0 || yrow_begin % BM != 0) return fail("mmd_partial: shard starts must be multiples of %d", BM);
+    if (n > 2000000000LL || m > 2000000000LL) return fail("mmd_partial: more than 2^31 rows");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int sms = current_sms();
+    const bool x3 = precision == OSTEO_PREC_FP32X3;
+    const int kp = static_cast<int>(round_up(d, BK));
+    const long long np = round_up(n, BM), mp = round_up(m, BM);
+    DevBuf xb, yb, nx, ny, status;
+    OSTEO_TRY(xb.alloc(static_cast<size_t>(np) * 2 * kp * 2));
+    OSTEO_TRY(yb.alloc(static_cast<size_t>(mp) * 2 * kp * 2));
+    OSTEO_TRY(nx.alloc(static_cast<size_t>(np) * 4));
+    OSTEO_TRY(ny.alloc(static_cast<size_t>(mp) * 4));
+    OSTEO_TRY(status.alloc(sizeof(int)));
+    OSTEO_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), s));
+    OSTEO_CUDA(cudaMemsetAsync(sums_dev, 0, 3 * sizeof(double), s));
+    const int lo = x3 ? kp : 0;
+    pack_center_norm_kernel<<<sms * 8, 256, 0, s>>>(x_dev, n, d, center_dev, xb.as<__nv_bfloat16>(), np, kp, lo, nx.as<float>());
+    pack_center_norm_kernel<<<sms * 8, 256, 0, s>>>(y_dev, m, d, center_dev, yb.as<__nv_bfloat16>(), mp, kp, lo, ny.as<float>());
+    OSTEO_CUDA(cudaGetLastError());
+    CUtensorMap tx, ty;
+    OSTEO_TRY(make_tmap_bf16(&tx, xb.p, np, 2 * kp, 2 * kp, BM));
+    OSTEO_TRY(make_tmap_bf16(&ty, yb.p, mp, 2 * kp, 2 * kp, BM));
+    auto gram = [&](const CUtensorMap& ta, const CUtensorMap& tb, const float* na, const float* nb, long long rb, long long re, long long cols, bool symmetric,
+                    double* acc) -> int {
+        if (re <= rb) return 0;
+        GemmParams p;
+        std::memset(&p, 0, sizeof p);
+        p.tma_a[0] = p.tma_a[1] = ta;
+        p.tma_b[0] = p.tma_b[1] = tb;
+        OSTEO_TRY(add_segments(p, 0, 0, kp, 0, kp, kp, x3));
+        p.M = static_cast<int>(re);
+        p.N = static_cast<int>(cols);
+        p.m_tile0 = static_cast<int>(rb / BM);
+        p.m_tiles = static_cast<int>((re - rb + BM - 1) / BM);
+        p.n_tiles = static_cast<int>((cols + BN - 1) / BN);
+        p.status = status.as<int>();
+        p.norm_a = na;
+        p.norm_b = nb;
+        p.rbf_gamma = gamma;
+        p.rbf_symmetric = symmetric ? 1 : 0;
+        p.rbf_acc = acc;
+        return launch_gemm(EPI_RBF, 64, p, sms, s);
+    };
+    // K(X,X) rows [row_begin,row_end): the symmetric half-Gram is only valid when this call owns every row
+    OSTEO_TRY(gram(tx, tx, nx.as<float>(), nx.as<float>(), row_begin, row_end, n, row_begin == 0 && row_end == n, sums_dev + 0));
+    OSTEO_TRY(gram(ty, ty, ny.as<float>(), ny.as<float>(), yrow_begin, yrow_end, m, yrow_begin == 0 && yrow_end == m, sums_dev + 1));
+    OSTEO_TRY(gram(tx, ty, nx.as<float>(), ny.as<float>(), row_begin, row_end, m, false, sums_dev + 2));
+    int h = 0;
+    OSTEO_CUDA(cudaMemcpyAsync(&h, status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    OSTEO_CUDA(cudaStreamSynchronize(s));
+    if (h != 0) return fail("tcgen05 pipeline error %d in mmd_partial", h);
+    return 0;
 }
 
 int osteo_corr_moments(const float* data_dev, long long n, int ld, const int* cols_dev, int k, const float* shift_dev, long long row_begin, long long row_end,
                        double* out_dev, void* stream) {
-    return fail("osteo_corr_moments: not built yet");
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (k <= 0 || k > 32) return fail("corr_moments: k=%d outside [1, 32]", k);
+    if (row_begin < 0 || row_end > n || row_begin > row_end) return fail("corr_moments: bad row range");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OSTEO_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * (1 + k + k * k), s));
+    if (row_end == row_begin) return 0;
+    long long warps = row_end - row_begin;
+    const int sms = current_sms();
+    long long blocks = (warps + 7) / 8;
+    if (blocks > sms * 8LL) blocks = sms * 8LL;
+    corr_moments_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(data_dev, ld, cols_dev, k, shift_dev, row_begin, row_end, out_dev);
+    OSTEO_CUDA(cudaGetLastError());
+    return 0;
 }
 
 }  // extern "C"

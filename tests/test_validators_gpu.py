@@ -1,0 +1,104 @@
+"""GPU: MMD / pathway coherence / mutation-pathway correlation against the reference's own outputs (golden) and the numpy oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import validators_oracle as V
+from osteosarcoma_diffusionmodel_b200.validation import BiologicalValidator
+from tests.test_validators_oracle import _mmd_inputs, coherence_inputs, mutexpr_inputs
+
+pytestmark = pytest.mark.gpu
+
+CONFIG = {"evaluation": {"driver_genes": ["TP53"], "mutually_exclusive_pairs": [],
+                         "required_correlations": [{"mutation": "TP53", "pathway": "HALLMARK_P53_PATHWAY", "direction": "negative"},
+                                                   {"mutation": "MYC", "pathway": "HALLMARK_MYC_TARGETS_V1", "direction": "positive"}]}}
+
+
+def test_mmd_matches_reference_golden(golden_dir):
+    g = np.load(golden_dir / "validators.npz")
+    val = BiologicalValidator(CONFIG)
+    rs = np.random.RandomState(11)
+    for tag in ("small", "wide"):
+        n, m, d = (int(v) for v in g[f"mmd_{tag}_shape"])
+        X, Y = _mmd_inputs(n, m, d, rs)
+        assert abs(val.compute_mmd(X, Y) - float(g[f"mmd_{tag}"])) < 1e-4 * float(g[f"mmd_{tag}"])          # fp32 tolerance: rel 1e-4
+        assert abs(val.compute_mmd(X, Y, gamma=0.5 / d) - float(g[f"mmd_{tag}_gamma2"])) < 1e-4 * float(g[f"mmd_{tag}_gamma2"])
+        assert val.compute_mmd(X, X) < 2e-4        # reference: exactly 0.0; ours: sqrt of an O(1e-8) cancellation residue
+    bf = BiologicalValidator(CONFIG, precision="bf16")
+    X, Y = _mmd_inputs(150, 120, 64, np.random.RandomState(11))
+    assert abs(bf.compute_mmd(X, Y) - float(g["mmd_small"])) < 2e-2 * float(g["mmd_small"])
+
+
+@pytest.mark.parametrize("n,m,d", [(1, 1, 8), (129, 300, 70), (1000, 777, 5142), (2048, 2048, 256)])
+def test_mmd_matches_oracle_ragged_shapes(n, m, d):
+    rs = np.random.RandomState(n + m)
+    X = (rs.standard_normal((n, d)) * 0.9 + 4.0).astype(np.float32)      # un-centred, expression-scale offset
+    Y = (rs.standard_normal((m, d)) * 1.2 + 4.1).astype(np.float32)
+    ref = V.compute_mmd(X, Y)
+    got = BiologicalValidator(CONFIG).compute_mmd(X, Y)
+    assert abs(got - ref) < 1e-4 * max(ref, 1e-3)
+    # the three Gram sums themselves
+    from osteosarcoma_diffusionmodel_b200 import validation as val
+    Xt, Yt = torch.from_numpy(X).cuda(), torch.from_numpy(Y).cuda()
+    center = ((Xt.sum(0, dtype=torch.float64) + Yt.sum(0, dtype=torch.float64)) / (n + m)).float()
+    sums = val._gram_partial_sums(Xt, Yt, 1.0 / d, center, (0, n), (0, m), 1).cpu().numpy()
+    ref_sums = np.array(V.rbf_sums(X.astype(np.float64), Y.astype(np.float64), 1.0 / d))
+    assert np.allclose(sums, ref_sums, rtol=2e-5)
+
+
+def test_mmd_row_sharding_sums_to_the_whole():
+    """Emulate 3 ranks on one GPU: partial sums over 128-aligned row shards add up to the single-call result (§8e)."""
+    from osteosarcoma_diffusionmodel_b200 import distributed as D, validation as val
+    rs = np.random.RandomState(7)
+    n, m, d = 700, 450, 96
+    X = torch.from_numpy(rs.standard_normal((n, d)).astype(np.float32)).cuda()
+    Y = torch.from_numpy((rs.standard_normal((m, d)) + 0.2).astype(np.float32)).cuda()
+    center = ((X.sum(0) + Y.sum(0)) / (n + m)).contiguous()
+    whole = val._gram_partial_sums(X, Y, 1.0 / d, center, (0, n), (0, m), 1)
+    parts = sum(val._gram_partial_sums(X, Y, 1.0 / d, center, D.shard_rows(n, r, 3, 128), D.shard_rows(m, r, 3, 128), 1) for r in range(3))
+    assert torch.allclose(whole, parts, rtol=1e-6)
+
+
+def test_pathway_coherence_matches_reference_golden(golden_dir):
+    import pandas as pd
+    g = np.load(golden_dir / "validators.npz")
+    real, syn, members = coherence_inputs(g)
+    n_genes = real.shape[1]
+    genes = [f"G{i}" for i in range(n_genes)]
+    gpm = pd.DataFrame(0, index=genes, columns=[f"P{p}" for p in range(12)])
+    for p, idx in enumerate(members):
+        gpm.iloc[idx, p] = 1
+    gpm.iloc[[0, 1], 10] = 1      # an 11th pathway that must be ignored (only the first 10 count)
+    val = BiologicalValidator(CONFIG)
+    res = val.validate_pathway_coherence(pd.DataFrame(real, columns=genes), pd.DataFrame(syn, columns=genes), gpm)
+    for k in ("real_pathway_coherence", "synthetic_pathway_coherence", "pathway_coherence_correlation"):
+        assert abs(res[k] - float(g[f"coh_{k}"])) < 1e-6, k
+    res2 = val.pathway_coherence_from_tensors(torch.from_numpy(real), torch.from_numpy(syn), members)
+    assert res2 == pytest.approx(res, abs=1e-12)
+    assert val.validate_pathway_coherence(pd.DataFrame(real[:, :2], columns=genes[:2]), pd.DataFrame(syn[:, :2], columns=genes[:2]), gpm) == {}
+
+
+def test_mutation_expression_matches_reference_golden(golden_dir):
+    import pandas as pd
+    g = np.load(golden_dir / "validators.npz")
+    mut, path = mutexpr_inputs()
+    mdf = pd.DataFrame(mut, columns=["TP53", "MYC"])
+    pdf = pd.DataFrame(path, columns=["HALLMARK_P53_PATHWAY", "HALLMARK_MYC_TARGETS_V1"])
+    val = BiologicalValidator(CONFIG)
+    res = val.validate_mutation_expression_correlation(mdf, pd.DataFrame(), pdf)
+    assert res["mutation_expression_violation_rate"] == float(g["mutexpr_violation_rate"])
+    assert val.validate_mutation_expression_correlation(mdf[["MYC"]], pd.DataFrame(), pdf[["HALLMARK_P53_PATHWAY"]]) == {}
+
+
+def test_moments_large_cohort_against_numpy():
+    from osteosarcoma_diffusionmodel_b200 import validation as val
+    rs = np.random.RandomState(3)
+    n = 200_000
+    data = (rs.standard_normal((n, 40)) * 2 + 6).astype(np.float32)
+    data[:, 5] = 0.7 * data[:, 3] + 0.3 * data[:, 5]
+    cols = [3, 5, 17, 39, 0]
+    t = torch.from_numpy(data).cuda()
+    mom = val._moments(t, cols, t[0, cols].contiguous(), (0, n)).cpu().numpy()
+    corr = val._corr_from_moments(mom, len(cols))
+    ref = np.corrcoef(data[:, cols].astype(np.float64), rowvar=False)
+    assert np.abs(corr - ref).max() < 1e-9
