@@ -133,7 +133,7 @@ int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long 
     if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
     if (n <= 0 || m <= 0 || d <= 0) return fail("mmd_partial: bad shape");
     if (row_begin < 0 || row_end > n || row_begin > row_end || yrow_begin < 0 || yrow_end > m || yrow_begin > yrow_end) return fail("mmd_partial: bad row range");
-    if (row_begin % BM != 0 || yrow_begin % BM != 0) return fail("mmd_partial: shard starts must be multiples of %d", BM);
+    if ((row_begin < row_end && row_begin % BM != 0) || (yrow_begin < yrow_end && yrow_begin % BM != 0)) return fail("mmd_partial: shard starts must be multiples of %d", BM);
     if (n > 2000000000LL || m > 2000000000LL) return fail("mmd_partial: more than 2^31 rows");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int sms = current_sms();

@@ -26,7 +26,7 @@ def _to_device(a, device) -> torch.Tensor:
     if hasattr(a, "values") and not isinstance(a, torch.Tensor):
         a = a.values
     if isinstance(a, np.ndarray):
-        a = torch.from_numpy(np.ascontiguousarray(a))
+        a = torch.from_numpy(np.array(a, copy=True) if not a.flags.writeable else np.ascontiguousarray(a))
     return a.to(device=device, dtype=torch.float32).contiguous()
 
 
