@@ -45,7 +45,7 @@ def words(seed: int, rows: np.ndarray, ncol4: int, stream: int, step: int) -> np
 
 
 def u01(w: np.ndarray) -> np.ndarray:
-    """24-bit uniform in (0, 1), exact in fp32 (csrc/philox.cuh u01)."""
+    """24-bit uniform in (0, 1] (never 0), same fp32 rounding as csrc/philox.cuh u01."""
     return ((w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24) + np.float32(2.0 ** -25)).astype(np.float32)
 
 

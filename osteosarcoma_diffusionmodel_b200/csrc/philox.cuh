@@ -36,7 +36,7 @@ __device__ __forceinline__ uint4 philox_words(uint64_t seed, uint64_t row, uint3
     return philox4x32_10(ctr, key);
 }
 
-// 24-bit uniform strictly inside (0,1): exactly representable in fp32.
+// 24-bit uniform in (0, 1] (never 0, so the log is finite; the largest value rounds to 1.0f).
 __device__ __forceinline__ float u01(uint32_t w) { return static_cast<float>(w >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f; }
 
 // Box-Muller on hardware approximations (lg2 / sqrt / sin / cos MUFU ops).
