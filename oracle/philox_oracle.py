@@ -44,19 +44,26 @@ def words(seed: int, rows: np.ndarray, ncol4: int, stream: int, step: int) -> np
     return philox4x32_10(ctr, key)
 
 
+def unit_1_2(w: np.ndarray) -> np.ndarray:
+    """Mantissa trick of csrc/philox.cuh: float32 in [1, 2) from the top 23 bits."""
+    return (np.uint32(0x3F800000) | (w >> np.uint32(9))).astype(np.uint32).view(np.float32)
+
+
 def u01(w: np.ndarray) -> np.ndarray:
-    """24-bit uniform in (0, 1] (never 0), same fp32 rounding as csrc/philox.cuh u01."""
-    return ((w >> np.uint32(8)).astype(np.float32) * np.float32(2.0 ** -24) + np.float32(2.0 ** -25)).astype(np.float32)
+    """23-bit uniform in [0, 1) (dropout draws); exact in fp32."""
+    return (unit_1_2(w) - np.float32(1.0)).astype(np.float32)
 
 
 def normals(seed: int, rows: np.ndarray, d: int, stream: int, step: int) -> np.ndarray:
     """fp64-evaluated Box-Muller on the same words: float64 [len(rows), d]."""
     ncol4 = (d + 3) // 4
     w = words(seed, rows, ncol4, stream, step)
-    u = u01(w).astype(np.float64)
-    r0 = np.sqrt(-2.0 * np.log(u[..., 0]))
-    r1 = np.sqrt(-2.0 * np.log(u[..., 2]))
-    t0 = 2.0 * np.pi * u[..., 1]
-    t1 = 2.0 * np.pi * u[..., 3]
+    f = unit_1_2(w)
+    u_r = (np.float32(2.0) - f).astype(np.float64)        # (0, 1]: radius uniforms (words 0 and 2)
+    u_a = (f - np.float32(1.0)).astype(np.float64)        # [0, 1): angle uniforms (words 1 and 3)
+    r0 = np.sqrt(-2.0 * np.log(u_r[..., 0]))
+    r1 = np.sqrt(-2.0 * np.log(u_r[..., 2]))
+    t0 = 2.0 * np.pi * u_a[..., 1]
+    t1 = 2.0 * np.pi * u_a[..., 3]
     z = np.stack([r0 * np.cos(t0), r0 * np.sin(t0), r1 * np.cos(t1), r1 * np.sin(t1)], axis=-1)
     return z.reshape(len(rows), ncol4 * 4)[:, :d]

@@ -32,6 +32,9 @@ inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m
 // 128-byte swizzle (matches make_kmajor_sw128_desc). Out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
+// fp32 row-major [rows, cols] (ld in elements); box = box_rows x 32 columns (128-byte rows), 128-byte swizzle.
+int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
 int sm_count(int device);
 
 // Device buffer owned by the context.

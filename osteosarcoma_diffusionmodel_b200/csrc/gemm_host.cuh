@@ -9,13 +9,13 @@ template <int EPI, int GW, bool MN = false>
 int launch_gemm_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
-        OSTEO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, GW, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_BYTES));
+        OSTEO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, GW, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<EPI>()));
         configured = true;
     }
     const int tiles = (MN ? p.splits : 1) * p.m_tiles * p.n_tiles;
     if (tiles <= 0) return 0;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<EPI, GW, MN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, stream>>>(p);
+    gemm_tc_kernel<EPI, GW, MN><<<grid, GEMM_THREADS, gemm_smem_bytes<EPI>(), stream>>>(p);
     OSTEO_CUDA(cudaGetLastError());
     return 0;
 }

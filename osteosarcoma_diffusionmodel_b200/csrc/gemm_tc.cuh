@@ -24,13 +24,23 @@ namespace osteo {
 constexpr int BM = 128;
 constexpr int BN = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 6;
+constexpr int STAGES_DEFAULT = 6;
+constexpr int STAGES_DDPM = 3;            // K = 256 only: the freed shared memory stages the fp32 state tile instead
+constexpr int X_BOX_COLS = 32;            // 32 fp32 = 128 B rows (SWIZZLE_128B)
+constexpr int X_BOX_BYTES = BM * X_BOX_COLS * 4;          // 16 KB: [128 rows x 32 cols]
+constexpr int X_TILE_BYTES = (BN / X_BOX_COLS) * X_BOX_BYTES;   // 64 KB: 4 boxes
+constexpr int X_BUFFERS = 2;
 constexpr int NUM_ACC = 4;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int B_TILE_BYTES = BN * BK * 2;
-constexpr int GEMM_SMEM_BYTES = STAGES * (A_TILE_BYTES + B_TILE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+template <int EPI>
+__host__ __device__ constexpr int stages_of() { return EPI == 2 /*EPI_DDPM*/ ? STAGES_DDPM : STAGES_DEFAULT; }
+template <int EPI>
+__host__ __device__ constexpr int gemm_smem_bytes() {
+    return stages_of<EPI>() * (A_TILE_BYTES + B_TILE_BYTES) + (EPI == 2 ? X_BUFFERS * X_TILE_BYTES : 0) + 1024 /*align*/ + 256 /*barriers*/;
+}
 constexpr int MAX_KSEG = 8;
 
 enum EpiKind : int {
@@ -57,6 +67,8 @@ struct KSeg {
 struct GemmParams {
     CUtensorMap tma_a[2];
     CUtensorMap tma_b[2];
+    CUtensorMap tma_x_ld;     // EPI_DDPM: fp32 state, box 128 rows x 32 cols (load)
+    CUtensorMap tma_x_st;     // EPI_DDPM: fp32 state, box  32 rows x 32 cols (per-warp store)
     int M, N;                 // valid rows / valid output columns
     int m_tiles, n_tiles;     // tiles this launch covers: m blocks [m_tile0, m_tile0 + m_tiles)
     int m_tile0;
@@ -192,13 +204,18 @@ template <int EPI, int GW, bool MN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    constexpr int STAGES = stages_of<EPI>();
+    constexpr bool XSTAGE = (EPI == EPI_DDPM);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES));
+    uint8_t* smem_x = smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES);      // 1024-aligned: stages are multiples of 32 KB
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_x + (XSTAGE ? X_BUFFERS * X_TILE_BYTES : 0));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + NUM_ACC;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + NUM_ACC);
+    uint64_t* xfull_bar = tempty_bar + NUM_ACC;
+    uint64_t* xempty_bar = xfull_bar + X_BUFFERS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty_bar + X_BUFFERS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -208,6 +225,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         tma_prefetch_desc(&p.tma_a[1]);
         tma_prefetch_desc(&p.tma_b[0]);
         tma_prefetch_desc(&p.tma_b[1]);
+        if (XSTAGE) {
+            tma_prefetch_desc(&p.tma_x_ld);
+            tma_prefetch_desc(&p.tma_x_st);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
@@ -217,6 +238,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         for (int i = 0; i < NUM_ACC; ++i) {
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], NUM_EPI_WARPS);
+        }
+        for (int i = 0; i < X_BUFFERS; ++i) {
+            mbar_init(&xfull_bar[i], 1);
+            mbar_init(&xempty_bar[i], NUM_EPI_WARPS);
         }
         fence_mbar_init();
     }
@@ -233,10 +258,22 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            int xit = 0;
             bool ok = true;
             for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
                 const TileInfo ti = decode_tile<EPI, MN>(p, tile);
                 if (ti.skip) continue;
+                if (XSTAGE) {
+                    // fp32 state tile of this output tile: 4 boxes of [128 rows x 32 cols], double buffered
+                    const int xb = xit & 1;
+                    const uint32_t xphase = static_cast<uint32_t>(xit >> 1) & 1u;
+                    ++xit;
+                    if (!mbar_wait(&xempty_bar[xb], xphase ^ 1u)) { ok = false; break; }
+                    mbar_arrive_expect_tx(&xfull_bar[xb], X_TILE_BYTES);
+#pragma unroll
+                    for (int b = 0; b < BN / X_BOX_COLS; ++b)
+                        tma_load_2d(&p.tma_x_ld, smem_x + xb * X_TILE_BYTES + b * X_BOX_BYTES, &xfull_bar[xb], ti.n_blk * BN + b * X_BOX_COLS, ti.m_blk * BM);
+                }
                 for (int s = 0; s < p.nseg && ok; ++s) {
                     const KSeg sg = p.seg[s];
                     const CUtensorMap* ta = &p.tma_a[sg.a_sel];
@@ -341,7 +378,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
             const int row = ti.m_blk * BM + q * 32 + lane;
             const int col = ti.n_blk * BN + half * 64;
-            Epilogue<EPI>::template run<GW>(p, row, col, v0, v1, thread_acc);
+            if constexpr (XSTAGE) {
+                const int xb = (it - 1) & 1;
+                const uint32_t xphase = static_cast<uint32_t>((it - 1) >> 1) & 1u;
+                if (!mbar_wait(&xfull_bar[xb], xphase)) { ok = false; break; }
+                uint8_t* xt = smem_x + xb * X_TILE_BYTES;
+                Epilogue<EPI>::run_staged(p, row, col, q * 32 + lane, half, xt, v0, v1);
+                // make this warp's generic-proxy writes visible to the TMA engine, then store its 32 x 64 block
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        const int box = 2 * half + b;
+                        tma_store_2d(&p.tma_x_st, xt + box * X_BOX_BYTES + q * 32 * 128, ti.n_blk * BN + box * X_BOX_COLS, ti.m_blk * BM + q * 32);
+                    }
+                    tma_store_commit();
+                    tma_store_wait_read<0>();      // smem may be overwritten once the bulk store has READ it
+                    mbar_arrive(&xempty_bar[xb]);
+                }
+                __syncwarp();
+            } else {
+                Epilogue<EPI>::template run<GW>(p, row, col, v0, v1, thread_acc);
+            }
+        }
+        if constexpr (XSTAGE) {
+            if (lane == 0) tma_store_wait_all<0>();   // all bulk stores complete before the CTA exits
         }
         if (EPI == EPI_MSE || EPI == EPI_RBF) {
             // warp reduce then one atomic per warp
@@ -504,9 +566,115 @@ struct Epilogue<EPI_GN_SILU> {
 
 template <>
 struct Epilogue<EPI_DDPM> {
-    // Reverse step (models/diffusion.py:400-423) collapsed to
-    //   x <- c_x[t]*x - c_eps[t]*eps + sigma[t]*z ,  sigma[0] = 0 (the t == 0 branch returns x0_pred)
-    // with the three fp32 tables derived in fp64 from the reference's fp32 buffers.
+    // Shared-memory staged variant (the one the kernel uses): the fp32 state tile was brought in by TMA as four
+    // [128 rows x 32 cols] boxes with the 128-byte swizzle (16-byte chunk index XOR (row & 7)); this thread owns row
+    // `r_tile` and the two boxes 2*half, 2*half+1. x is updated IN PLACE in shared memory; the caller TMA-stores it.
+    // Global accesses left in here: the bf16 shadow (128 contiguous bytes per thread) and the optional parity hooks.
+    // MASKED: the 64-column span crosses N (last column tile only). INJECT: z / eps hooks of the parity runs.
+    template <bool MASKED, bool INJECT>
+    __device__ static __forceinline__ void process(const GemmParams& p, int row, int col, int r_tile, int half, uint8_t* xt, float (&v0)[32], float (&v1)[32],
+                                                   int t, float cx, float ce, float sg) {
+        const int sw = r_tile & 7;
+        const uint64_t grow = static_cast<uint64_t>(p.row_base + row);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            float(&v)[32] = h ? v1 : v0;
+            const int c0 = col + 32 * h;
+            if (MASKED && c0 >= p.N) break;
+            uint8_t* xrow = xt + (2 * half + h) * X_BOX_BYTES + r_tile * 128;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const int c = c0 + 4 * j4;
+                float4* xp = reinterpret_cast<float4*>(xrow + ((j4 ^ sw) << 4));
+                if (MASKED && c >= p.N) {
+                    *xp = make_float4(0.f, 0.f, 0.f, 0.f);
+                    v[4 * j4 + 0] = v[4 * j4 + 1] = v[4 * j4 + 2] = v[4 * j4 + 3] = 0.f;
+                    continue;
+                }
+                float e[4];
+                if (MASKED) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) e[i] = (c + i < p.N) ? v[4 * j4 + i] + __ldg(p.bias + c + i) : 0.0f;
+                } else {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                    e[0] = v[4 * j4 + 0] + b4.x;
+                    e[1] = v[4 * j4 + 1] + b4.y;
+                    e[2] = v[4 * j4 + 2] + b4.z;
+                    e[3] = v[4 * j4 + 3] + b4.w;
+                }
+                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (INJECT) {
+                    if (p.eps_out) {
+                        float* eo = p.eps_out + static_cast<size_t>(row) * p.eps_ld + c;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (c + i < p.N) eo[i] = e[i];
+                    }
+                    if (p.noise && sg != 0.0f) {
+                        const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c;
+                        z.x = nz[0];
+                        if (c + 1 < p.N) z.y = nz[1];
+                        if (c + 2 < p.N) z.z = nz[2];
+                        if (c + 3 < p.N) z.w = nz[3];
+                    } else if (sg != 0.0f) {
+                        z = philox_normal4(p.seed, grow, static_cast<uint32_t>(c >> 2), STREAM_REVERSE, static_cast<uint32_t>(t));
+                    }
+                } else {
+                    if (sg != 0.0f) z = philox_normal4(p.seed, grow, static_cast<uint32_t>(c >> 2), STREAM_REVERSE, static_cast<uint32_t>(t));
+                }
+                const float4 xv = *xp;
+                float4 xn;
+                xn.x = fmaf(sg, z.x, fmaf(cx, xv.x, -ce * e[0]));
+                xn.y = fmaf(sg, z.y, fmaf(cx, xv.y, -ce * e[1]));
+                xn.z = fmaf(sg, z.z, fmaf(cx, xv.z, -ce * e[2]));
+                xn.w = fmaf(sg, z.w, fmaf(cx, xv.w, -ce * e[3]));
+                if (MASKED) {
+                    if (c + 1 >= p.N) xn.y = 0.0f;
+                    if (c + 2 >= p.N) xn.z = 0.0f;
+                    if (c + 3 >= p.N) xn.w = 0.0f;
+                }
+                *xp = xn;
+                v[4 * j4 + 0] = xn.x;
+                v[4 * j4 + 1] = xn.y;
+                v[4 * j4 + 2] = xn.z;
+                v[4 * j4 + 3] = xn.w;
+            }
+            if (p.xb) {
+                __nv_bfloat16* xbrow = p.xb + static_cast<size_t>(row) * p.xb_ld + c0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (MASKED && c0 + 8 * j >= p.N) break;
+                    uint4 u;
+                    u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
+                    u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
+                    u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
+                    u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
+                    reinterpret_cast<uint4*>(xbrow)[j] = u;
+                    if (p.xb_lo_off > 0) {
+                        uint4 l;
+                        l.x = pack_bf16x2(v[8 * j + 0] - bf16_round(v[8 * j + 0]), v[8 * j + 1] - bf16_round(v[8 * j + 1]));
+                        l.y = pack_bf16x2(v[8 * j + 2] - bf16_round(v[8 * j + 2]), v[8 * j + 3] - bf16_round(v[8 * j + 3]));
+                        l.z = pack_bf16x2(v[8 * j + 4] - bf16_round(v[8 * j + 4]), v[8 * j + 5] - bf16_round(v[8 * j + 5]));
+                        l.w = pack_bf16x2(v[8 * j + 6] - bf16_round(v[8 * j + 6]), v[8 * j + 7] - bf16_round(v[8 * j + 7]));
+                        reinterpret_cast<uint4*>(xbrow + p.xb_lo_off)[j] = l;
+                    }
+                }
+            }
+        }
+    }
+
+    __device__ static __forceinline__ void run_staged(const GemmParams& p, int row, int col, int r_tile, int half, uint8_t* xt, float (&v0)[32], float (&v1)[32]) {
+        if (row >= p.M) return;            // rows past the batch: leave the staged tile as loaded
+        const int t = *p.step;
+        const float cx = __ldg(p.coef_x + t), ce = __ldg(p.coef_eps + t), sg = __ldg(p.coef_sigma + t);
+        const bool masked = col + 64 > p.N;                       // warp-uniform
+        const bool inject = p.noise != nullptr || p.eps_out != nullptr;   // kernel-uniform
+        if (!masked && !inject) process<false, false>(p, row, col, r_tile, half, xt, v0, v1, t, cx, ce, sg);
+        else if (!masked) process<false, true>(p, row, col, r_tile, half, xt, v0, v1, t, cx, ce, sg);
+        else process<true, true>(p, row, col, r_tile, half, xt, v0, v1, t, cx, ce, sg);
+    }
+
+    // Direct-to-global variant (kept for reference / fallback-free comparison in tests of the math; not launched).
     template <int GW>
     __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double&) {
         if (row >= p.M) return;

@@ -59,6 +59,20 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
     return 0;
 }
 
+int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 4) % 16 != 0) return fail("tensor map operand not 16-byte aligned");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 4};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(X_BOX_COLS), box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (fp32) failed with CUresult %d", static_cast<int>(r));
+    return 0;
+}
+
 int sm_count(int device) {
     int n = 0;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return 0;
@@ -161,6 +175,7 @@ struct osteo_ddpm_ctx {
 
     // workspace (capacity `cap` rows)
     DevBuf x;                            // fp32 [cap, DP]
+    CUtensorMap x_tmap_ld, x_tmap_st;    // TMA views of x: 128x32 load boxes, 32x32 store boxes
     ActBuf xb;                           // bf16 [cap, 2*DP]
     std::vector<std::unique_ptr<ActBuf>> acts;   // [0] = h0, then one per half block
     DevBuf cproj;                        // fp32 [cap, h0]
@@ -320,6 +335,8 @@ static int launch_output_ddpm(osteo_ddpm_ctx* c, long long row0, long long row1,
     p.coef_sigma = c->coef_sigma.as<float>();
     p.x = c->x.as<float>();
     p.x_ld = c->DP;
+    p.tma_x_ld = c->x_tmap_ld;
+    p.tma_x_st = c->x_tmap_st;
     p.xb = c->xb.ptr();
     p.xb_ld = 2 * c->DP;
     p.xb_lo_off = c->lo(c->DP);
@@ -532,6 +549,8 @@ int osteo_ddpm_reserve(osteo_ddpm_ctx* c, long long rows) {
     const long long cap = round_up(rows, BM);
     OSTEO_TRY(c->x.alloc(static_cast<size_t>(cap) * c->DP * 4));
     OSTEO_CUDA(cudaMemset(c->x.p, 0, c->x.bytes));
+    OSTEO_TRY(make_tmap_f32(&c->x_tmap_ld, c->x.p, cap, c->DP, c->DP, BM));
+    OSTEO_TRY(make_tmap_f32(&c->x_tmap_st, c->x.p, cap, c->DP, c->DP, 32));
     OSTEO_TRY(c->xb.init(cap, c->DP));
     OSTEO_CUDA(cudaMemset(c->xb.buf.p, 0, c->xb.buf.bytes));
     OSTEO_TRY(c->cproj.alloc(static_cast<size_t>(cap) * c->h0() * 4));

@@ -36,13 +36,17 @@ __device__ __forceinline__ uint4 philox_words(uint64_t seed, uint64_t row, uint3
     return philox4x32_10(ctr, key);
 }
 
-// 24-bit uniform in (0, 1] (never 0, so the log is finite; the largest value rounds to 1.0f).
-__device__ __forceinline__ float u01(uint32_t w) { return static_cast<float>(w >> 8) * 5.9604644775390625e-8f + 2.98023223876953125e-8f; }
+// 23-bit uniforms built with integer ops only (no I2F on the XU pipe): the mantissa trick gives f in [1, 2).
+__device__ __forceinline__ float unit_1_2(uint32_t w) { return __uint_as_float(0x3f800000u | (w >> 9)); }
+// [0, 1): used for Bernoulli draws (dropout keep-masks).
+__device__ __forceinline__ float u01(uint32_t w) { return unit_1_2(w) - 1.0f; }
 
-// Box-Muller on hardware approximations (lg2 / sqrt / sin / cos MUFU ops).
+// Box-Muller on the MUFU approximations (lg2 / sqrt / sin / cos). u1 = 2 - f is in (0, 1] (never 0: the log is finite),
+// u2 = f - 1 is in [0, 1); both are exact in fp32, so the fp64 oracle sees the same uniforms.
 __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, float& z1) {
-    const float u1 = u01(w0), u2 = u01(w1);
-    const float r = __fsqrt_rn(-1.3862943611198906f * __log2f(u1));   // sqrt(-2 ln u1)
+    const float u1 = 2.0f - unit_1_2(w0), u2 = unit_1_2(w1) - 1.0f;
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u1)));   // sqrt(-2 ln u1)
     float s, c;
     __sincosf(6.283185307179586f * u2, &s, &c);
     z0 = r * c;

@@ -22,7 +22,7 @@ def test_counter_layout_and_uniforms():
     direct = P.philox4x32_10(np.array([1, 3, 1, (2 << 16) | 999], dtype=np.uint32), np.array([5, 7], dtype=np.uint32))
     assert np.array_equal(w[1, 1], direct)
     u = P.u01(np.array([0, 0xFFFFFFFF], dtype=np.uint32))
-    assert 0.0 < u[0] < u[1] <= 1.0      # never 0 (log is finite); the top value rounds to exactly 1.0 in fp32
+    assert u[0] == 0.0 and 0.999 < u[1] < 1.0      # [0, 1); the radius uniform is 2 - f in (0, 1], never 0
 
 
 def test_normals_have_unit_moments():
