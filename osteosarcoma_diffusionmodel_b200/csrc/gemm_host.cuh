@@ -15,7 +15,7 @@ int launch_gemm_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
     const int tiles = (MN ? p.splits : 1) * p.m_tiles * p.n_tiles;
     if (tiles <= 0) return 0;
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<EPI, GW, MN><<<grid, GEMM_THREADS, gemm_smem_bytes<EPI>(), stream>>>(p);
+    gemm_tc_kernel<EPI, GW, MN><<<grid, gemm_threads<EPI>(), gemm_smem_bytes<EPI>(), stream>>>(p);
     OSTEO_CUDA(cudaGetLastError());
     return 0;
 }

@@ -31,8 +31,12 @@ constexpr int X_BOX_BYTES = BM * X_BOX_COLS * 4;          // 16 KB: [128 rows x 
 constexpr int X_TILE_BYTES = (BN / X_BOX_COLS) * X_BOX_BYTES;   // 64 KB: 4 boxes
 constexpr int X_BUFFERS = 2;
 constexpr int NUM_ACC = 4;
-constexpr int NUM_EPI_WARPS = 8;
-constexpr int GEMM_THREADS = 128 + NUM_EPI_WARPS * 32;
+// Epilogue warps: 8 (thread <-> row x 64 columns: a whole GroupNorm group per thread) except for the RNG-heavy
+// reverse-update epilogue, which runs 16 (thread <-> row x 32 columns) to double the warps per scheduler.
+template <int EPI>
+__host__ __device__ constexpr int epi_warps_of() { return EPI == 2 /*EPI_DDPM*/ ? 16 : 8; }
+template <int EPI>
+__host__ __device__ constexpr int gemm_threads() { return 128 + 32 * epi_warps_of<EPI>(); }
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int B_TILE_BYTES = BN * BK * 2;
 template <int EPI>
@@ -201,11 +205,12 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
 }
 
 template <int EPI, int GW, bool MN = false>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     constexpr int STAGES = stages_of<EPI>();
     constexpr bool XSTAGE = (EPI == EPI_DDPM);
+    constexpr int NUM_EPI_WARPS = epi_warps_of<EPI>();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
     uint8_t* smem_x = smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES);      // 1024-aligned: stages are multiples of 32 KB
@@ -355,50 +360,65 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access
-        const int half = (warp - 4) >> 2;       // which 64-column half of the tile
+        const int part = (warp - 4) >> 2;       // which 64-column half (8 warps) / 32-column quarter (16 warps) of the tile
+        constexpr int CPT = BN / (NUM_EPI_WARPS / 4);   // accumulator columns per thread
         int it = 0;
         bool ok = true;
         double thread_acc = 0.0;                // EPI_MSE / EPI_RBF partial sums
+        int ddpm_t = 0;
+        float ddpm_cx = 0.f, ddpm_ce = 0.f, ddpm_sg = 0.f;
+        if constexpr (XSTAGE) {                 // timestep and its three coefficients: once per kernel, not once per tile
+            ddpm_t = *p.step;
+            ddpm_cx = __ldg(p.coef_x + ddpm_t);
+            ddpm_ce = __ldg(p.coef_eps + ddpm_t);
+            ddpm_sg = __ldg(p.coef_sigma + ddpm_t);
+        }
         for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
             const TileInfo ti = decode_tile<EPI, MN>(p, tile);
             if (ti.skip) continue;
             const int acc = it % NUM_ACC;
             const uint32_t acc_phase = static_cast<uint32_t>(it / NUM_ACC) & 1u;
             ++it;
-            if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
-            tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + half * 64);
-            float v0[32], v1[32];
-            tmem_ld_32(taddr, v0);
-            tmem_ld_32(taddr + 32, v1);
-            // accumulator is in registers: hand the TMEM stage back to the MMA warp
-            tc_fence_before_sync();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + part * CPT);
             const int row = ti.m_blk * BM + q * 32 + lane;
-            const int col = ti.n_blk * BN + half * 64;
+            const int col = ti.n_blk * BN + part * CPT;
             if constexpr (XSTAGE) {
+                // The noise of this tile depends only on (row, column, t): draw it BEFORE waiting for the accumulator and the
+                // staged state tile, so the Philox / Box-Muller instruction stream hides those waits.
+                float z[32];
+                Epilogue<EPI>::draw_noise(p, row, col, ddpm_t, ddpm_sg, z);
+                if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
+                tc_fence_after_sync();
+                float v[32];
+                tmem_ld_32(taddr, v);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 const int xb = (it - 1) & 1;
                 const uint32_t xphase = static_cast<uint32_t>((it - 1) >> 1) & 1u;
                 if (!mbar_wait(&xfull_bar[xb], xphase)) { ok = false; break; }
                 uint8_t* xt = smem_x + xb * X_TILE_BYTES;
-                Epilogue<EPI>::run_staged(p, row, col, q * 32 + lane, half, xt, v0, v1);
-                // make this warp's generic-proxy writes visible to the TMA engine, then store its 32 x 64 block
+                Epilogue<EPI>::run_staged(p, row, col, q * 32 + lane, xt + part * X_BOX_BYTES, v, z, ddpm_cx, ddpm_ce, ddpm_sg);
+                // make this warp's generic-proxy writes visible to the TMA engine, then store its 32 x 32 block
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
-#pragma unroll
-                    for (int b = 0; b < 2; ++b) {
-                        const int box = 2 * half + b;
-                        tma_store_2d(&p.tma_x_st, xt + box * X_BOX_BYTES + q * 32 * 128, ti.n_blk * BN + box * X_BOX_COLS, ti.m_blk * BM + q * 32);
-                    }
+                    tma_store_2d(&p.tma_x_st, xt + part * X_BOX_BYTES + q * 32 * 128, ti.n_blk * BN + part * X_BOX_COLS, ti.m_blk * BM + q * 32);
                     tma_store_commit();
                     tma_store_wait_read<0>();      // smem may be overwritten once the bulk store has READ it
                     mbar_arrive(&xempty_bar[xb]);
                 }
                 __syncwarp();
             } else {
+                if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
+                tc_fence_after_sync();
+                float v0[32], v1[32];
+                tmem_ld_32(taddr, v0);
+                tmem_ld_32(taddr + 32, v1);
+                // accumulator is in registers: hand the TMEM stage back to the MMA warp
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 Epilogue<EPI>::template run<GW>(p, row, col, v0, v1, thread_acc);
             }
         }
@@ -566,190 +586,122 @@ struct Epilogue<EPI_GN_SILU> {
 
 template <>
 struct Epilogue<EPI_DDPM> {
-    // Shared-memory staged variant (the one the kernel uses): the fp32 state tile was brought in by TMA as four
-    // [128 rows x 32 cols] boxes with the 128-byte swizzle (16-byte chunk index XOR (row & 7)); this thread owns row
-    // `r_tile` and the two boxes 2*half, 2*half+1. x is updated IN PLACE in shared memory; the caller TMA-stores it.
-    // Global accesses left in here: the bf16 shadow (128 contiguous bytes per thread) and the optional parity hooks.
-    // MASKED: the 64-column span crosses N (last column tile only). INJECT: z / eps hooks of the parity runs.
-    template <bool MASKED, bool INJECT>
-    __device__ static __forceinline__ void process(const GemmParams& p, int row, int col, int r_tile, int half, uint8_t* xt, float (&v0)[32], float (&v1)[32],
-                                                   int t, float cx, float ce, float sg) {
-        const int sw = r_tile & 7;
+    // Reverse step (models/diffusion.py:400-423) collapsed to
+    //   x <- c_x[t]*x - c_eps[t]*eps + sigma[t]*z ,  sigma[0] = 0 (the t == 0 branch returns x0_pred)
+    // with the three fp32 tables derived in fp64 from the reference's fp32 buffers.
+    // The fp32 state tile was brought in by TMA as four [128 rows x 32 cols] boxes with the 128-byte swizzle (16-byte chunk
+    // index XOR (row & 7)); this thread owns row `r_tile` of ONE box (32 columns). x is updated IN PLACE in shared memory and
+    // the caller TMA-stores the warp's 32 x 32 block. Global accesses left in here: the bf16 shadow (64 contiguous bytes per
+    // thread) and the optional parity hooks.
+    // z for this thread's (row, 32 columns): injected tensor (parity runs) or Philox4x32-10 + Box-Muller.
+    __device__ static __forceinline__ void draw_noise(const GemmParams& p, int row, int c0, int t, float sg, float (&z)[32]) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) z[j] = 0.0f;
+        if (row >= p.M || c0 >= p.N || sg == 0.0f) return;
+        if (p.noise) {
+            const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (c0 + j < p.N) z[j] = nz[j];
+            return;
+        }
         const uint64_t grow = static_cast<uint64_t>(p.row_base + row);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float(&v)[32] = h ? v1 : v0;
-            const int c0 = col + 32 * h;
-            if (MASKED && c0 >= p.N) break;
-            uint8_t* xrow = xt + (2 * half + h) * X_BOX_BYTES + r_tile * 128;
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-                const int c = c0 + 4 * j4;
-                float4* xp = reinterpret_cast<float4*>(xrow + ((j4 ^ sw) << 4));
-                if (MASKED && c >= p.N) {
-                    *xp = make_float4(0.f, 0.f, 0.f, 0.f);
-                    v[4 * j4 + 0] = v[4 * j4 + 1] = v[4 * j4 + 2] = v[4 * j4 + 3] = 0.f;
-                    continue;
-                }
-                float e[4];
-                if (MASKED) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) e[i] = (c + i < p.N) ? v[4 * j4 + i] + __ldg(p.bias + c + i) : 0.0f;
-                } else {
-                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-                    e[0] = v[4 * j4 + 0] + b4.x;
-                    e[1] = v[4 * j4 + 1] + b4.y;
-                    e[2] = v[4 * j4 + 2] + b4.z;
-                    e[3] = v[4 * j4 + 3] + b4.w;
-                }
-                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (INJECT) {
-                    if (p.eps_out) {
-                        float* eo = p.eps_out + static_cast<size_t>(row) * p.eps_ld + c;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            if (c + i < p.N) eo[i] = e[i];
-                    }
-                    if (p.noise && sg != 0.0f) {
-                        const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c;
-                        z.x = nz[0];
-                        if (c + 1 < p.N) z.y = nz[1];
-                        if (c + 2 < p.N) z.z = nz[2];
-                        if (c + 3 < p.N) z.w = nz[3];
-                    } else if (sg != 0.0f) {
-                        z = philox_normal4(p.seed, grow, static_cast<uint32_t>(c >> 2), STREAM_REVERSE, static_cast<uint32_t>(t));
-                    }
-                } else {
-                    if (sg != 0.0f) z = philox_normal4(p.seed, grow, static_cast<uint32_t>(c >> 2), STREAM_REVERSE, static_cast<uint32_t>(t));
-                }
-                const float4 xv = *xp;
-                float4 xn;
-                xn.x = fmaf(sg, z.x, fmaf(cx, xv.x, -ce * e[0]));
-                xn.y = fmaf(sg, z.y, fmaf(cx, xv.y, -ce * e[1]));
-                xn.z = fmaf(sg, z.z, fmaf(cx, xv.z, -ce * e[2]));
-                xn.w = fmaf(sg, z.w, fmaf(cx, xv.w, -ce * e[3]));
-                if (MASKED) {
-                    if (c + 1 >= p.N) xn.y = 0.0f;
-                    if (c + 2 >= p.N) xn.z = 0.0f;
-                    if (c + 3 >= p.N) xn.w = 0.0f;
-                }
-                *xp = xn;
-                v[4 * j4 + 0] = xn.x;
-                v[4 * j4 + 1] = xn.y;
-                v[4 * j4 + 2] = xn.z;
-                v[4 * j4 + 3] = xn.w;
-            }
-            if (p.xb) {
-                __nv_bfloat16* xbrow = p.xb + static_cast<size_t>(row) * p.xb_ld + c0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (MASKED && c0 + 8 * j >= p.N) break;
-                    uint4 u;
-                    u.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-                    u.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-                    u.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-                    u.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-                    reinterpret_cast<uint4*>(xbrow)[j] = u;
-                    if (p.xb_lo_off > 0) {
-                        uint4 l;
-                        l.x = pack_bf16x2(v[8 * j + 0] - bf16_round(v[8 * j + 0]), v[8 * j + 1] - bf16_round(v[8 * j + 1]));
-                        l.y = pack_bf16x2(v[8 * j + 2] - bf16_round(v[8 * j + 2]), v[8 * j + 3] - bf16_round(v[8 * j + 3]));
-                        l.z = pack_bf16x2(v[8 * j + 4] - bf16_round(v[8 * j + 4]), v[8 * j + 5] - bf16_round(v[8 * j + 5]));
-                        l.w = pack_bf16x2(v[8 * j + 6] - bf16_round(v[8 * j + 6]), v[8 * j + 7] - bf16_round(v[8 * j + 7]));
-                        reinterpret_cast<uint4*>(xbrow + p.xb_lo_off)[j] = l;
-                    }
-                }
-            }
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 g = philox_normal4(p.seed, grow, static_cast<uint32_t>((c0 >> 2) + j4), STREAM_REVERSE, static_cast<uint32_t>(t));
+            z[4 * j4 + 0] = g.x;
+            z[4 * j4 + 1] = g.y;
+            z[4 * j4 + 2] = g.z;
+            z[4 * j4 + 3] = g.w;
         }
     }
 
-    __device__ static __forceinline__ void run_staged(const GemmParams& p, int row, int col, int r_tile, int half, uint8_t* xt, float (&v0)[32], float (&v1)[32]) {
-        if (row >= p.M) return;            // rows past the batch: leave the staged tile as loaded
-        const int t = *p.step;
-        const float cx = __ldg(p.coef_x + t), ce = __ldg(p.coef_eps + t), sg = __ldg(p.coef_sigma + t);
-        const bool masked = col + 64 > p.N;                       // warp-uniform
-        const bool inject = p.noise != nullptr || p.eps_out != nullptr;   // kernel-uniform
-        if (!masked && !inject) process<false, false>(p, row, col, r_tile, half, xt, v0, v1, t, cx, ce, sg);
-        else if (!masked) process<false, true>(p, row, col, r_tile, half, xt, v0, v1, t, cx, ce, sg);
-        else process<true, true>(p, row, col, r_tile, half, xt, v0, v1, t, cx, ce, sg);
-    }
-
-    // Direct-to-global variant (kept for reference / fallback-free comparison in tests of the math; not launched).
-    template <int GW>
-    __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double&) {
-        if (row >= p.M) return;
-        const int t = *p.step;
-        const float cx = __ldg(p.coef_x + t), ce = __ldg(p.coef_eps + t), sg = __ldg(p.coef_sigma + t);
-        float* xrow = p.x + static_cast<size_t>(row) * p.x_ld;
+    // MASKED: the 32-column span crosses N (last column tile only).
+    template <bool MASKED>
+    __device__ static __forceinline__ void process(const GemmParams& p, int row, int c0, int r_tile, uint8_t* xbox, float (&v)[32], const float (&z)[32], float cx,
+                                                   float ce, float sg) {
+        const int sw = r_tile & 7;
+        uint8_t* xrow = xbox + r_tile * 128;
+        float4 xv[8];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float(&v)[32] = h ? v1 : v0;
-            const int c0 = col + 32 * h;
-            if (c0 >= p.N) break;
+        for (int j4 = 0; j4 < 8; ++j4) xv[j4] = *reinterpret_cast<const float4*>(xrow + ((j4 ^ sw) << 4));
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-                const int c = c0 + 4 * j4;
-                if (c >= p.N) break;
-                float e[4];
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const int c = c0 + 4 * j4;
+            if (MASKED && c >= p.N) {
+                xv[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
+            float e[4];
+            if (MASKED) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) e[i] = (c + i < p.N) ? v[4 * j4 + i] + __ldg(p.bias + c + i) : 0.0f;
-                if (p.eps_out) {
-                    float* eo = p.eps_out + static_cast<size_t>(row) * p.eps_ld + c;
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        if (c + i < p.N) eo[i] = e[i];
-                }
-                const float4 xv = *reinterpret_cast<const float4*>(xrow + c);
-                float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (sg != 0.0f) {
-                    if (p.noise) {
-                        const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c;
-                        z.x = nz[0];
-                        if (c + 1 < p.N) z.y = nz[1];
-                        if (c + 2 < p.N) z.z = nz[2];
-                        if (c + 3 < p.N) z.w = nz[3];
-                    } else {
-                        z = philox_normal4(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c >> 2), STREAM_REVERSE, static_cast<uint32_t>(t));
-                    }
-                }
-                float4 xn;
-                xn.x = fmaf(sg, z.x, fmaf(cx, xv.x, -ce * e[0]));
-                xn.y = (c + 1 < p.N) ? fmaf(sg, z.y, fmaf(cx, xv.y, -ce * e[1])) : 0.0f;
-                xn.z = (c + 2 < p.N) ? fmaf(sg, z.z, fmaf(cx, xv.z, -ce * e[2])) : 0.0f;
-                xn.w = (c + 3 < p.N) ? fmaf(sg, z.w, fmaf(cx, xv.w, -ce * e[3])) : 0.0f;
-                *reinterpret_cast<float4*>(xrow + c) = xn;
-                v[4 * j4 + 0] = xn.x;
-                v[4 * j4 + 1] = xn.y;
-                v[4 * j4 + 2] = xn.z;
-                v[4 * j4 + 3] = xn.w;
+            } else {
+                const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+                e[0] = v[4 * j4 + 0] + b4.x;
+                e[1] = v[4 * j4 + 1] + b4.y;
+                e[2] = v[4 * j4 + 2] + b4.z;
+                e[3] = v[4 * j4 + 3] + b4.w;
             }
-            if (p.xb) {
-                // bf16 shadow, 8 elements (16 B) at a time; xb_ld >= round_up(N, 8)
-                __nv_bfloat16* xbrow = p.xb + static_cast<size_t>(row) * p.xb_ld + c0;
+            if (p.eps_out) {
+                float* eo = p.eps_out + static_cast<size_t>(row) * p.eps_ld + c;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (c0 + 8 * j >= p.N) break;
-                    float w[8];
+                for (int i = 0; i < 4; ++i)
+                    if (c + i < p.N) eo[i] = e[i];
+            }
+            float4 xn;
+            xn.x = fmaf(sg, z[4 * j4 + 0], fmaf(cx, xv[j4].x, -ce * e[0]));
+            xn.y = fmaf(sg, z[4 * j4 + 1], fmaf(cx, xv[j4].y, -ce * e[1]));
+            xn.z = fmaf(sg, z[4 * j4 + 2], fmaf(cx, xv[j4].z, -ce * e[2]));
+            xn.w = fmaf(sg, z[4 * j4 + 3], fmaf(cx, xv[j4].w, -ce * e[3]));
+            if (MASKED) {
+                if (c + 1 >= p.N) xn.y = 0.0f;
+                if (c + 2 >= p.N) xn.z = 0.0f;
+                if (c + 3 >= p.N) xn.w = 0.0f;
+            }
+            xv[j4] = xn;
+        }
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) w[i] = (c0 + 8 * j + i < p.N) ? v[8 * j + i] : 0.0f;
-                    uint4 u;
-                    u.x = pack_bf16x2(w[0], w[1]);
-                    u.y = pack_bf16x2(w[2], w[3]);
-                    u.z = pack_bf16x2(w[4], w[5]);
-                    u.w = pack_bf16x2(w[6], w[7]);
-                    reinterpret_cast<uint4*>(xbrow)[j] = u;
-                    if (p.xb_lo_off > 0) {
-                        uint4 l;
-                        l.x = pack_bf16x2(w[0] - bf16_round(w[0]), w[1] - bf16_round(w[1]));
-                        l.y = pack_bf16x2(w[2] - bf16_round(w[2]), w[3] - bf16_round(w[3]));
-                        l.z = pack_bf16x2(w[4] - bf16_round(w[4]), w[5] - bf16_round(w[5]));
-                        l.w = pack_bf16x2(w[6] - bf16_round(w[6]), w[7] - bf16_round(w[7]));
-                        reinterpret_cast<uint4*>(xbrow + p.xb_lo_off)[j] = l;
-                    }
+        for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(xrow + ((j4 ^ sw) << 4)) = xv[j4];
+        if (p.xb) {
+            __nv_bfloat16* xbrow = p.xb + static_cast<size_t>(row) * p.xb_ld + c0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (MASKED && c0 + 8 * j >= p.N) break;
+                const float4 a = xv[2 * j], b = xv[2 * j + 1];
+                uint4 u;
+                u.x = pack_bf16x2(a.x, a.y);
+                u.y = pack_bf16x2(a.z, a.w);
+                u.z = pack_bf16x2(b.x, b.y);
+                u.w = pack_bf16x2(b.z, b.w);
+                reinterpret_cast<uint4*>(xbrow)[j] = u;
+                if (p.xb_lo_off > 0) {
+                    uint4 l;
+                    l.x = pack_bf16x2(a.x - bf16_round(a.x), a.y - bf16_round(a.y));
+                    l.y = pack_bf16x2(a.z - bf16_round(a.z), a.w - bf16_round(a.w));
+                    l.z = pack_bf16x2(b.x - bf16_round(b.x), b.y - bf16_round(b.y));
+                    l.w = pack_bf16x2(b.z - bf16_round(b.z), b.w - bf16_round(b.w));
+                    reinterpret_cast<uint4*>(xbrow + p.xb_lo_off)[j] = l;
                 }
             }
         }
     }
+
+    __device__ static __forceinline__ void run_staged(const GemmParams& p, int row, int col, int r_tile, uint8_t* xbox, float (&v)[32], const float (&z)[32], float cx,
+                                                      float ce, float sg) {
+        if (row >= p.M) return;            // rows past the batch: leave the staged tile as loaded
+        if (col >= p.N) {                  // whole 32-column span is padding: keep it at zero
+            const int sw = r_tile & 7;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(xbox + r_tile * 128 + ((j4 ^ sw) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+            return;
+        }
+        if (col + 32 <= p.N) process<false>(p, row, col, r_tile, xbox, v, z, cx, ce, sg);      // warp-uniform
+        else process<true>(p, row, col, r_tile, xbox, v, z, cx, ce, sg);
+    }
+
+    template <int GW>
+    __device__ static __forceinline__ void run(const GemmParams&, int, int, float (&)[32], float (&)[32], double&) {}
 };
 
 template <>

@@ -275,15 +275,19 @@ class BiologyAwareDiffusionModel(nn.Module):
         self._weights_sig = sig
 
     def _destroy_ctx(self) -> None:
-        if getattr(self, "_ctx", None) is not None:
+        ctx = self.__dict__.get("_ctx")
+        if ctx is not None:
+            self.__dict__["_ctx"] = None
             try:
-                _lib.load().osteo_ddpm_destroy(self._ctx)
+                _lib.load().osteo_ddpm_destroy(ctx)
             except Exception:
                 pass
-            self._ctx = None
 
     def __del__(self):
-        self._destroy_ctx()
+        try:
+            self._destroy_ctx()
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     def __getstate__(self):
         # the C context is per-object device state: copies / pickles start without one
