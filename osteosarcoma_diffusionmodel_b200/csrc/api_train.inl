@@ -32,6 +32,10 @@ static int ensure_train_ws(osteo_ddpm_ctx* c) {
     OSTEO_TRY(w.deps.alloc(static_cast<size_t>(cap) * 2 * c->DP * 2));
     OSTEO_CUDA(cudaMemset(w.deps.p, 0, w.deps.bytes));
     OSTEO_TRY(make_tmap_bf16(&w.deps_tmap, w.deps.p, cap, 2 * c->DP, 2 * c->DP, BM));
+    OSTEO_TRY(w.xt_bf.alloc(static_cast<size_t>(cap) * 2 * c->DP * 2));
+    OSTEO_CUDA(cudaMemset(w.xt_bf.p, 0, w.xt_bf.bytes));
+    OSTEO_TRY(make_tmap_bf16(&w.xt_tmap, w.xt_bf.p, cap, 2 * c->DP, 2 * c->DP, BM));
+    OSTEO_TRY(w.noise.alloc(static_cast<size_t>(cap) * c->DP * 4));
     for (DevBuf* b : {&w.pre0, &w.cemb, &w.h1, &w.dcemb, &w.dpre0}) OSTEO_TRY(b->alloc(static_cast<size_t>(cap) * c->E * 4));
     int max_hidden = 0;
     for (auto& hb : c->halves) max_hidden = hb->lin.n > max_hidden ? hb->lin.n : max_hidden;
@@ -123,7 +127,7 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
     // ------------------------------------------------------------------ forward
     zero_double_kernel<<<1, 1, 0, s>>>(c->loss_acc.as<double>());
     train_prepare_kernel<<<grid_for(n * (DP / 4), 256, c->sms), 256, 0, s>>>(x0_dev, noise_dev, t_idx_dev, n, D, c->sqrt_ab.as<float>(), c->sqrt_1mab.as<float>(),
-                                                                             c->x.as<float>(), DP, c->xb.ptr(), 2 * DP, c->lo(DP), seed, row_base);
+                                                                             w.noise.as<float>(), DP, w.xt_bf.as<__nv_bfloat16>(), 2 * DP, c->lo(DP), seed, row_base);
     OSTEO_CUDA(cudaGetLastError());
     {
         const size_t smem = sizeof(float) * 8 * (c->C + 2 * E);
@@ -133,7 +137,7 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
         OSTEO_CUDA(cudaGetLastError());
     }
     c->launches += 3;
-    OSTEO_TRY(launch_input_proj(c, 0, n, t_idx_dev, s));
+    OSTEO_TRY(launch_input_proj(c, 0, n, t_idx_dev, s, &w.xt_tmap));
     for (int i = 0; i < H; ++i) {
         HalfOpts o;
         o.train = train != 0;
@@ -146,7 +150,7 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
     {
         GemmParams p;
         out_proj_common(c, p, 0, n);
-        p.target = c->x.as<float>();
+        p.target = w.noise.as<float>();
         p.target_ld = DP;
         p.grad_scale = static_cast<float>(2.0 / (static_cast<double>(n) * D));
         p.loss_acc = c->loss_acc.as<double>();
@@ -277,7 +281,7 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
         }
     }
     // input_proj weight gradient: dh0^T . x_t
-    OSTEO_TRY(after_launch(c, launch_wgrad(w.dh0_bf.as<__nv_bfloat16>(), 2 * h0, h0, h0, c->xb.ptr(), 2 * DP, 0, DP, D, grads_dev[4], D, n, x3, c->status_dev.as<int>(),
+    OSTEO_TRY(after_launch(c, launch_wgrad(w.dh0_bf.as<__nv_bfloat16>(), 2 * h0, h0, h0, w.xt_bf.as<__nv_bfloat16>(), 2 * DP, 0, DP, D, grads_dev[4], D, n, x3, c->status_dev.as<int>(),
                                            c->sms, s), s));
     // time_proj / cond_proj / ConditionalEmbedding (fp32 CUDA-core kernels; tiny matrices)
     OSTEO_TRY(outer_accum(c, w.dh0_f32.as<float>(), h0, c->emb_table.as<float>(), c->TD, t_idx_dev, n, grads_dev[8], s));

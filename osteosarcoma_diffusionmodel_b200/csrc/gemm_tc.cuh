@@ -78,6 +78,8 @@ struct GemmParams {
     int m_tile0;
     int nseg;
     KSeg seg[MAX_KSEG];
+    int dbg;                  // diagnostic switches (0 in production; scripts/ddpm_probe.py)
+    int a_blocked_nbox;       // > 0: tma_a[0] views a BLOCKED operand [m_tile][nbox][128 rows][64 cols] (16 KB contiguous per k-block)
     int* status;              // sticky error word (device)
     long long row_base;       // global row index of row 0 (RNG keying under row sharding)
 
@@ -109,9 +111,10 @@ struct GemmParams {
     const float* coef_sigma;  // [T]
     float* x;                 // [M, x_ld] fp32 master state, updated in place
     int x_ld;
-    __nv_bfloat16* xb;        // bf16 shadow [hi|lo] of x: next step's input_proj operand
-    int xb_ld;
-    int xb_lo_off;
+    __nv_bfloat16* xb;        // bf16 shadow of x, BLOCKED [m_tile][xb_nbox][128][64]: next step's input_proj operand
+    int xb_nbox;              // boxes per m-tile (hi boxes, then lo boxes)
+    int xb_lo_boxes;          // > 0: the bf16 residual of column box k goes to box k + xb_lo_boxes
+    int x_nbox;               // fp32 state is BLOCKED [m_tile][x_nbox][128][32] (each TMA box = 16 KB contiguous)
     const float* noise;       // injected z [M, noise_ld] (parity) or nullptr (Philox)
     int noise_ld;
     float* eps_out;           // optional fp32 eps [M, eps_ld]
@@ -268,7 +271,7 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
             for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
                 const TileInfo ti = decode_tile<EPI, MN>(p, tile);
                 if (ti.skip) continue;
-                if (XSTAGE) {
+                if (XSTAGE && !(p.dbg & 16)) {
                     // fp32 state tile of this output tile: 4 boxes of [128 rows x 32 cols], double buffered
                     const int xb = xit & 1;
                     const uint32_t xphase = static_cast<uint32_t>(xit >> 1) & 1u;
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
                     mbar_arrive_expect_tx(&xfull_bar[xb], X_TILE_BYTES);
 #pragma unroll
                     for (int b = 0; b < BN / X_BOX_COLS; ++b)
-                        tma_load_2d(&p.tma_x_ld, smem_x + xb * X_TILE_BYTES + b * X_BOX_BYTES, &xfull_bar[xb], ti.n_blk * BN + b * X_BOX_COLS, ti.m_blk * BM);
+                        tma_load_2d(&p.tma_x_ld, smem_x + xb * X_TILE_BYTES + b * X_BOX_BYTES, &xfull_bar[xb], 0, (ti.m_blk * p.x_nbox + ti.n_blk * (BN / X_BOX_COLS) + b) * BM);
                 }
                 for (int s = 0; s < p.nseg && ok; ++s) {
                     const KSeg sg = p.seg[s];
@@ -296,7 +299,10 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
                             tma_load_2d(tb, sb, &full_bar[stage], sg.b_col + ti.n_blk * BN, kb * BK);
                             tma_load_2d(tb, sb + B_TILE_BYTES / 2, &full_bar[stage], sg.b_col + ti.n_blk * BN + 64, kb * BK);
                         } else {
-                            tma_load_2d(ta, sa, &full_bar[stage], sg.a_col + kb * BK, ti.m_blk * BM);
+                            if (p.a_blocked_nbox > 0 && sg.a_sel == 0)
+                                tma_load_2d(ta, sa, &full_bar[stage], 0, (ti.m_blk * p.a_blocked_nbox + sg.a_col / BK + kb) * BM);
+                            else
+                                tma_load_2d(ta, sa, &full_bar[stage], sg.a_col + kb * BK, ti.m_blk * BM);
                             tma_load_2d(tb, sb, &full_bar[stage], sg.b_col + kb * BK, sg.b_row0 + ti.n_blk * BN);
                         }
                         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -386,7 +392,7 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
                 // The noise of this tile depends only on (row, column, t): draw it BEFORE waiting for the accumulator and the
                 // staged state tile, so the Philox / Box-Muller instruction stream hides those waits.
                 float z[32];
-                Epilogue<EPI>::draw_noise(p, row, col, ddpm_t, ddpm_sg, z);
+                Epilogue<EPI>::draw_noise(p, row, col, ddpm_t, (p.dbg & 8) ? 0.0f : ddpm_sg, z);
                 if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
                 tc_fence_after_sync();
                 float v[32];
@@ -396,17 +402,18 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 const int xb = (it - 1) & 1;
                 const uint32_t xphase = static_cast<uint32_t>((it - 1) >> 1) & 1u;
-                if (!mbar_wait(&xfull_bar[xb], xphase)) { ok = false; break; }
+                if (!(p.dbg & 16) && !mbar_wait(&xfull_bar[xb], xphase)) { ok = false; break; }
                 uint8_t* xt = smem_x + xb * X_TILE_BYTES;
-                Epilogue<EPI>::run_staged(p, row, col, q * 32 + lane, xt + part * X_BOX_BYTES, v, z, ddpm_cx, ddpm_ce, ddpm_sg);
+                if (!(p.dbg & 4)) Epilogue<EPI>::run_staged(p, row, col, q * 32 + lane, ti.m_blk, xt + part * X_BOX_BYTES, v, z, ddpm_cx, ddpm_ce, ddpm_sg);
                 // make this warp's generic-proxy writes visible to the TMA engine, then store its 32 x 32 block
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&p.tma_x_st, xt + part * X_BOX_BYTES + q * 32 * 128, ti.n_blk * BN + part * X_BOX_COLS, ti.m_blk * BM + q * 32);
+                if (lane == 0 && (p.dbg & 1) && !(p.dbg & 16)) mbar_arrive(&xempty_bar[xb]);
+                if (lane == 0 && !(p.dbg & 1)) {
+                    tma_store_2d(&p.tma_x_st, xt + part * X_BOX_BYTES + q * 32 * 128, 0, (ti.m_blk * p.x_nbox + ti.n_blk * (BN / X_BOX_COLS) + part) * BM + q * 32);
                     tma_store_commit();
                     tma_store_wait_read<0>();      // smem may be overwritten once the bulk store has READ it
-                    mbar_arrive(&xempty_bar[xb]);
+                    if (!(p.dbg & 16)) mbar_arrive(&xempty_bar[xb]);
                 }
                 __syncwarp();
             } else {
@@ -618,8 +625,8 @@ struct Epilogue<EPI_DDPM> {
 
     // MASKED: the 32-column span crosses N (last column tile only).
     template <bool MASKED>
-    __device__ static __forceinline__ void process(const GemmParams& p, int row, int c0, int r_tile, uint8_t* xbox, float (&v)[32], const float (&z)[32], float cx,
-                                                   float ce, float sg) {
+    __device__ static __forceinline__ void process(const GemmParams& p, int row, int c0, int r_tile, int m_blk, uint8_t* xbox, float (&v)[32], const float (&z)[32],
+                                                   float cx, float ce, float sg) {
         const int sw = r_tile & 7;
         uint8_t* xrow = xbox + r_tile * 128;
         float4 xv[8];
@@ -663,8 +670,10 @@ struct Epilogue<EPI_DDPM> {
         }
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(xrow + ((j4 ^ sw) << 4)) = xv[j4];
-        if (p.xb) {
-            __nv_bfloat16* xbrow = p.xb + static_cast<size_t>(row) * p.xb_ld + c0;
+        if (p.xb && !(p.dbg & 2)) {
+            // blocked shadow: box (m_blk, c0 / 64), row r_tile, 32 consecutive bf16 = 64 contiguous bytes
+            __nv_bfloat16* xbrow = p.xb + ((static_cast<size_t>(m_blk) * p.xb_nbox + (c0 >> 6)) * BM + r_tile) * BK + (c0 & 63);
+            const size_t lo_off = static_cast<size_t>(p.xb_lo_boxes) * BM * BK;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 if (MASKED && c0 + 8 * j >= p.N) break;
@@ -675,20 +684,20 @@ struct Epilogue<EPI_DDPM> {
                 u.z = pack_bf16x2(b.x, b.y);
                 u.w = pack_bf16x2(b.z, b.w);
                 reinterpret_cast<uint4*>(xbrow)[j] = u;
-                if (p.xb_lo_off > 0) {
+                if (p.xb_lo_boxes > 0) {
                     uint4 l;
                     l.x = pack_bf16x2(a.x - bf16_round(a.x), a.y - bf16_round(a.y));
                     l.y = pack_bf16x2(a.z - bf16_round(a.z), a.w - bf16_round(a.w));
                     l.z = pack_bf16x2(b.x - bf16_round(b.x), b.y - bf16_round(b.y));
                     l.w = pack_bf16x2(b.z - bf16_round(b.z), b.w - bf16_round(b.w));
-                    reinterpret_cast<uint4*>(xbrow + p.xb_lo_off)[j] = l;
+                    reinterpret_cast<uint4*>(xbrow + lo_off)[j] = l;
                 }
             }
         }
     }
 
-    __device__ static __forceinline__ void run_staged(const GemmParams& p, int row, int col, int r_tile, uint8_t* xbox, float (&v)[32], const float (&z)[32], float cx,
-                                                      float ce, float sg) {
+    __device__ static __forceinline__ void run_staged(const GemmParams& p, int row, int col, int r_tile, int m_blk, uint8_t* xbox, float (&v)[32], const float (&z)[32],
+                                                      float cx, float ce, float sg) {
         if (row >= p.M) return;            // rows past the batch: leave the staged tile as loaded
         if (col >= p.N) {                  // whole 32-column span is padding: keep it at zero
             const int sw = r_tile & 7;
@@ -696,8 +705,8 @@ struct Epilogue<EPI_DDPM> {
             for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(xbox + r_tile * 128 + ((j4 ^ sw) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
             return;
         }
-        if (col + 32 <= p.N) process<false>(p, row, col, r_tile, xbox, v, z, cx, ce, sg);      // warp-uniform
-        else process<true>(p, row, col, r_tile, xbox, v, z, cx, ce, sg);
+        if (col + 32 <= p.N) process<false>(p, row, col, r_tile, m_blk, xbox, v, z, cx, ce, sg);      // warp-uniform
+        else process<true>(p, row, col, r_tile, m_blk, xbox, v, z, cx, ce, sg);
     }
 
     template <int GW>

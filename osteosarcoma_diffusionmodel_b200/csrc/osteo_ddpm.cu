@@ -1,6 +1,7 @@
 // C-ABI of the B200-native DDPM hot path (see include/osteo_ddpm.h).
 // Context = repacked weights + workspace + prebuilt TMA descriptors; every compute entry
 // point enqueues hand-written sm_100a kernels on the caller's stream. No CPU fallback.
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -161,7 +162,7 @@ struct osteo_ddpm_ctx {
     int precision = OSTEO_PREC_BF16;
     int DP = 0;                 // padded feature pitch (multiple of 64)
     long long cap = 0;
-    int chunk_rows = 32768;
+    int chunk_rows = 131072;
     long long launches = 0;
 
     // parameters
@@ -174,9 +175,11 @@ struct osteo_ddpm_ctx {
     bool have_weights = false, have_schedule = false, have_emb = false;
 
     // workspace (capacity `cap` rows)
-    DevBuf x;                            // fp32 [cap, DP]
+    DevBuf x;                            // fp32 state, blocked [cap/128][x_nbox][128][32]
     CUtensorMap x_tmap_ld, x_tmap_st;    // TMA views of x: 128x32 load boxes, 32x32 store boxes
-    ActBuf xb;                           // bf16 [cap, 2*DP]
+    DevBuf xb;                           // bf16 shadow, blocked [cap/128][xb_nbox][128][64] (hi boxes then lo boxes)
+    CUtensorMap xb_tmap;
+    int x_nbox = 0, xb_nbox = 0;
     std::vector<std::unique_ptr<ActBuf>> acts;   // [0] = h0, then one per half block
     DevBuf cproj;                        // fp32 [cap, h0]
     DevBuf step_dev, status_dev;
@@ -195,6 +198,8 @@ struct osteo_ddpm_ctx {
     bool x3() const { return precision == OSTEO_PREC_FP32X3; }
     int h0() const { return hidden[0]; }
     int lo(int width) const { return x3() ? width : 0; }
+    int lo_boxes() const { return x3() ? DP / BK : 0; }
+    __nv_bfloat16* xb_ptr() const { return xb.as<__nv_bfloat16>(); }
     ~osteo_ddpm_ctx() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
     }
@@ -232,11 +237,15 @@ static void set_rows(GemmParams& p, long long row0, long long row1) {
 }
 
 // input_proj + time/cond embedding add (models/diffusion.py:229-232) for rows [row0, row1).
-static int launch_input_proj(osteo_ddpm_ctx* c, long long row0, long long row1, const int* t_idx, cudaStream_t s) {
+static int launch_input_proj(osteo_ddpm_ctx* c, long long row0, long long row1, const int* t_idx, cudaStream_t s, const CUtensorMap* rowmajor_a = nullptr) {
     GemmParams p;
     base_params(c, p);
-    p.tma_a[0] = c->xb.tmap;
-    p.tma_a[1] = c->xb.tmap;
+    if (rowmajor_a) {            // training: x_t lives in a row-major [rows, 2*DP] buffer (it is also the MN-major wgrad operand)
+        p.tma_a[0] = p.tma_a[1] = *rowmajor_a;
+    } else {                     // sampling / denoise: the blocked bf16 shadow of the state
+        p.tma_a[0] = p.tma_a[1] = c->xb_tmap;
+        p.a_blocked_nbox = c->xb_nbox;
+    }
     p.tma_b[0] = p.tma_b[1] = c->in_proj.tmap;
     OSTEO_TRY(add_segments(p, 0, 0, c->DP, 0, c->in_proj.kp, c->DP, c->x3()));
     set_rows(p, row0, row1);
@@ -334,12 +343,13 @@ static int launch_output_ddpm(osteo_ddpm_ctx* c, long long row0, long long row1,
     p.coef_eps = c->coef_eps.as<float>();
     p.coef_sigma = c->coef_sigma.as<float>();
     p.x = c->x.as<float>();
-    p.x_ld = c->DP;
+    p.x_nbox = c->x_nbox;
     p.tma_x_ld = c->x_tmap_ld;
     p.tma_x_st = c->x_tmap_st;
-    p.xb = c->xb.ptr();
-    p.xb_ld = 2 * c->DP;
-    p.xb_lo_off = c->lo(c->DP);
+    p.xb = c->xb_ptr();
+    p.xb_nbox = c->xb_nbox;
+    p.xb_lo_boxes = c->lo_boxes();
+    if (const char* e = getenv("OSTEO_DDPM_DBG")) p.dbg = atoi(e);
     p.noise = noise;
     p.noise_ld = c->D;
     p.eps_out = eps_out;
@@ -516,7 +526,7 @@ long long osteo_ddpm_launch_count(const osteo_ddpm_ctx* ctx) { return ctx ? ctx-
 
 long long osteo_ddpm_workspace_bytes(const osteo_ddpm_ctx* c) {
     if (!c) return 0;
-    size_t b = c->x.bytes + c->xb.buf.bytes + c->cproj.bytes + c->in_proj.w.bytes + c->out_proj.w.bytes;
+    size_t b = c->x.bytes + c->xb.bytes + c->cproj.bytes + c->in_proj.w.bytes + c->out_proj.w.bytes;
     for (auto& a : c->acts) b += a->buf.bytes;
     for (auto& h : c->halves) b += h->lin.w.bytes + h->lin.wt.bytes;
     b += c->train.bytes();
@@ -547,12 +557,16 @@ int osteo_ddpm_reserve(osteo_ddpm_ctx* c, long long rows) {
         c->graph_n = -1;
     }
     const long long cap = round_up(rows, BM);
-    OSTEO_TRY(c->x.alloc(static_cast<size_t>(cap) * c->DP * 4));
+    const long long mt = cap / BM;
+    c->x_nbox = (c->out_proj.np / BN) * (BN / X_BOX_COLS);      // 4 boxes of 32 columns per output tile
+    c->xb_nbox = 2 * (c->DP / BK);                               // hi boxes then lo boxes
+    OSTEO_TRY(c->x.alloc(static_cast<size_t>(mt) * c->x_nbox * BM * X_BOX_COLS * 4));
     OSTEO_CUDA(cudaMemset(c->x.p, 0, c->x.bytes));
-    OSTEO_TRY(make_tmap_f32(&c->x_tmap_ld, c->x.p, cap, c->DP, c->DP, BM));
-    OSTEO_TRY(make_tmap_f32(&c->x_tmap_st, c->x.p, cap, c->DP, c->DP, 32));
-    OSTEO_TRY(c->xb.init(cap, c->DP));
-    OSTEO_CUDA(cudaMemset(c->xb.buf.p, 0, c->xb.buf.bytes));
+    OSTEO_TRY(make_tmap_f32(&c->x_tmap_ld, c->x.p, static_cast<uint64_t>(mt) * c->x_nbox * BM, X_BOX_COLS, X_BOX_COLS, BM));
+    OSTEO_TRY(make_tmap_f32(&c->x_tmap_st, c->x.p, static_cast<uint64_t>(mt) * c->x_nbox * BM, X_BOX_COLS, X_BOX_COLS, 32));
+    OSTEO_TRY(c->xb.alloc(static_cast<size_t>(mt) * c->xb_nbox * BM * BK * 2));
+    OSTEO_CUDA(cudaMemset(c->xb.p, 0, c->xb.bytes));
+    OSTEO_TRY(make_tmap_bf16(&c->xb_tmap, c->xb.p, static_cast<uint64_t>(mt) * c->xb_nbox * BM, BK, BK, BM));
     OSTEO_TRY(c->cproj.alloc(static_cast<size_t>(cap) * c->h0() * 4));
     OSTEO_CUDA(cudaMemset(c->cproj.p, 0, c->cproj.bytes));
     c->acts.clear();
@@ -637,7 +651,7 @@ int osteo_ddpm_load_state(osteo_ddpm_ctx* c, const float* x_dev, long long n, vo
     if (n <= 0 || n > c->cap) return fail("load_state: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long items = n * (c->DP / 4);
-    load_state_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(x_dev, n, c->D, c->x.as<float>(), c->DP, c->xb.ptr(), 2 * c->DP, c->lo(c->DP));
+    load_state_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(x_dev, n, c->D, c->DP, c->x.as<float>(), c->x_nbox, c->xb_ptr(), c->xb_nbox, c->lo_boxes());
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -647,7 +661,7 @@ int osteo_ddpm_store_state(osteo_ddpm_ctx* c, float* out_dev, long long n, void*
     OSTEO_TRY(check_ctx(c));
     if (n <= 0 || n > c->cap) return fail("store_state: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    store_state_kernel<<<grid_for(n * c->D, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->DP, out_dev, n, c->D);
+    store_state_kernel<<<grid_for(n * c->D, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->x_nbox, out_dev, n, c->D);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -658,7 +672,7 @@ int osteo_ddpm_init_noise(osteo_ddpm_ctx* c, long long n, uint64_t seed, long lo
     if (n <= 0 || n > c->cap) return fail("init_noise: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long items = n * (c->DP / 4);
-    init_noise_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->DP, c->xb.ptr(), 2 * c->DP, c->lo(c->DP), n, c->D, seed, row_base,
+    init_noise_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->x_nbox, c->DP, c->xb_ptr(), c->xb_nbox, c->lo_boxes(), n, c->D, seed, row_base,
                                                                   STREAM_XT, 0u);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
@@ -758,7 +772,7 @@ int osteo_ddpm_denoise(osteo_ddpm_ctx* c, const float* xt_dev, const int* t_idx_
     OSTEO_TRY(require_ready(c, n));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long items = n * (c->DP / 4);
-    load_state_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(xt_dev, n, c->D, nullptr, c->DP, c->xb.ptr(), 2 * c->DP, c->lo(c->DP));
+    load_state_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(xt_dev, n, c->D, c->DP, nullptr, c->x_nbox, c->xb_ptr(), c->xb_nbox, c->lo_boxes());
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     const long long ch = chunk_of(c, n);

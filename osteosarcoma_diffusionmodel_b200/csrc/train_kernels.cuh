@@ -21,11 +21,14 @@ struct TrainWorkspace {
     DevBuf dh0_bf, dh0_f32;                      // d(loss)/d(h0): bf16 [cap, 2*h0], fp32 [cap, h0]
     DevBuf deps;                                 // bf16 [cap, 2*DP]  d(loss)/d(eps_hat)
     CUtensorMap deps_tmap;
+    DevBuf xt_bf;                                // bf16 [cap, 2*DP]  x_t [hi|lo], row-major: A operand of input_proj AND MN-major wgrad operand
+    CUtensorMap xt_tmap;
+    DevBuf noise;                                // fp32 [cap, DP]    target of the MSE epilogue
     DevBuf pre0, cemb, h1, dcemb, dpre0;         // fp32 [cap, E] each: condition-embedding forward saves / backward temporaries
     DevBuf partials;                             // fp32 [cap/32, 3, max_width]
     DevBuf colsum_tmp;                           // fp32 [E] scratch
     size_t bytes() const {
-        size_t b = dh0_bf.bytes + dh0_f32.bytes + deps.bytes + pre0.bytes + cemb.bytes + h1.bytes + dcemb.bytes + dpre0.bytes + partials.bytes;
+        size_t b = dh0_bf.bytes + dh0_f32.bytes + deps.bytes + xt_bf.bytes + noise.bytes + pre0.bytes + cemb.bytes + h1.bytes + dcemb.bytes + dpre0.bytes + partials.bytes;
         for (auto& p : xhat) b += p->bytes;
         for (auto& p : rstd) b += p->bytes;
         for (auto& p : dy) b += p->bytes;
@@ -36,7 +39,7 @@ struct TrainWorkspace {
         rstd.clear();
         dy.clear();
         dy_tmap.clear();
-        for (DevBuf* b : {&dh0_bf, &dh0_f32, &deps, &pre0, &cemb, &h1, &dcemb, &dpre0, &partials, &colsum_tmp}) b->release();
+        for (DevBuf* b : {&dh0_bf, &dh0_f32, &deps, &xt_bf, &noise, &pre0, &cemb, &h1, &dcemb, &dpre0, &partials, &colsum_tmp}) b->release();
         cap = 0;
     }
 };

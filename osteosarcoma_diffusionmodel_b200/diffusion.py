@@ -138,7 +138,7 @@ class BiologyAwareDiffusionModel(nn.Module):
         self._precision = str(os.environ.get("OSTEO_DDPM_PRECISION", b200.get("precision", "bf16")))
         if self._precision not in _PRECISIONS:
             raise ValueError(f"unknown precision {self._precision!r} (bf16 | fp32x3)")
-        self._chunk_rows = int(os.environ.get("OSTEO_DDPM_CHUNK_ROWS", b200.get("chunk_rows", 32768)))
+        self._chunk_rows = int(os.environ.get("OSTEO_DDPM_CHUNK_ROWS", b200.get("chunk_rows", 131072)))
         self._use_graph = bool(int(os.environ.get("OSTEO_DDPM_GRAPH", b200.get("use_graph", 1))))
         self._seed = int(b200.get("seed", 0))
         self._draws = 0                 # counter mixed into the seed of un-seeded calls

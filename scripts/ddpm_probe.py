@@ -14,7 +14,9 @@ cond = synth.scenario_conditions(rows, 3).cuda()
 model.sample(cond, rows, seed=1, t_stop=998)
 lib = _lib.load()
 buf = (C.c_float * 4096)()
-for t in (500, 0, 500, 0):
+import os
+for t, dbg in [(500, int(d)) for d in os.environ.get('PROBE_DBG', '0').split(',')]:
+    os.environ['OSTEO_DDPM_DBG'] = str(dbg)
     acc = None
     for rep in range(4):
         n = lib.osteo_ddpm_profile_step(model._ctx, rows, t, 9, 0, buf, 4096, _lib.stream_handle())
@@ -24,4 +26,4 @@ for t in (500, 0, 500, 0):
     acc = [a / 3 for a in acc]
     k = len(acc) // 12 if len(acc) >= 12 else 1
     ddpm = sum(acc[11::12]); inp = sum(acc[0::12]); hid = sum(acc) - ddpm - inp
-    print(f"t={t}: step {sum(acc):.3f} ms  input_proj {inp:.3f}  hidden {hid:.3f}  output_proj+update {ddpm:.3f}", flush=True)
+    print(f"dbg={dbg:2d} t={t}: step {sum(acc):.3f} ms  input_proj {inp:.3f}  hidden {hid:.3f}  output_proj+update {ddpm:.3f}", flush=True)
