@@ -12,8 +12,9 @@ int launch_gemm_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
         OSTEO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, GW, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<EPI>()));
         configured = true;
     }
-    const int tiles = (MN ? p.splits : 1) * p.m_tiles * p.n_tiles;
+    int tiles = (MN ? p.splits : 1) * p.m_tiles * p.n_tiles;
     if (tiles <= 0) return 0;
+    if (EPI == EPI_DDPM && p.a_resident) tiles = p.m_tiles * p.n_chunks;      // work units, not tiles
     const int grid = tiles < num_sms ? tiles : num_sms;
     gemm_tc_kernel<EPI, GW, MN><<<grid, gemm_threads<EPI>(), gemm_smem_bytes<EPI>(), stream>>>(p);
     OSTEO_CUDA(cudaGetLastError());

@@ -78,6 +78,8 @@ struct GemmParams {
     int m_tile0;
     int nseg;
     KSeg seg[MAX_KSEG];
+    int a_resident;           // EPI_DDPM, single K segment of <= 4 k-blocks: keep the A tile in shared memory across the n-tiles of an m-block
+    int n_chunks;             //   ... and split each m-block's n-tiles into this many work units (load balance)
     int dbg;                  // diagnostic switches (0 in production; scripts/ddpm_probe.py)
     int a_blocked_nbox;       // > 0: tma_a[0] views a BLOCKED operand [m_tile][nbox][128 rows][64 cols] (16 KB contiguous per k-block)
     int* status;              // sticky error word (device)
@@ -207,6 +209,52 @@ __device__ __forceinline__ TileInfo decode_tile(const GemmParams& p, int tile) {
     return t;
 }
 
+// The order in which one CTA walks its tiles; identical in the producer, MMA and epilogue roles.
+//   default     tile = blockIdx.x, blockIdx.x + grid, ...  (round robin over (m, n) with n fastest)
+//   A-resident  work unit = (m block, chunk of consecutive n tiles), units round robin over CTAs; inside a unit the n tiles
+//               are consecutive so the A tile (128 rows x K) is loaded once and only W streams (halves L2 -> SMEM traffic).
+template <int EPI, bool MN>
+struct TileSeq {
+    const GemmParams& p;
+    bool ares;
+    int num_tiles, tile;              // default order
+    int units, unit, per_chunk, n, n_end;   // A-resident order
+    __device__ TileSeq(const GemmParams& p_) : p(p_) {
+        ares = (EPI == EPI_DDPM) && p.a_resident != 0;
+        num_tiles = (MN ? p.splits : 1) * p.m_tiles * p.n_tiles;
+        tile = static_cast<int>(blockIdx.x) - static_cast<int>(gridDim.x);
+        per_chunk = (p.n_tiles + (p.n_chunks > 0 ? p.n_chunks : 1) - 1) / (p.n_chunks > 0 ? p.n_chunks : 1);
+        units = p.m_tiles * (p.n_chunks > 0 ? p.n_chunks : 1);
+        unit = static_cast<int>(blockIdx.x) - static_cast<int>(gridDim.x);
+        n = n_end = 0;
+    }
+    __device__ bool next(TileInfo& ti, bool& first, bool& last) {
+        if (!ares) {
+            tile += gridDim.x;
+            if (tile >= num_tiles) return false;
+            ti = decode_tile<EPI, MN>(p, tile);
+            first = last = true;
+            return true;
+        }
+        first = false;
+        while (n >= n_end) {
+            unit += gridDim.x;
+            if (unit >= units) return false;
+            const int chunk = unit % p.n_chunks;
+            n = chunk * per_chunk;
+            n_end = n + per_chunk < p.n_tiles ? n + per_chunk : p.n_tiles;
+            first = true;
+        }
+        ti.m_blk = p.m_tile0 + unit / p.n_chunks;
+        ti.n_blk = n;
+        ti.kb0 = ti.kb1 = 0;
+        ti.skip = false;
+        ++n;
+        last = n >= n_end;
+        return true;
+    }
+};
+
 template <int EPI, int GW, bool MN = false>
 __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -223,7 +271,9 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
     uint64_t* tempty_bar = tfull_bar + NUM_ACC;
     uint64_t* xfull_bar = tempty_bar + NUM_ACC;
     uint64_t* xempty_bar = xfull_bar + X_BUFFERS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(xempty_bar + X_BUFFERS);
+    uint64_t* afull_bar = xempty_bar + X_BUFFERS;      // A-resident mode: A tile landed / A tile no longer read by any MMA
+    uint64_t* aempty_bar = afull_bar + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -251,6 +301,8 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
             mbar_init(&xfull_bar[i], 1);
             mbar_init(&xempty_bar[i], NUM_EPI_WARPS);
         }
+        mbar_init(afull_bar, 1);
+        mbar_init(aempty_bar, 1);
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -259,17 +311,18 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int num_tiles = (MN ? p.splits : 1) * p.m_tiles * p.n_tiles;
-
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            int xit = 0;
+            int xit = 0, uit = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                const TileInfo ti = decode_tile<EPI, MN>(p, tile);
+            TileSeq<EPI, MN> seq(p);
+            const int ring = seq.ares ? 2 : STAGES;      // A-resident: 64 KB resident A + two 16 KB W stages in the same 96 KB
+            TileInfo ti;
+            bool first, last;
+            while (ok && seq.next(ti, first, last)) {
                 if (ti.skip) continue;
                 if (XSTAGE && !(p.dbg & 16)) {
                     // fp32 state tile of this output tile: 4 boxes of [128 rows x 32 cols], double buffered
@@ -281,6 +334,23 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
 #pragma unroll
                     for (int b = 0; b < BN / X_BOX_COLS; ++b)
                         tma_load_2d(&p.tma_x_ld, smem_x + xb * X_TILE_BYTES + b * X_BOX_BYTES, &xfull_bar[xb], 0, (ti.m_blk * p.x_nbox + ti.n_blk * (BN / X_BOX_COLS) + b) * BM);
+                }
+                if (XSTAGE && seq.ares) {
+                    const KSeg sg = p.seg[0];
+                    if (first) {
+                        if (!mbar_wait(aempty_bar, (static_cast<uint32_t>(uit) & 1u) ^ 1u)) { ok = false; break; }
+                        ++uit;
+                        mbar_arrive_expect_tx(afull_bar, sg.nkb * A_TILE_BYTES);
+                        for (int kb = 0; kb < sg.nkb; ++kb)
+                            tma_load_2d(&p.tma_a[0], smem + kb * A_TILE_BYTES, afull_bar, sg.a_col + kb * BK, ti.m_blk * BM);
+                    }
+                    for (int kb = 0; kb < sg.nkb; ++kb) {
+                        if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; break; }
+                        mbar_arrive_expect_tx(&full_bar[stage], B_TILE_BYTES);
+                        tma_load_2d(&p.tma_b[0], smem + 4 * A_TILE_BYTES + stage * B_TILE_BYTES, &full_bar[stage], sg.b_col + kb * BK, sg.b_row0 + ti.n_blk * BN);
+                        if (++stage == ring) { stage = 0; phase ^= 1u; }
+                    }
+                    continue;
                 }
                 for (int s = 0; s < p.nseg && ok; ++s) {
                     const KSeg sg = p.seg[s];
@@ -317,10 +387,12 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
             constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MN ? 1 : 0, MN ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
+            int it = 0, uit = 0;
             bool ok = true;
-            for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-                const TileInfo ti = decode_tile<EPI, MN>(p, tile);
+            TileSeq<EPI, MN> seq(p);
+            TileInfo ti;
+            bool first, last;
+            while (ok && seq.next(ti, first, last)) {
                 if (ti.skip) continue;
                 const int acc = it % NUM_ACC;
                 const uint32_t acc_phase = static_cast<uint32_t>(it / NUM_ACC) & 1u;
@@ -329,6 +401,32 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
                 tc_fence_after_sync();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
                 uint32_t accumulate = 0;
+                if (XSTAGE && seq.ares) {
+                    if (first) {
+                        if (!mbar_wait(afull_bar, static_cast<uint32_t>(uit) & 1u)) { ok = false; break; }
+                        ++uit;
+                        tc_fence_after_sync();
+                    }
+                    const int nkb = p.seg[0].nkb;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        if (!mbar_wait(&full_bar[stage], phase)) { ok = false; break; }
+                        tc_fence_after_sync();
+                        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem + kb * A_TILE_BYTES));
+                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + 4 * A_TILE_BYTES + stage * B_TILE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k) {
+                            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accumulate);
+                            accumulate = 1;
+                        }
+                        umma_commit(&empty_bar[stage]);
+                        if (++stage == 2) { stage = 0; phase ^= 1u; }
+                    }
+                    if (ok) {
+                        umma_commit(&tfull_bar[acc]);
+                        if (last) umma_commit(aempty_bar);     // every MMA that reads the resident A tile has retired
+                    }
+                    continue;
+                }
                 for (int s = 0; s < p.nseg && ok; ++s) {
                     const int kb_begin = MN ? ti.kb0 : 0, kb_end = MN ? ti.kb1 : p.seg[s].nkb;
                     for (int kb = kb_begin; kb < kb_end; ++kb) {
@@ -379,8 +477,10 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
             ddpm_ce = __ldg(p.coef_eps + ddpm_t);
             ddpm_sg = __ldg(p.coef_sigma + ddpm_t);
         }
-        for (int tile = blockIdx.x; tile < num_tiles && ok; tile += gridDim.x) {
-            const TileInfo ti = decode_tile<EPI, MN>(p, tile);
+        TileSeq<EPI, MN> seq(p);
+        TileInfo ti;
+        bool first, last;
+        while (ok && seq.next(ti, first, last)) {
             if (ti.skip) continue;
             const int acc = it % NUM_ACC;
             const uint32_t acc_phase = static_cast<uint32_t>(it / NUM_ACC) & 1u;

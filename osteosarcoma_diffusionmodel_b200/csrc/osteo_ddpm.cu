@@ -349,7 +349,12 @@ static int launch_output_ddpm(osteo_ddpm_ctx* c, long long row0, long long row1,
     p.xb = c->xb_ptr();
     p.xb_nbox = c->xb_nbox;
     p.xb_lo_boxes = c->lo_boxes();
+    if (p.nseg == 1 && p.seg[0].nkb <= 4) {     // bf16 mode, h0 <= 256: A tile (<= 64 KB) stays resident across an m-block's n-tiles
+        p.a_resident = 1;
+        p.n_chunks = 2;
+    }
     if (const char* e = getenv("OSTEO_DDPM_DBG")) p.dbg = atoi(e);
+    if (p.dbg & 32) p.a_resident = 0;
     p.noise = noise;
     p.noise_ld = c->D;
     p.eps_out = eps_out;
