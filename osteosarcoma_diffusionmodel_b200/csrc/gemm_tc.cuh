@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
         bool ok = true;
         double thread_acc = 0.0;                // EPI_MSE / EPI_RBF partial sums
         int ddpm_t = 0;
+        int pending_xb = -1;      // x buffer whose bulk store has been issued but not yet confirmed read
         float ddpm_cx = 0.f, ddpm_ce = 0.f, ddpm_sg = 0.f;
         if constexpr (XSTAGE) {                 // timestep and its three coefficients: once per kernel, not once per tile
             ddpm_t = *p.step;
@@ -493,6 +494,14 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
                 // staged state tile, so the Philox / Box-Muller instruction stream hides those waits.
                 float z[32];
                 Epilogue<EPI>::draw_noise(p, row, col, ddpm_t, (p.dbg & 8) ? 0.0f : ddpm_sg, z);
+                if (pending_xb >= 0) {
+                    // the previous tile's bulk store has had the whole noise draw to read its shared-memory block: release it
+                    if (lane == 0) {
+                        tma_store_wait_read<0>();
+                        mbar_arrive(&xempty_bar[pending_xb]);
+                    }
+                    pending_xb = -1;
+                }
                 if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
                 tc_fence_after_sync();
                 float v[32];
@@ -508,13 +517,11 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
                 // make this warp's generic-proxy writes visible to the TMA engine, then store its 32 x 32 block
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0 && (p.dbg & 1) && !(p.dbg & 16)) mbar_arrive(&xempty_bar[xb]);
-                if (lane == 0 && !(p.dbg & 1)) {
+                if (lane == 0) {
                     tma_store_2d(&p.tma_x_st, xt + part * X_BOX_BYTES + q * 32 * 128, 0, (ti.m_blk * p.x_nbox + ti.n_blk * (BN / X_BOX_COLS) + part) * BM + q * 32);
                     tma_store_commit();
-                    tma_store_wait_read<0>();      // smem may be overwritten once the bulk store has READ it
-                    if (!(p.dbg & 16)) mbar_arrive(&xempty_bar[xb]);
                 }
+                pending_xb = (p.dbg & 16) ? -1 : xb;      // released after the next tile's noise draw (or after the loop)
                 __syncwarp();
             } else {
                 if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
@@ -530,7 +537,13 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
             }
         }
         if constexpr (XSTAGE) {
-            if (lane == 0) tma_store_wait_all<0>();   // all bulk stores complete before the CTA exits
+            if (lane == 0) {
+                if (pending_xb >= 0) {
+                    tma_store_wait_read<0>();
+                    mbar_arrive(&xempty_bar[pending_xb]);
+                }
+                tma_store_wait_all<0>();   // all bulk stores complete before the CTA exits
+            }
         }
         if (EPI == EPI_MSE || EPI == EPI_RBF) {
             // warp reduce then one atomic per warp
@@ -712,15 +725,7 @@ struct Epilogue<EPI_DDPM> {
                 if (c0 + j < p.N) z[j] = nz[j];
             return;
         }
-        const uint64_t grow = static_cast<uint64_t>(p.row_base + row);
-#pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 g = philox_normal4(p.seed, grow, static_cast<uint32_t>((c0 >> 2) + j4), STREAM_REVERSE, static_cast<uint32_t>(t));
-            z[4 * j4 + 0] = g.x;
-            z[4 * j4 + 1] = g.y;
-            z[4 * j4 + 2] = g.z;
-            z[4 * j4 + 3] = g.w;
-        }
+        philox_normal_row<8>(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 2), STREAM_REVERSE, static_cast<uint32_t>(t), z);
     }
 
     // MASKED: the 32-column span crosses N (last column tile only).

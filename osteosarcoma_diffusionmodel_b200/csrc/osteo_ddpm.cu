@@ -354,7 +354,7 @@ static int launch_output_ddpm(osteo_ddpm_ctx* c, long long row0, long long row1,
         p.n_chunks = 2;
     }
     if (const char* e = getenv("OSTEO_DDPM_DBG")) p.dbg = atoi(e);
-    if (p.dbg & 32) p.a_resident = 0;
+    if (!(p.dbg & 32)) p.a_resident = 0;      // measured SLOWER than streaming A (2-stage W ring is latency-bound): off unless bit 5 is set
     p.noise = noise;
     p.noise_ld = c->D;
     p.eps_out = eps_out;

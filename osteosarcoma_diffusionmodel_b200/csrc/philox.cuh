@@ -53,6 +53,39 @@ __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, 
     z1 = r * s;
 }
 
+// N independent Philox4x32-10 blocks advanced round by round (round loop outermost): N independent dependency
+// chains in flight instead of one, which is what keeps the integer pipes busy with few warps per scheduler.
+template <int N>
+__device__ __forceinline__ void philox4x32_10_batch(uint4 (&c)[N], uint2 k) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            const uint32_t hi0 = __umulhi(M0, c[i].x), lo0 = M0 * c[i].x;
+            const uint32_t hi1 = __umulhi(M1, c[i].z), lo1 = M1 * c[i].z;
+            c[i] = make_uint4(hi1 ^ c[i].y ^ k.x, lo1, hi0 ^ c[i].w ^ k.y, lo0);
+        }
+        k.x += W0;
+        k.y += W1;
+    }
+}
+
+// 4*N normals for columns [4*col4_0, 4*(col4_0 + N)) of one row: same values as N calls of philox_normal4.
+template <int N>
+__device__ __forceinline__ void philox_normal_row(uint64_t seed, uint64_t row, uint32_t col4_0, uint32_t stream, uint32_t step, float (&z)[4 * N]) {
+    uint4 c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        c[i] = make_uint4(col4_0 + i, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), (stream << 16) | (step & 0xFFFFu));
+    philox4x32_10_batch<N>(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        box_muller(c[i].x, c[i].y, z[4 * i + 0], z[4 * i + 1]);
+        box_muller(c[i].z, c[i].w, z[4 * i + 2], z[4 * i + 3]);
+    }
+}
+
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t row, uint32_t col4, uint32_t stream, uint32_t step) {
     const uint4 w = philox_words(seed, row, col4, stream, step);
     float4 z;

@@ -44,21 +44,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
+    // The suspend-time hint lets the hardware park the warp (no issue slots burnt) until the phase flips or ~2 us elapse.
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
         : "memory");
     return ok != 0;
 }
-// Bounded wait. Returns false on timeout.
+// Bounded wait. Returns false on timeout (~2 s): each failed try_wait already slept up to the hint, so the
+// clock is only consulted every 64 iterations.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > OSTEO_WAIT_LIMIT_CYCLES) return false;
+        if ((++spins & 63u) == 0 && clock64() - t0 > OSTEO_WAIT_LIMIT_CYCLES) return false;
     }
     return true;
 }
@@ -135,6 +138,18 @@ __device__ __forceinline__ void tmem_ld_32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+
+// Same, 16 columns, WITHOUT the wait: callers batch several loads and then call tmem_ld_wait().
+__device__ __forceinline__ void tmem_ld_16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- descriptors
 // Shared-memory matrix descriptor, K-major operand tile written by TMA with
