@@ -315,6 +315,11 @@ def run_ours(args):
         roofline["step"] = {"ms_per_reverse_step": step_ms, "hbm_frac_of_algorithmic": ALGO_BYTES_PER_PATIENT_STEP * rows / (step_ms / 1e3) / 1e9 / hbm_peak,
                             "tensor_frac": ALGO_FLOPS_PER_PATIENT_STEP * rows / (gemm_ms / 1e3) / 1e12 / tf_peak}
 
+    # ---- secondary workloads of the same hot path (BASELINE.json: "train step time"; configs[3], configs[4]); N=1 only
+    secondary = None
+    if rank == 0 and world == 1 and not args.no_secondary:
+        secondary = run_secondary(model, dev, hbm_peak, tf_peak)
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -328,12 +333,115 @@ def run_ours(args):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "bf16x3 (split-bf16, fp32-equivalent)", "data": "synthetic",
             "config": workload_config(args, rows), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline, "secondary": secondary,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def run_secondary(model, dev, hbm_peak, tf_peak):
+    """Train step (fwd + bwd + clip + AdamW, batch 8192 = one GPU's share of BASELINE.json configs[3]), RBF-MMD Gram reduction and
+    pathway-coherence moments, each timed with CUDA events after warm-up. CPU figures are the oracle port on bounded samples."""
+    import numpy as np
+    import torch
+    from oracle import ddpm_oracle as O
+    from oracle import synth
+    from oracle import validators_oracle as V
+    from osteosarcoma_diffusionmodel_b200.validation import BiologicalValidator
+
+    out = {}
+
+    def timed(fn, warm, reps):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # -------- training step
+    B = 8192
+    x0, cond = synth.make_cohort(B, D_MUT, D_EXPR, D_PATH, N_COND, seed=3)
+    x0, cond = x0.to(dev), cond.to(dev)
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)      # utils/train.py:169-173
+
+    def step():
+        opt.zero_grad(set_to_none=False)
+        loss = model(x0, cond, return_loss=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+
+    def fwd_bwd():
+        model.zero_grad(set_to_none=False)
+        model(x0, cond, return_loss=True).backward()
+
+    ms = timed(step, 3, 10)
+    ms_fb = timed(fwd_bwd, 2, 10)
+    flops = 22.6e6 * B          # SURVEY.md §8(d): fwd + wgrad + dgrad per sample
+    out["train_step"] = {"batch": B, "precision": model._precision, "ms_per_step": ms, "samples_per_s": B / (ms / 1e3), "fwd_bwd_ms": ms_fb,
+                         "tensor_frac_fwd_bwd": flops / (ms_fb / 1e3) / 1e12 / tf_peak, "optimizer": "torch AdamW + clip_grad_norm_(1.0), unmodified"}
+    model.eval()
+    # CPU port: autograd over the oracle, batch 1024
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.make_params(D, N_COND, HIDDEN, seed=0)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    full = dict(params)
+    full.update(O.schedule_buffers("cosine", T_STEPS))
+    copt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=1e-5)
+    bx, bc = x0[:1024].cpu(), cond[:1024].cpu()
+    masks = synth.dropout_masks(0, 1024, synth.block_widths(HIDDEN), 0.2)
+
+    def cpu_step():
+        copt.zero_grad()
+        t = torch.randint(0, T_STEPS, (1024,))
+        loss = O.forward_loss(full, bx, bc, t, torch.randn_like(bx), T_STEPS, drop_masks=masks, p=0.2, training=True)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(list(params.values()), 1.0)
+        copt.step()
+
+    cpu_step()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        cpu_step()
+    cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+    out["train_step"]["cpu_port"] = {"batch": 1024, "ms_per_step": cpu_ms, "samples_per_s": 1024 / (cpu_ms / 1e3), "cores": torch.get_num_threads()}
+
+    # -------- RBF-MMD (utils/validation.py:273-298): N = M = 16384 rows of 5142 features
+    n = 16384
+    g = torch.Generator(device=dev).manual_seed(1)
+    X = torch.randn(n, D, device=dev, generator=g) + 4.0
+    Y = torch.randn(n, D, device=dev, generator=g) * 1.1 + 4.1
+    for prec in ("bf16", "fp32x3"):
+        val = BiologicalValidator({"evaluation": {}}, precision=prec)
+        ms = timed(lambda: val.compute_mmd(X, Y), 1, 3)
+        pairs = 3.0 * n * n
+        passes = 3 if prec == "fp32x3" else 1
+        # half-Gram for XX and YY: 2 * n(n+1)/2 + n*n tile-pairs actually multiplied
+        mults = (n * (n + 128) + n * n) * 2.0 * D * passes
+        out[f"mmd_{prec}"] = {"rows": n, "ms": ms, "kernel_pairs_per_s": pairs / (ms / 1e3), "tensor_tflops": mults / (ms / 1e3) / 1e12,
+                              "tensor_frac": mults / (ms / 1e3) / 1e12 / tf_peak, "value": val.compute_mmd(X, Y), "includes": "centring, bf16 packing, row norms, 3 Gram reductions"}
+    Xc, Yc = X[:384].cpu().numpy(), Y[:384].cpu().numpy()
+    t0 = time.perf_counter()
+    V.compute_mmd(Xc, Yc)
+    dt = time.perf_counter() - t0
+    out["mmd_cpu_port"] = {"rows": 384, "s": dt, "kernel_pairs_per_s": 3 * 384 * 384 / dt, "note": "numpy restatement of scipy cdist + exp, literal differences"}
+
+    # -------- pathway coherence moments (utils/validation.py:125-175): 1M rows, 10 pathways x 15 genes
+    rows = 1_000_000
+    cohort = torch.randn(rows, 371, device=dev, generator=g)
+    members = [list(range(15 * p, 15 * p + 15)) for p in range(10)]
+    val = BiologicalValidator({"evaluation": {}})
+    ms = timed(lambda: val.pathway_coherence_from_tensors(cohort[: rows // 2], cohort[rows // 2:], members), 1, 3)
+    out["coherence"] = {"rows": rows, "genes": 371, "pathways": 10, "ms": ms, "gathered_gb_per_s": rows * 150 * 4 / (ms / 1e3) / 1e9}
+    return out
 
 
 def main():
@@ -347,6 +455,7 @@ def main():
     ap.add_argument("--chunk-rows", type=int, default=None)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the train-step / MMD / coherence timings")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3          # timing rule: at least 3 warm-up steps

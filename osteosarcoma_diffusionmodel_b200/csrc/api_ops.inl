@@ -198,7 +198,7 @@ int osteo_corr_moments(const float* data_dev, long long n, int ld, const int* co
     long long warps = row_end - row_begin;
     const int sms = current_sms();
     long long blocks = (warps + 7) / 8;
-    if (blocks > sms * 8LL) blocks = sms * 8LL;
+    if (blocks > sms * 4LL) blocks = sms * 4LL;
     corr_moments_kernel<<<static_cast<unsigned>(blocks), 256, 0, s>>>(data_dev, ld, cols_dev, k, shift_dev, row_begin, row_end, out_dev);
     OSTEO_CUDA(cudaGetLastError());
     return 0;

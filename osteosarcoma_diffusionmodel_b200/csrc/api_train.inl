@@ -184,7 +184,17 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
         }
         return (j - 4 * H == 0) ? static_cast<size_t>(D) * h0 : static_cast<size_t>(D);
     };
-    for (int i = 0; i < n_tensors; ++i) OSTEO_CUDA(cudaMemsetAsync(grads_dev[i], 0, numel(i) * sizeof(float), s));
+    {
+        // weight gradients accumulate atomically (split-batch wgrad): zero them; contiguous tensors share one memset
+        int i = 0;
+        while (i < n_tensors) {
+            int j = i;
+            size_t total = numel(i);
+            while (j + 1 < n_tensors && grads_dev[j + 1] == grads_dev[j] + numel(j)) total += numel(++j);
+            OSTEO_CUDA(cudaMemsetAsync(grads_dev[i], 0, total * sizeof(float), s));
+            i = j + 1;
+        }
+    }
     const int gi_out_w = 10 + 4 * H, gi_out_b = gi_out_w + 1;
 
     // output_proj: bias gradient from the MSE epilogue's column partials, weight gradient = deps^T . act_last

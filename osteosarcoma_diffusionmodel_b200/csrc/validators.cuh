@@ -62,13 +62,21 @@ __global__ void corr_moments_kernel(const float* __restrict__ data, int ld, cons
         }
         ++count;
     }
+    // block-level reduction in shared memory (fp64), then ONE set of global atomics per block: the k + k*k addresses are
+    // shared by every warp of the grid, so per-warp global atomics would serialise on them.
+    __shared__ double red[1 + 32 + 32 * 32];
+    for (int i = threadIdx.x; i < 1 + k + k * k; i += blockDim.x) red[i] = 0.0;
+    __syncthreads();
     if (lane < k) {
-        atomicAdd(out + 1 + lane, s1);
+        atomicAdd(&red[1 + lane], s1);
 #pragma unroll
         for (int i = 0; i < 32; ++i)
-            if (i < k) atomicAdd(out + 1 + k + lane * k + i, s2[i]);
+            if (i < k) atomicAdd(&red[1 + k + lane * k + i], s2[i]);
     }
-    if (lane == 0 && count) atomicAdd(out, static_cast<double>(count));
+    if (lane == 0 && count) atomicAdd(&red[0], static_cast<double>(count));
+    __syncthreads();
+    for (int i = threadIdx.x; i < 1 + k + k * k; i += blockDim.x)
+        if (red[i] != 0.0) atomicAdd(out + i, red[i]);
 }
 
 }  // namespace osteo

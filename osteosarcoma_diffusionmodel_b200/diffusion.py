@@ -364,7 +364,14 @@ class BiologyAwareDiffusionModel(nn.Module):
                 masks = [m.to(device=dev, dtype=torch.uint8).contiguous() for m in inject["masks"]]
         loss = torch.zeros((), device=dev, dtype=torch.float32)
         ps = self._param_list()
-        grads = [torch.empty_like(p) for p in ps] if want_grads else []
+        grads = []
+        if want_grads:
+            # one flat buffer, per-parameter views: the library zeroes it with a single memset
+            flat = torch.empty(sum(p.numel() for p in ps), device=dev, dtype=torch.float32)
+            o = 0
+            for p in ps:
+                grads.append(flat[o:o + p.numel()].view_as(p))
+                o += p.numel()
         garr = (C.c_void_p * len(ps))(*[g.data_ptr() for g in grads]) if want_grads else None
         marr = (C.c_void_p * len(masks))(*[m.data_ptr() for m in masks]) if masks is not None else None
         _lib.check(lib.osteo_ddpm_train_step(self._ctx, x_0.data_ptr(), conditions.data_ptr(), n, t.data_ptr(),

@@ -102,15 +102,21 @@ class BiologicalValidator:
 
     # ------------------------------------------------------------------ utils/validation.py:125-175
     def _coherence_scores(self, data: torch.Tensor, member_cols: List[List[int]]) -> List[float]:
+        """One moment kernel per pathway, all enqueued before a single all-reduce and a single device->host copy."""
         rank, ws = D.world()
         rows = D.shard_rows(data.shape[0], rank, ws)
-        scores = []
+        parts = []
         for cols in member_cols:
-            k = len(cols)
             ci = torch.tensor(cols, dtype=torch.long, device=data.device)
             shift = data[0, ci].contiguous()            # any value near the column mean conditions the fp64 moments
-            mom = D.all_reduce_sum_(_moments(data, cols, shift, rows)).cpu().numpy()
-            corr = _corr_from_moments(mom, k)
+            parts.append(_moments(data, cols, shift, rows))
+        flat = D.all_reduce_sum_(torch.cat(parts)).cpu().numpy()
+        scores, o = [], 0
+        for cols in member_cols:
+            k = len(cols)
+            n = 1 + k + k * k
+            corr = _corr_from_moments(flat[o:o + n], k)
+            o += n
             scores.append(float(corr[np.triu_indices(k, k=1)].mean()))
         return scores
 
