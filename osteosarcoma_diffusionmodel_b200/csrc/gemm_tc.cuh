@@ -504,16 +504,25 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
                 }
                 if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
                 tc_fence_after_sync();
-                float v[32];
-                tmem_ld_32(taddr, v);
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
                 const int xb = (it - 1) & 1;
                 const uint32_t xphase = static_cast<uint32_t>((it - 1) >> 1) & 1u;
                 if (!(p.dbg & 16) && !mbar_wait(&xfull_bar[xb], xphase)) { ok = false; break; }
                 uint8_t* xt = smem_x + xb * X_TILE_BYTES;
-                if (!(p.dbg & 4)) Epilogue<EPI>::run_staged(p, row, col, q * 32 + lane, ti.m_blk, xt + part * X_BOX_BYTES, v, z, ddpm_cx, ddpm_ce, ddpm_sg);
+                // two passes of 16 accumulator columns keep z[32] + v[16] + x[16] in registers without spilling
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    uint32_t vr[16];
+                    tmem_ld_16_nowait(taddr + 16 * hh, vr);
+                    tmem_ld_wait();
+                    if (hh == 1) {
+                        // accumulator fully in registers: hand the TMEM stage back to the MMA warp
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
+                    if (!(p.dbg & 4))
+                        Epilogue<EPI>::run_staged16(p, row, col + 16 * hh, q * 32 + lane, ti.m_blk, xt + part * X_BOX_BYTES, 4 * hh, vr, &z[16 * hh], ddpm_cx, ddpm_ce, ddpm_sg);
+                }
                 // make this warp's generic-proxy writes visible to the TMA engine, then store its 32 x 32 block
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -728,32 +737,32 @@ struct Epilogue<EPI_DDPM> {
         philox_normal_row<8>(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 2), STREAM_REVERSE, static_cast<uint32_t>(t), z);
     }
 
-    // MASKED: the 32-column span crosses N (last column tile only).
+    // One pass = 16 columns [c0, c0 + 16) of row `row`: chunks j4_0 .. j4_0 + 3 of the 128-byte swizzled row in the staged box.
+    // MASKED: the span crosses N (last column tile only).
     template <bool MASKED>
-    __device__ static __forceinline__ void process(const GemmParams& p, int row, int c0, int r_tile, int m_blk, uint8_t* xbox, float (&v)[32], const float (&z)[32],
-                                                   float cx, float ce, float sg) {
+    __device__ static __forceinline__ void process16(const GemmParams& p, int row, int c0, int r_tile, int m_blk, uint8_t* xrow, int j4_0, const uint32_t (&vr)[16],
+                                                     const float* z, float cx, float ce, float sg) {
         const int sw = r_tile & 7;
-        uint8_t* xrow = xbox + r_tile * 128;
-        float4 xv[8];
+        float4 xv[4];
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) xv[j4] = *reinterpret_cast<const float4*>(xrow + ((j4 ^ sw) << 4));
+        for (int j = 0; j < 4; ++j) xv[j] = *reinterpret_cast<const float4*>(xrow + (((j4_0 + j) ^ sw) << 4));
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-            const int c = c0 + 4 * j4;
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + 4 * j;
             if (MASKED && c >= p.N) {
-                xv[j4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
                 continue;
             }
             float e[4];
             if (MASKED) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) e[i] = (c + i < p.N) ? v[4 * j4 + i] + __ldg(p.bias + c + i) : 0.0f;
+                for (int i = 0; i < 4; ++i) e[i] = (c + i < p.N) ? __uint_as_float(vr[4 * j + i]) + __ldg(p.bias + c + i) : 0.0f;
             } else {
                 const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-                e[0] = v[4 * j4 + 0] + b4.x;
-                e[1] = v[4 * j4 + 1] + b4.y;
-                e[2] = v[4 * j4 + 2] + b4.z;
-                e[3] = v[4 * j4 + 3] + b4.w;
+                e[0] = __uint_as_float(vr[4 * j + 0]) + b4.x;
+                e[1] = __uint_as_float(vr[4 * j + 1]) + b4.y;
+                e[2] = __uint_as_float(vr[4 * j + 2]) + b4.z;
+                e[3] = __uint_as_float(vr[4 * j + 3]) + b4.w;
             }
             if (p.eps_out) {
                 float* eo = p.eps_out + static_cast<size_t>(row) * p.eps_ld + c;
@@ -762,25 +771,24 @@ struct Epilogue<EPI_DDPM> {
                     if (c + i < p.N) eo[i] = e[i];
             }
             float4 xn;
-            xn.x = fmaf(sg, z[4 * j4 + 0], fmaf(cx, xv[j4].x, -ce * e[0]));
-            xn.y = fmaf(sg, z[4 * j4 + 1], fmaf(cx, xv[j4].y, -ce * e[1]));
-            xn.z = fmaf(sg, z[4 * j4 + 2], fmaf(cx, xv[j4].z, -ce * e[2]));
-            xn.w = fmaf(sg, z[4 * j4 + 3], fmaf(cx, xv[j4].w, -ce * e[3]));
+            xn.x = fmaf(sg, z[4 * j + 0], fmaf(cx, xv[j].x, -ce * e[0]));
+            xn.y = fmaf(sg, z[4 * j + 1], fmaf(cx, xv[j].y, -ce * e[1]));
+            xn.z = fmaf(sg, z[4 * j + 2], fmaf(cx, xv[j].z, -ce * e[2]));
+            xn.w = fmaf(sg, z[4 * j + 3], fmaf(cx, xv[j].w, -ce * e[3]));
             if (MASKED) {
                 if (c + 1 >= p.N) xn.y = 0.0f;
                 if (c + 2 >= p.N) xn.z = 0.0f;
                 if (c + 3 >= p.N) xn.w = 0.0f;
             }
-            xv[j4] = xn;
+            xv[j] = xn;
         }
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(xrow + ((j4 ^ sw) << 4)) = xv[j4];
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(xrow + (((j4_0 + j) ^ sw) << 4)) = xv[j];
         if (p.xb && !(p.dbg & 2)) {
-            // blocked shadow: box (m_blk, c0 / 64), row r_tile, 32 consecutive bf16 = 64 contiguous bytes
+            // blocked shadow: box (m_blk, c0 / 64), row r_tile, 16 consecutive bf16 = one full 32-byte sector
             __nv_bfloat16* xbrow = p.xb + ((static_cast<size_t>(m_blk) * p.xb_nbox + (c0 >> 6)) * BM + r_tile) * BK + (c0 & 63);
-            const size_t lo_off = static_cast<size_t>(p.xb_lo_boxes) * BM * BK;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < 2; ++j) {
                 if (MASKED && c0 + 8 * j >= p.N) break;
                 const float4 a = xv[2 * j], b = xv[2 * j + 1];
                 uint4 u;
@@ -795,23 +803,24 @@ struct Epilogue<EPI_DDPM> {
                     l.y = pack_bf16x2(a.z - bf16_round(a.z), a.w - bf16_round(a.w));
                     l.z = pack_bf16x2(b.x - bf16_round(b.x), b.y - bf16_round(b.y));
                     l.w = pack_bf16x2(b.z - bf16_round(b.z), b.w - bf16_round(b.w));
-                    reinterpret_cast<uint4*>(xbrow + lo_off)[j] = l;
+                    reinterpret_cast<uint4*>(xbrow + static_cast<size_t>(p.xb_lo_boxes) * BM * BK)[j] = l;
                 }
             }
         }
     }
 
-    __device__ static __forceinline__ void run_staged(const GemmParams& p, int row, int col, int r_tile, int m_blk, uint8_t* xbox, float (&v)[32], const float (&z)[32],
-                                                      float cx, float ce, float sg) {
+    __device__ static __forceinline__ void run_staged16(const GemmParams& p, int row, int col, int r_tile, int m_blk, uint8_t* xbox, int j4_0, const uint32_t (&vr)[16],
+                                                        const float* z, float cx, float ce, float sg) {
         if (row >= p.M) return;            // rows past the batch: leave the staged tile as loaded
-        if (col >= p.N) {                  // whole 32-column span is padding: keep it at zero
+        uint8_t* xrow = xbox + r_tile * 128;
+        if (col >= p.N) {                  // whole span is padding: keep it at zero
             const int sw = r_tile & 7;
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) *reinterpret_cast<float4*>(xbox + r_tile * 128 + ((j4 ^ sw) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(xrow + (((j4_0 + j) ^ sw) << 4)) = make_float4(0.f, 0.f, 0.f, 0.f);
             return;
         }
-        if (col + 32 <= p.N) process<false>(p, row, col, r_tile, m_blk, xbox, v, z, cx, ce, sg);      // warp-uniform
-        else process<true>(p, row, col, r_tile, m_blk, xbox, v, z, cx, ce, sg);
+        if (col + 16 <= p.N) process16<false>(p, row, col, r_tile, m_blk, xrow, j4_0, vr, z, cx, ce, sg);      // warp-uniform
+        else process16<true>(p, row, col, r_tile, m_blk, xrow, j4_0, vr, z, cx, ce, sg);
     }
 
     template <int GW>
