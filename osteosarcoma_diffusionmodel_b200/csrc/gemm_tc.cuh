@@ -180,6 +180,13 @@ __device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float
     }
 }
 
+// 256-bit global store (sm_100+): one full 32-byte sector per lane.
+__device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&w)[8]) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]),
+                 "r"(w[7])
+                 : "memory");
+}
+
 __device__ __forceinline__ float silu_f(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
 
 // One epilogue pass over 32 columns [col, col+32) of row `row` held in v[].
@@ -787,23 +794,42 @@ struct Epilogue<EPI_DDPM> {
         if (p.xb && !(p.dbg & 2)) {
             // blocked shadow: box (m_blk, c0 / 64), row r_tile, 16 consecutive bf16 = one full 32-byte sector
             __nv_bfloat16* xbrow = p.xb + ((static_cast<size_t>(m_blk) * p.xb_nbox + (c0 >> 6)) * BM + r_tile) * BK + (c0 & 63);
+            if (!MASKED) {
+                // one 256-bit store: a full 32-byte sector per lane
+                uint32_t u[8];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                if (MASKED && c0 + 8 * j >= p.N) break;
-                const float4 a = xv[2 * j], b = xv[2 * j + 1];
-                uint4 u;
-                u.x = pack_bf16x2(a.x, a.y);
-                u.y = pack_bf16x2(a.z, a.w);
-                u.z = pack_bf16x2(b.x, b.y);
-                u.w = pack_bf16x2(b.z, b.w);
-                reinterpret_cast<uint4*>(xbrow)[j] = u;
+                for (int j = 0; j < 4; ++j) {
+                    u[2 * j] = pack_bf16x2(xv[j].x, xv[j].y);
+                    u[2 * j + 1] = pack_bf16x2(xv[j].z, xv[j].w);
+                }
+                st_global_v8(xbrow, u);
                 if (p.xb_lo_boxes > 0) {
-                    uint4 l;
-                    l.x = pack_bf16x2(a.x - bf16_round(a.x), a.y - bf16_round(a.y));
-                    l.y = pack_bf16x2(a.z - bf16_round(a.z), a.w - bf16_round(a.w));
-                    l.z = pack_bf16x2(b.x - bf16_round(b.x), b.y - bf16_round(b.y));
-                    l.w = pack_bf16x2(b.z - bf16_round(b.z), b.w - bf16_round(b.w));
-                    reinterpret_cast<uint4*>(xbrow + static_cast<size_t>(p.xb_lo_boxes) * BM * BK)[j] = l;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        u[2 * j] = pack_bf16x2(xv[j].x - bf16_round(xv[j].x), xv[j].y - bf16_round(xv[j].y));
+                        u[2 * j + 1] = pack_bf16x2(xv[j].z - bf16_round(xv[j].z), xv[j].w - bf16_round(xv[j].w));
+                    }
+                    st_global_v8(xbrow + static_cast<size_t>(p.xb_lo_boxes) * BM * BK, u);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    if (c0 + 8 * j >= p.N) break;
+                    const float4 a = xv[2 * j], b = xv[2 * j + 1];
+                    uint4 u;
+                    u.x = pack_bf16x2(a.x, a.y);
+                    u.y = pack_bf16x2(a.z, a.w);
+                    u.z = pack_bf16x2(b.x, b.y);
+                    u.w = pack_bf16x2(b.z, b.w);
+                    reinterpret_cast<uint4*>(xbrow)[j] = u;
+                    if (p.xb_lo_boxes > 0) {
+                        uint4 l;
+                        l.x = pack_bf16x2(a.x - bf16_round(a.x), a.y - bf16_round(a.y));
+                        l.y = pack_bf16x2(a.z - bf16_round(a.z), a.w - bf16_round(a.w));
+                        l.z = pack_bf16x2(b.x - bf16_round(b.x), b.y - bf16_round(b.y));
+                        l.w = pack_bf16x2(b.z - bf16_round(b.z), b.w - bf16_round(b.w));
+                        reinterpret_cast<uint4*>(xbrow + static_cast<size_t>(p.xb_lo_boxes) * BM * BK)[j] = l;
+                    }
                 }
             }
         }
