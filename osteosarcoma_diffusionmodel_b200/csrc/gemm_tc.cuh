@@ -187,6 +187,19 @@ __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&w)[8]) 
                  : "memory");
 }
 
+// v[j] += src[j], j < 32, through eight 128-bit read-only loads (src 16-byte aligned).
+__device__ __forceinline__ void add_row32(float (&v)[32], const float* __restrict__ src) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 t = __ldg(s4 + j);
+        v[4 * j + 0] += t.x;
+        v[4 * j + 1] += t.y;
+        v[4 * j + 2] += t.z;
+        v[4 * j + 3] += t.w;
+    }
+}
+
 __device__ __forceinline__ float silu_f(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
 
 // One epilogue pass over 32 columns [col, col+32) of row `row` held in v[].
@@ -611,17 +624,23 @@ struct Epilogue<EPI_LINEAR> {
             float(&v)[32] = h ? v1 : v0;
             const int c0 = col + 32 * h;
             if (c0 >= p.N) break;
+            if (live && c0 + 32 <= p.N && ((p.add_tab_ld | p.add_mat_ld) & 3) == 0) {
+                if (p.bias) add_row32(v, p.bias + c0);
+                if (tab) add_row32(v, tab + c0);
+                if (mat) add_row32(v, mat + c0);
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int c = c0 + j;
-                if (live && c < p.N) {
-                    float a = v[j];
-                    if (p.bias) a += __ldg(p.bias + c);
-                    if (tab) a += __ldg(tab + c);
-                    if (mat) a += __ldg(mat + c);
-                    v[j] = a;
-                } else {
-                    v[j] = 0.0f;
+                for (int j = 0; j < 32; ++j) {
+                    const int c = c0 + j;
+                    if (live && c < p.N) {
+                        float a = v[j];
+                        if (p.bias) a += __ldg(p.bias + c);
+                        if (tab) a += __ldg(tab + c);
+                        if (mat) a += __ldg(mat + c);
+                        v[j] = a;
+                    } else {
+                        v[j] = 0.0f;
+                    }
                 }
             }
             if (live && p.out_f32) {
@@ -652,11 +671,8 @@ struct Epilogue<EPI_GN_SILU> {
     template <int GW>
     __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double&) {
         if (row >= p.M) return;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            v0[j] += __ldg(p.bias + col + j);
-            v1[j] += __ldg(p.bias + col + 32 + j);
-        }
+        add_row32(v0, p.bias + col);
+        add_row32(v1, p.bias + col + 32);
         float mean[64 / GW], rstd[64 / GW];
         constexpr int NG = 64 / GW;   // groups inside this thread's 64 columns
 #pragma unroll
@@ -694,10 +710,15 @@ struct Epilogue<EPI_GN_SILU> {
                 v[j] = (v[j] - mean[g]) * rstd[g];
             }
             if (p.xhat_bf) store_row32_bf16(p.xhat_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
+            const float4* g4 = reinterpret_cast<const float4*>(p.gamma + c0);
+            const float4* b4 = reinterpret_cast<const float4*>(p.beta + c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float y = fmaf(v[j], __ldg(p.gamma + c0 + j), __ldg(p.beta + c0 + j));
-                v[j] = silu_f(y);
+            for (int j = 0; j < 8; ++j) {
+                const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+                v[4 * j + 0] = silu_f(fmaf(v[4 * j + 0], g.x, b.x));
+                v[4 * j + 1] = silu_f(fmaf(v[4 * j + 1], g.y, b.y));
+                v[4 * j + 2] = silu_f(fmaf(v[4 * j + 2], g.z, b.z));
+                v[4 * j + 3] = silu_f(fmaf(v[4 * j + 3], g.w, b.w));
             }
             if (p.drop_p > 0.0f) {
                 if (p.drop_mask) {
