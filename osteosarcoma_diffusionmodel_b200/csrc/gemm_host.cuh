@@ -16,7 +16,7 @@ int launch_gemm_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
     if (tiles <= 0) return 0;
     if (EPI == EPI_DDPM && p.a_resident) tiles = p.m_tiles * p.n_chunks;      // work units, not tiles
     const int grid = tiles < num_sms ? tiles : num_sms;
-    gemm_tc_kernel<EPI, GW, MN><<<grid, gemm_threads<EPI>(), gemm_smem_bytes<EPI>(), stream>>>(p);
+    gemm_tc_kernel<EPI, GW, MN><<<grid, gemm_threads<EPI, GW>(), gemm_smem_bytes<EPI>(), stream>>>(p);
     OSTEO_CUDA(cudaGetLastError());
     return 0;
 }

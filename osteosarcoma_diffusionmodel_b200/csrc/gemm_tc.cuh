@@ -33,10 +33,11 @@ constexpr int X_BUFFERS = 2;
 constexpr int NUM_ACC = 4;
 // Epilogue warps: 8 (thread <-> row x 64 columns: a whole GroupNorm group per thread) except for the RNG-heavy
 // reverse-update epilogue, which runs 16 (thread <-> row x 32 columns) to double the warps per scheduler.
-template <int EPI>
-__host__ __device__ constexpr int epi_warps_of() { return EPI == 2 /*EPI_DDPM*/ ? 16 : 8; }
-template <int EPI>
-__host__ __device__ constexpr int gemm_threads() { return 128 + 32 * epi_warps_of<EPI>(); }
+// ... and for Linear+GroupNorm+SiLU with groups of <= 32 columns (a group still fits one thread's 32 columns).
+template <int EPI, int GW>
+__host__ __device__ constexpr int epi_warps_of() { return (EPI == 2 /*EPI_DDPM*/ || (EPI == 1 /*EPI_GN_SILU*/ && GW <= 32)) ? 16 : 8; }
+template <int EPI, int GW>
+__host__ __device__ constexpr int gemm_threads() { return 128 + 32 * epi_warps_of<EPI, GW>(); }
 constexpr int A_TILE_BYTES = BM * BK * 2;
 constexpr int B_TILE_BYTES = BN * BK * 2;
 template <int EPI>
@@ -276,12 +277,12 @@ struct TileSeq {
 };
 
 template <int EPI, int GW, bool MN = false>
-__global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
     constexpr int STAGES = stages_of<EPI>();
     constexpr bool XSTAGE = (EPI == EPI_DDPM);
-    constexpr int NUM_EPI_WARPS = epi_warps_of<EPI>();
+    constexpr int NUM_EPI_WARPS = epi_warps_of<EPI, GW>();
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + STAGES * A_TILE_BYTES;
     uint8_t* smem_x = smem + STAGES * (A_TILE_BYTES + B_TILE_BYTES);      // 1024-aligned: stages are multiples of 32 KB
@@ -552,6 +553,15 @@ __global__ void __launch_bounds__(gemm_threads<EPI>(), 1) gemm_tc_kernel(const _
                 }
                 pending_xb = (p.dbg & 16) ? -1 : xb;      // released after the next tile's noise draw (or after the loop)
                 __syncwarp();
+            } else if constexpr (CPT == 32) {
+                if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
+                tc_fence_after_sync();
+                float v[32];
+                tmem_ld_32(taddr, v);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                Epilogue<EPI>::template run32<GW>(p, row, col, v);
             } else {
                 if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
                 tc_fence_after_sync();
@@ -665,6 +675,67 @@ struct Epilogue<EPI_LINEAR> {
 
 template <>
 struct Epilogue<EPI_GN_SILU> {
+    // 32-column variant (16 epilogue warps, GW <= 32): same arithmetic as run<GW> below on one 32-column span.
+    template <int GW>
+    __device__ static __forceinline__ void run32(const GemmParams& p, int row, int col, float (&v)[32]) {
+        if (row >= p.M) return;
+        static_assert(GW <= 32, "a GroupNorm group must fit the thread's 32 columns");
+        constexpr int NG = 32 / GW;
+        add_row32(v, p.bias + col);
+        float mean[NG], rstd[NG];
+#pragma unroll
+        for (int g = 0; g < NG; ++g) {
+            float s = 0.0f;
+#pragma unroll
+            for (int j = 0; j < GW; ++j) s += v[g * GW + j];
+            const float mu = s * (1.0f / GW);
+            float ss = 0.0f;
+#pragma unroll
+            for (int j = 0; j < GW; ++j) {
+                const float d = v[g * GW + j] - mu;
+                ss = fmaf(d, d, ss);
+            }
+            mean[g] = mu;
+            rstd[g] = rsqrtf(ss * (1.0f / GW) + p.gn_eps);
+        }
+        if (p.rstd_out) {
+            const int g0 = col / GW;
+#pragma unroll
+            for (int g = 0; g < NG; ++g) p.rstd_out[static_cast<size_t>(row) * 8 + g0 + g] = rstd[g];
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean[j / GW]) * rstd[j / GW];
+        if (p.xhat_bf) store_row32_bf16(p.xhat_bf + static_cast<size_t>(row) * p.out_bf_ld + col, v, p.out_lo_off);
+        const float4* g4 = reinterpret_cast<const float4*>(p.gamma + col);
+        const float4* b4 = reinterpret_cast<const float4*>(p.beta + col);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+            v[4 * j + 0] = silu_f(fmaf(v[4 * j + 0], g.x, b.x));
+            v[4 * j + 1] = silu_f(fmaf(v[4 * j + 1], g.y, b.y));
+            v[4 * j + 2] = silu_f(fmaf(v[4 * j + 2], g.z, b.z));
+            v[4 * j + 3] = silu_f(fmaf(v[4 * j + 3], g.w, b.w));
+        }
+        if (p.drop_p > 0.0f) {
+            const float keep_scale = 1.0f / (1.0f - p.drop_p);
+            if (p.drop_mask) {
+                const uint8_t* mk = p.drop_mask + static_cast<size_t>(row) * p.N + col;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = mk[j] ? v[j] * keep_scale : 0.0f;
+            } else {
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const uint4 w = philox_words(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>((col >> 2) + j4), p.drop_stream, p.step ? static_cast<uint32_t>(*p.step) : 0u);
+                    v[4 * j4 + 0] = (u01(w.x) >= p.drop_p) ? v[4 * j4 + 0] * keep_scale : 0.0f;
+                    v[4 * j4 + 1] = (u01(w.y) >= p.drop_p) ? v[4 * j4 + 1] * keep_scale : 0.0f;
+                    v[4 * j4 + 2] = (u01(w.z) >= p.drop_p) ? v[4 * j4 + 2] * keep_scale : 0.0f;
+                    v[4 * j4 + 3] = (u01(w.w) >= p.drop_p) ? v[4 * j4 + 3] * keep_scale : 0.0f;
+                }
+            }
+        }
+        store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + col, v, p.out_lo_off);
+    }
+
     // GroupNorm(8, N) -> group width GW = N / 8. Biased variance, eps inside the sqrt
     // (torch.nn.GroupNorm, models/diffusion.py:202,206), then SiLU (:203,207) and the
     // block's Dropout (:204) when drop_p > 0.
