@@ -50,13 +50,13 @@ def report(path, out, traffic):
             tr.setdefault(r[idx["Kernel Name"]], []).append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
     print(open(out).read())
     if traffic:
-        names = {"gemm_tc_kernel<2, 64>": "output_proj+reverse_update", "gemm_tc_kernel<0, 64>": "input_proj+emb_add"}
+        names = {"gemm_tc_kernel<2,": "output_proj+reverse_update", "gemm_tc_kernel<0,": "input_proj+emb_add"}
         outj = {}
         for k, v in tr.items():
             for pat, nice in names.items():
                 if pat in k:
                     outj[nice] = sum(v) / len(v)
-        outj["_note"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch (one 32768-row chunk) from {path}"
+        outj["_note"] = f"dram__bytes_read.sum + dram__bytes_write.sum per launch (100k patients, one row chunk) from {path}"
         json.dump(outj, open(traffic, "w"), indent=1)
 
 
