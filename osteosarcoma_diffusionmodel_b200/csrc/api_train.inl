@@ -130,10 +130,10 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
                                                                              w.noise.as<float>(), DP, w.xt_bf.as<__nv_bfloat16>(), 2 * DP, c->lo(DP), seed, row_base);
     OSTEO_CUDA(cudaGetLastError());
     {
-        const size_t smem = sizeof(float) * 8 * (c->C + 2 * E);
-        cond_path_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, s>>>(cond_dev, n, c->C, E, h0, c->ce_w0.as<float>(), c->ce_b0.as<float>(), c->ce_w2.as<float>(),
-                                                                             c->ce_b2.as<float>(), c->cp_w.as<float>(), c->cp_b.as<float>(), c->cproj.as<float>(),
-                                                                             w.pre0.as<float>(), w.cemb.as<float>());
+        const size_t smem = sizeof(float) * 16 * (c->C + 2 * E);
+        cond_path_kernel<<<static_cast<unsigned>((n + 15) / 16), 256, smem, s>>>(cond_dev, n, c->C, E, h0, c->ce_w0t.as<float>(), c->ce_b0.as<float>(),
+                                                                               c->ce_w2t.as<float>(), c->ce_b2.as<float>(), c->cp_wt.as<float>(), c->cp_b.as<float>(),
+                                                                               c->cproj.as<float>(), w.pre0.as<float>(), w.cemb.as<float>());
         OSTEO_CUDA(cudaGetLastError());
     }
     c->launches += 3;

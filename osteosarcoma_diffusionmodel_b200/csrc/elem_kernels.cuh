@@ -210,14 +210,21 @@ __global__ void time_table_kernel(const float* __restrict__ emb, const float* __
     }
 }
 
+// dst[c, r] = src[r, c] (tiny weight matrices; run once per set_weights)
+__global__ void transpose_f32_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < rows * cols) dst[(i % cols) * rows + i / cols] = src[i];
+}
+
 // ConditionalEmbedding (Linear C->E, SiLU, Linear E->E; models/diffusion.py:101-114) followed by
-// cond_proj (Linear E->h0; :226). fp32 on CUDA cores: runs once per sample() call. One block = 8 rows.
-// Optionally keeps the intermediate activations for the training backward.
+// cond_proj (Linear E->h0; :226). fp32 on CUDA cores: once per sample() call, once per training step. One block = 16 rows.
+// The three weight matrices are passed TRANSPOSED ([in, out]) so that consecutive threads (consecutive output features)
+// read consecutive addresses. Optionally keeps the intermediate activations for the training backward.
 __global__ void cond_path_kernel(const float* __restrict__ cond, long long n, int C, int E, int h0,
-                                 const float* __restrict__ w0, const float* __restrict__ b0, const float* __restrict__ w2, const float* __restrict__ b2,
-                                 const float* __restrict__ wc, const float* __restrict__ bc, float* __restrict__ cproj,
+                                 const float* __restrict__ w0t, const float* __restrict__ b0, const float* __restrict__ w2t, const float* __restrict__ b2,
+                                 const float* __restrict__ wct, const float* __restrict__ bc, float* __restrict__ cproj,
                                  float* __restrict__ save_pre0, float* __restrict__ save_emb) {
-    constexpr int R = 8;
+    constexpr int R = 16;
     extern __shared__ float sm[];
     float* s_c = sm;                 // [R, C]
     float* s_h = s_c + R * C;        // [R, E]
@@ -231,7 +238,7 @@ __global__ void cond_path_kernel(const float* __restrict__ cond, long long n, in
     for (int i = threadIdx.x; i < R * E; i += blockDim.x) {
         const int rr = i / E, j = i % E;
         float a = b0[j];
-        for (int k = 0; k < C; ++k) a = fmaf(s_c[rr * C + k], w0[j * C + k], a);
+        for (int k = 0; k < C; ++k) a = fmaf(s_c[rr * C + k], w0t[k * E + j], a);
         if (save_pre0 && r0 + rr < n) save_pre0[(r0 + rr) * E + j] = a;
         s_h[i] = a / (1.0f + expf(-a));
     }
@@ -239,17 +246,26 @@ __global__ void cond_path_kernel(const float* __restrict__ cond, long long n, in
     for (int i = threadIdx.x; i < R * E; i += blockDim.x) {
         const int rr = i / E, j = i % E;
         float a = b2[j];
-        for (int k = 0; k < E; ++k) a = fmaf(s_h[rr * E + k], w2[j * E + k], a);
+#pragma unroll 8
+        for (int k = 0; k < E; ++k) a = fmaf(s_h[rr * E + k], w2t[k * E + j], a);
         if (save_emb && r0 + rr < n) save_emb[(r0 + rr) * E + j] = a;
         s_e[i] = a;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < R * h0; i += blockDim.x) {
-        const int rr = i / h0, j = i % h0;
-        if (r0 + rr >= n) continue;
-        float a = bc[j];
-        for (int k = 0; k < E; ++k) a = fmaf(s_e[rr * E + k], wc[j * E + k], a);
-        cproj[(r0 + rr) * h0 + j] = a;
+    // each thread owns one output feature j for all R rows: the weight column is read once per block
+    for (int j = threadIdx.x; j < h0; j += blockDim.x) {
+        float acc[R];
+        const float bj = bc[j];
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) acc[rr] = bj;
+        for (int k = 0; k < E; ++k) {
+            const float w = wct[k * h0 + j];
+#pragma unroll
+            for (int rr = 0; rr < R; ++rr) acc[rr] = fmaf(s_e[rr * E + k], w, acc[rr]);
+        }
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr)
+            if (r0 + rr < n) cproj[(r0 + rr) * h0 + j] = acc[rr];
     }
 }
 

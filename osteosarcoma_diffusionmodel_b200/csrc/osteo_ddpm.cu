@@ -167,6 +167,7 @@ struct osteo_ddpm_ctx {
 
     // parameters
     DevBuf ce_w0, ce_b0, ce_w2, ce_b2, cp_w, cp_b, tp_w, tp_b;   // fp32 copies of the small layers
+    DevBuf ce_w0t, ce_w2t, cp_wt;                                // ... and [in, out] transposes for the coalesced forward
     PackedLinear in_proj, out_proj;
     std::vector<std::unique_ptr<HalfBlock>> halves;
     DevBuf emb_table, time_table;        // [T, TD], [T, h0] fp32
@@ -459,6 +460,9 @@ int osteo_ddpm_create(osteo_ddpm_ctx** out, int device, int data_dim, int cond_d
     OSTEO_TRY(c->ce_w2.alloc(sizeof(float) * c->E * c->E));
     OSTEO_TRY(c->ce_b2.alloc(sizeof(float) * c->E));
     OSTEO_TRY(c->cp_w.alloc(sizeof(float) * h0 * c->E));
+    OSTEO_TRY(c->ce_w0t.alloc(sizeof(float) * c->E * c->C));
+    OSTEO_TRY(c->ce_w2t.alloc(sizeof(float) * c->E * c->E));
+    OSTEO_TRY(c->cp_wt.alloc(sizeof(float) * h0 * c->E));
     OSTEO_TRY(c->cp_b.alloc(sizeof(float) * h0));
     OSTEO_TRY(c->tp_w.alloc(sizeof(float) * h0 * c->TD));
     OSTEO_TRY(c->tp_b.alloc(sizeof(float) * h0));
@@ -612,6 +616,10 @@ int osteo_ddpm_set_weights(osteo_ddpm_ctx* c, const float* const* w, int n_tenso
     OSTEO_TRY(copy(c->cp_b, w[7]));
     OSTEO_TRY(copy(c->tp_w, w[8]));
     OSTEO_TRY(copy(c->tp_b, w[9]));
+    transpose_f32_kernel<<<(c->E * c->C + 255) / 256, 256, 0, s>>>(c->ce_w0.as<float>(), c->E, c->C, c->ce_w0t.as<float>());
+    transpose_f32_kernel<<<(c->E * c->E + 255) / 256, 256, 0, s>>>(c->ce_w2.as<float>(), c->E, c->E, c->ce_w2t.as<float>());
+    transpose_f32_kernel<<<(c->h0() * c->E + 255) / 256, 256, 0, s>>>(c->cp_w.as<float>(), c->h0(), c->E, c->cp_wt.as<float>());
+    OSTEO_CUDA(cudaGetLastError());
     int idx = 10;
     for (auto& hb : c->halves) {
         OSTEO_TRY(hb->lin.upload(w[idx], w[idx + 1], c->sms, s));
@@ -689,10 +697,10 @@ int osteo_ddpm_set_conditions(osteo_ddpm_ctx* c, const float* cond_dev, long lon
     if (!c->have_weights) return fail("weights not set");
     if (n <= 0 || n > c->cap) return fail("set_conditions: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const size_t smem = sizeof(float) * 8 * (c->C + 2 * c->E);
-    cond_path_kernel<<<static_cast<unsigned>((n + 7) / 8), 256, smem, s>>>(cond_dev, n, c->C, c->E, c->h0(), c->ce_w0.as<float>(), c->ce_b0.as<float>(),
-                                                                         c->ce_w2.as<float>(), c->ce_b2.as<float>(), c->cp_w.as<float>(), c->cp_b.as<float>(),
-                                                                         c->cproj.as<float>(), nullptr, nullptr);
+    const size_t smem = sizeof(float) * 16 * (c->C + 2 * c->E);
+    cond_path_kernel<<<static_cast<unsigned>((n + 15) / 16), 256, smem, s>>>(cond_dev, n, c->C, c->E, c->h0(), c->ce_w0t.as<float>(), c->ce_b0.as<float>(),
+                                                                           c->ce_w2t.as<float>(), c->ce_b2.as<float>(), c->cp_wt.as<float>(), c->cp_b.as<float>(),
+                                                                           c->cproj.as<float>(), nullptr, nullptr);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     return 0;
