@@ -384,14 +384,14 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)      # utils/train.py:169-173
 
     def step():
-        opt.zero_grad(set_to_none=False)
+        opt.zero_grad()                       # utils/train.py:230
         loss = model(x0, cond, return_loss=True)
         loss.backward()
         torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
         opt.step()
 
     def fwd_bwd():
-        model.zero_grad(set_to_none=False)
+        model.zero_grad()
         model(x0, cond, return_loss=True).backward()
 
     ms = timed(step, 3, 10)

@@ -197,16 +197,29 @@ __global__ void reverse_update_kernel(float* __restrict__ x, const float* __rest
 }
 
 // time_proj(time_embed(t / T)) for every integer t (models/diffusion.py:222-223): table[t, n] = emb[t, :] . W[n, :] + b[n].
-__global__ void time_table_kernel(const float* __restrict__ emb, const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ table, int T, int td, int h0) {
-    const int t = blockIdx.x;
-    extern __shared__ float e[];
-    for (int k = threadIdx.x; k < td; k += blockDim.x) e[k] = emb[static_cast<long long>(t) * td + k];
+// wt is the TRANSPOSED weight [td, h0] (coalesced across n); one block = 8 timesteps, each thread owns output features.
+__global__ void time_table_kernel(const float* __restrict__ emb, const float* __restrict__ wt, const float* __restrict__ b, float* __restrict__ table, int T, int td, int h0) {
+    constexpr int R = 8;
+    extern __shared__ float e[];          // [R, td]
+    const int t0 = blockIdx.x * R;
+    for (int i = threadIdx.x; i < R * td; i += blockDim.x) {
+        const int t = t0 + i / td;
+        e[i] = t < T ? emb[static_cast<long long>(t) * td + i % td] : 0.0f;
+    }
     __syncthreads();
     for (int n = threadIdx.x; n < h0; n += blockDim.x) {
-        float acc = 0.0f;
-        const float* wr = w + static_cast<long long>(n) * td;
-        for (int k = 0; k < td; ++k) acc = fmaf(e[k], wr[k], acc);
-        table[static_cast<long long>(t) * h0 + n] = acc + b[n];
+        float acc[R];
+        const float bn = b[n];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = bn;
+        for (int k = 0; k < td; ++k) {
+            const float w = wt[static_cast<long long>(k) * h0 + n];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = fmaf(e[r * td + k], w, acc[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (t0 + r < T) table[static_cast<long long>(t0 + r) * h0 + n] = acc[r];
     }
 }
 

@@ -961,17 +961,33 @@ struct Epilogue<EPI_MSE> {
             float(&v)[32] = h ? v1 : v0;
             const int c0 = col + 32 * h;
             if (c0 >= p.N) break;      // warp-uniform
+            if (live && c0 + 32 <= p.N && (p.target_ld & 3) == 0 && !p.eps_out) {
+                // interior span: 128-bit loads of the bias and of this row's noise target
+                add_row32(v, p.bias + c0);
+                const float4* t4 = reinterpret_cast<const float4*>(trow + c0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int c = c0 + j;
-                float d = 0.0f;
-                if (live && c < p.N) {
-                    const float e = v[j] + __ldg(p.bias + c);
-                    if (p.eps_out) p.eps_out[static_cast<size_t>(row) * p.eps_ld + c] = e;
-                    d = e - trow[c];
-                    local = fmaf(d, d, local);
+                for (int j = 0; j < 8; ++j) {
+                    const float4 t = __ldg(t4 + j);
+                    const float d0 = v[4 * j + 0] - t.x, d1 = v[4 * j + 1] - t.y, d2 = v[4 * j + 2] - t.z, d3 = v[4 * j + 3] - t.w;
+                    local = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, fmaf(d3, d3, local))));
+                    v[4 * j + 0] = d0 * p.grad_scale;
+                    v[4 * j + 1] = d1 * p.grad_scale;
+                    v[4 * j + 2] = d2 * p.grad_scale;
+                    v[4 * j + 3] = d3 * p.grad_scale;
                 }
-                v[j] = d * p.grad_scale;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int c = c0 + j;
+                    float d = 0.0f;
+                    if (live && c < p.N) {
+                        const float e = v[j] + __ldg(p.bias + c);
+                        if (p.eps_out) p.eps_out[static_cast<size_t>(row) * p.eps_ld + c] = e;
+                        d = e - trow[c];
+                        local = fmaf(d, d, local);
+                    }
+                    v[j] = d * p.grad_scale;
+                }
             }
             if (live && p.out_bf) store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
             if (p.col_partials) {

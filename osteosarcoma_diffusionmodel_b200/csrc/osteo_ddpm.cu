@@ -167,6 +167,7 @@ struct osteo_ddpm_ctx {
 
     // parameters
     DevBuf ce_w0, ce_b0, ce_w2, ce_b2, cp_w, cp_b, tp_w, tp_b;   // fp32 copies of the small layers
+    DevBuf tp_wt;                                                // time_proj.weight^T [TD, h0]
     DevBuf ce_w0t, ce_w2t, cp_wt;                                // ... and [in, out] transposes for the coalesced forward
     PackedLinear in_proj, out_proj;
     std::vector<std::unique_ptr<HalfBlock>> halves;
@@ -404,8 +405,8 @@ static int require_ready(const osteo_ddpm_ctx* c, long long n) {
 
 static int rebuild_time_table(osteo_ddpm_ctx* c, cudaStream_t s) {
     if (!c->have_weights || !c->have_emb) return 0;
-    time_table_kernel<<<c->T, 256, c->TD * sizeof(float), s>>>(c->emb_table.as<float>(), c->tp_w.as<float>(), c->tp_b.as<float>(),
-                                                                c->time_table.as<float>(), c->T, c->TD, c->h0());
+    time_table_kernel<<<(c->T + 7) / 8, 256, 8 * c->TD * sizeof(float), s>>>(c->emb_table.as<float>(), c->tp_wt.as<float>(), c->tp_b.as<float>(),
+                                                                              c->time_table.as<float>(), c->T, c->TD, c->h0());
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -463,6 +464,7 @@ int osteo_ddpm_create(osteo_ddpm_ctx** out, int device, int data_dim, int cond_d
     OSTEO_TRY(c->ce_w0t.alloc(sizeof(float) * c->E * c->C));
     OSTEO_TRY(c->ce_w2t.alloc(sizeof(float) * c->E * c->E));
     OSTEO_TRY(c->cp_wt.alloc(sizeof(float) * h0 * c->E));
+    OSTEO_TRY(c->tp_wt.alloc(sizeof(float) * h0 * c->TD));
     OSTEO_TRY(c->cp_b.alloc(sizeof(float) * h0));
     OSTEO_TRY(c->tp_w.alloc(sizeof(float) * h0 * c->TD));
     OSTEO_TRY(c->tp_b.alloc(sizeof(float) * h0));
@@ -619,6 +621,7 @@ int osteo_ddpm_set_weights(osteo_ddpm_ctx* c, const float* const* w, int n_tenso
     transpose_f32_kernel<<<(c->E * c->C + 255) / 256, 256, 0, s>>>(c->ce_w0.as<float>(), c->E, c->C, c->ce_w0t.as<float>());
     transpose_f32_kernel<<<(c->E * c->E + 255) / 256, 256, 0, s>>>(c->ce_w2.as<float>(), c->E, c->E, c->ce_w2t.as<float>());
     transpose_f32_kernel<<<(c->h0() * c->E + 255) / 256, 256, 0, s>>>(c->cp_w.as<float>(), c->h0(), c->E, c->cp_wt.as<float>());
+    transpose_f32_kernel<<<(c->h0() * c->TD + 255) / 256, 256, 0, s>>>(c->tp_w.as<float>(), c->h0(), c->TD, c->tp_wt.as<float>());
     OSTEO_CUDA(cudaGetLastError());
     int idx = 10;
     for (auto& hb : c->halves) {

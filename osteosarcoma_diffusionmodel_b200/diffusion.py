@@ -101,7 +101,8 @@ class _TrainStep(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         grads = ctx.saved_tensors
-        return (None, None, None, None) + tuple(g * grad_out for g in grads)
+        # one fused multi-tensor kernel instead of 52 tiny launches
+        return (None, None, None, None) + tuple(torch._foreach_mul(list(grads), grad_out))
 
 
 class BiologyAwareDiffusionModel(nn.Module):
