@@ -140,12 +140,26 @@ int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long 
     const bool x3 = precision == OSTEO_PREC_FP32X3;
     const int kp = static_cast<int>(round_up(d, BK));
     const long long np = round_up(n, BM), mp = round_up(m, BM);
-    DevBuf xb, yb, nx, ny, status;
-    OSTEO_TRY(xb.alloc(static_cast<size_t>(np) * 2 * kp * 2));
-    OSTEO_TRY(yb.alloc(static_cast<size_t>(mp) * 2 * kp * 2));
-    OSTEO_TRY(nx.alloc(static_cast<size_t>(np) * 4));
-    OSTEO_TRY(ny.alloc(static_cast<size_t>(mp) * 4));
-    OSTEO_TRY(status.alloc(sizeof(int)));
+    // Packed operands live in a grow-only per-process workspace: cudaMalloc / cudaFree of hundreds of MB per call costs more
+    // than the Gram itself at 16k rows (and synchronises the device). Not thread-safe; one validator per process.
+    static DevBuf xb, yb, nx, ny, status;
+    static int ws_device = -1;
+    int dev_now = 0;
+    OSTEO_CUDA(cudaGetDevice(&dev_now));
+    if (dev_now != ws_device) {
+        for (DevBuf* b : {&xb, &yb, &nx, &ny, &status}) b->release();
+        ws_device = dev_now;
+    }
+    auto grow = [](DevBuf& b, size_t bytes) -> int {
+        if (b.bytes >= bytes) return 0;
+        OSTEO_CUDA(cudaDeviceSynchronize());
+        return b.alloc(bytes);
+    };
+    OSTEO_TRY(grow(xb, static_cast<size_t>(np) * 2 * kp * 2));
+    OSTEO_TRY(grow(yb, static_cast<size_t>(mp) * 2 * kp * 2));
+    OSTEO_TRY(grow(nx, static_cast<size_t>(np) * 4));
+    OSTEO_TRY(grow(ny, static_cast<size_t>(mp) * 4));
+    OSTEO_TRY(grow(status, sizeof(int)));
     OSTEO_CUDA(cudaMemsetAsync(status.p, 0, sizeof(int), s));
     OSTEO_CUDA(cudaMemsetAsync(sums_dev, 0, 3 * sizeof(double), s));
     const int lo = x3 ? kp : 0;

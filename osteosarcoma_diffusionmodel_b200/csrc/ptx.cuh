@@ -44,18 +44,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
-    // The suspend-time hint lets the hardware park the warp (no issue slots burnt) until the phase flips or ~2 us elapse.
+    // No suspend-time hint: an explicit hint (tried: 2 us) made every not-yet-complete wait sleep the full interval and slowed
+    // the deep-K MMD pipeline 30x; the default hardware time limit wakes up promptly.
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
     return ok != 0;
 }
-// Bounded wait. Returns false on timeout (~2 s): each failed try_wait already slept up to the hint, so the
-// clock is only consulted every 64 iterations.
+// Bounded wait. Returns false on timeout (~2 s); the clock is only consulted every 64 failed polls.
 __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
