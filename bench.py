@@ -109,7 +109,7 @@ def cpu_reference_rate(rows: int, steps: int, repeats: int = 1):
     scaled to the 1000 steps a patient needs. Noise is drawn inside the timed region as the reference does."""
     import torch
     from oracle import ddpm_oracle as O
-    from oracle import synth
+    from osteosarcoma_diffusionmodel_b200 import synthetic as synth
 
     torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.make_params(D, N_COND, HIDDEN, seed=0)
@@ -198,7 +198,7 @@ def run_ours(args):
     from osteosarcoma_diffusionmodel_b200 import build
     from osteosarcoma_diffusionmodel_b200.diffusion import BiologyAwareDiffusionModel
     from osteosarcoma_diffusionmodel_b200 import _lib
-    from oracle import synth   # deterministic synthetic weights / cohort generator only (no compute)
+    from osteosarcoma_diffusionmodel_b200 import synthetic as synth   # deterministic synthetic weights / cohort generator
 
     build.build()
     rows = args.rows
@@ -357,9 +357,9 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
     pathway-coherence moments, each timed with CUDA events after warm-up. CPU figures are the oracle port on bounded samples."""
     import numpy as np
     import torch
-    from oracle import ddpm_oracle as O
-    from oracle import synth
-    from oracle import validators_oracle as V
+    from oracle import ddpm_oracle as O            # CPU-port legs only
+    from oracle import validators_oracle as V      # CPU-port legs only
+    from osteosarcoma_diffusionmodel_b200 import synthetic as synth
     from osteosarcoma_diffusionmodel_b200.validation import BiologicalValidator
 
     out = {}

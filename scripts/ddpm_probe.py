@@ -2,7 +2,7 @@
 import sys, ctypes as C
 sys.path.insert(0, ".")
 import torch
-from oracle import synth
+from osteosarcoma_diffusionmodel_b200 import synthetic as synth
 from osteosarcoma_diffusionmodel_b200.diffusion import BiologyAwareDiffusionModel
 from osteosarcoma_diffusionmodel_b200 import _lib
 

@@ -3,7 +3,7 @@ eagerly (no graph) so every kernel is a separate launch. Used for profiles/*.csv
 import sys
 sys.path.insert(0, ".")
 import torch
-from oracle import synth
+from osteosarcoma_diffusionmodel_b200 import synthetic as synth
 from osteosarcoma_diffusionmodel_b200.diffusion import BiologyAwareDiffusionModel
 
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 100_000

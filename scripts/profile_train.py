@@ -2,7 +2,7 @@
 import sys
 sys.path.insert(0, ".")
 import torch
-from oracle import synth
+from osteosarcoma_diffusionmodel_b200 import synthetic as synth
 from osteosarcoma_diffusionmodel_b200.diffusion import BiologyAwareDiffusionModel
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
