@@ -160,7 +160,7 @@ def workload_config(args, rows_per_gpu):
     return {"workload": "1000-step conditional DDPM sampling, config.yaml dims (5142 features, 3 conditions, hidden [256,512,256], cosine), "
                         "three config.yaml scenarios in equal thirds (BASELINE.json configs[1])",
             "patients_per_gpu": rows_per_gpu, "num_steps": T_STEPS, "precision": args.precision,
-            "rng": "in-kernel Philox4x32-10 keyed by (seed, global row, t, column)", "weights": "random init (oracle/synth.py seed 0)",
+            "rng": "in-kernel Philox4x32-10 keyed by (seed, global row, t, column)", "weights": "random init (synthetic.make_params seed 0)",
             "l2_policy": "state (fp32 x + bf16 shadow = 3.1 GB per 100k patients) is larger than L2; no flush needed",
             "sharding": "contiguous global-row ranges per rank, no data-path collective"}
 
