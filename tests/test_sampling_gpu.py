@@ -161,3 +161,61 @@ def test_standalone_reverse_update_matches_fused_epilogue():
     x2 = x.clone()
     _lib.check(_lib.load().osteo_ddpm_reverse_update(model._ctx, x2.data_ptr(), eps.data_ptr(), z.data_ptr(), B, t, 0, 0, _lib.stream_handle()))
     assert torch.equal(x2, nxt)
+
+
+@pytest.mark.parametrize("hidden", [(128, 128), (512, 256, 128, 256), (256, 256, 256)])
+def test_other_topologies_match_the_oracle(hidden):
+    """The constructor is generic in hidden_dims (models/diffusion.py:171-193): encoder / bottleneck / decoder wiring and the
+    GroupNorm group widths 16 / 32 / 64 against the oracle for a short injected-noise loop and one training step."""
+    dims = dict(mutation_dim=12, expression_dim=100, pathway_dim=8, condition_dim=3)
+    D, T, rows = 120, 1000, 70
+    sd = synth.make_params(D, 3, hidden, seed=11)
+    osd = dict(sd)
+    osd.update(O.schedule_buffers("cosine", T))
+    from osteosarcoma_diffusionmodel_b200.diffusion import BiologyAwareDiffusionModel
+    model = BiologyAwareDiffusionModel(12, 100, 8, 3, synth.model_config(hidden_dims=hidden))
+    model.load_state_dict(sd, strict=False)
+    model = model.cuda().eval().set_precision("fp32x3")
+    draw = synth.noise_stream(17)
+    cond = synth.scenario_conditions(rows, 3)
+    x_T = draw(1, (rows, D))
+    t_stop = 990
+    noises = {t: draw(100 + t, (rows, D)) for t in range(t_stop, T)}
+    ref = O.sample(osd, cond, x_T, lambda t: noises[t], T, t_stop=t_stop)
+    got = model.sample(cond, rows, x_T=x_T, noise=torch.stack([noises[t] for t in reversed(range(t_stop, T))]), t_stop=t_stop)
+    assert rel(got, ref) < TOL_FP32X3
+    # one training step: loss and every gradient
+    x0, c = synth.make_cohort(rows, 12, 100, 8, 3, seed=2)
+    t = torch.from_numpy(np.random.RandomState(3).randint(0, T, size=rows).astype(np.int64))
+    noise = draw(7, (rows, D))
+    masks = synth.dropout_masks(5, rows, synth.block_widths(hidden), 0.2)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    full = dict(osd)
+    full.update(params)
+    ref_loss = O.forward_loss(full, x0, c, t, noise, T, drop_masks=masks, p=0.2, training=True)
+    ref_loss.backward()
+    model.train()
+    model._inject = {"t": t, "noise": noise, "masks": masks}
+    loss = model(x0.cuda(), c.cuda())
+    loss.backward()
+    assert abs(loss.item() - ref_loss.item()) < 1e-5 * abs(ref_loss.item())
+    for n, p in model.named_parameters():
+        assert rel(p.grad, params[n].grad) < 2e-4, n
+    model.check_status()
+
+
+def test_more_rows_than_one_chunk_and_single_row():
+    case = load_case("linear3")
+    model = build_model(case, "bf16")
+    model.set_chunk_rows(256)
+    n = 1000
+    _, cond = synth.make_cohort(n, 20, 90, 10, 2, seed=8)
+    a = model.sample(cond, n, seed=3, t_stop=995)
+    model.set_chunk_rows(0)
+    b = model.sample(cond, n, seed=3, t_stop=995)
+    assert torch.equal(a, b)
+    one = model.sample(cond[:1], 1, seed=3, t_stop=995)
+    assert torch.equal(one, a[:1])
+    with pytest.raises(ValueError):
+        model.sample(cond[:3], 5)
+    model.check_status()
