@@ -161,7 +161,7 @@ def workload_config(args, rows_per_gpu):
                         "three config.yaml scenarios in equal thirds (BASELINE.json configs[1])",
             "patients_per_gpu": rows_per_gpu, "num_steps": T_STEPS, "precision": args.precision,
             "rng": "in-kernel Philox4x32-10 keyed by (seed, global row, t, column)", "weights": "random init (synthetic.make_params seed 0)",
-            "l2_policy": "state (fp32 x + bf16 shadow = 3.1 GB per 100k patients) is larger than L2; no flush needed",
+            "l2_policy": "fp32 state (2.1 GB per 100k patients) is larger than L2; no flush needed",
             "sharding": "contiguous global-row ranges per rank, no data-path collective"}
 
 
@@ -289,18 +289,21 @@ def run_ours(args):
                 _lib.check(n_l)
             per.append([buf[i] for i in range(n_l)])
         per = np.array(per[1:]).mean(axis=0)            # drop the first repetition
-        n_chunks = max(1, len(per) // 12)
-        names = ["input_proj+emb_add"] + [f"linear_gn_silu_{i}" for i in range(10)] + ["output_proj+reverse_update"]
+        fused = bool(lib.osteo_ddpm_step_is_fused(model._ctx))
+        if fused:      # fused_step.cuh: output_proj + reverse update + the next step's input_proj are one kernel
+            names = [f"linear_gn_silu_{i}" for i in range(10)] + ["output_proj+reverse_update+next_input_proj"]
+        else:
+            names = ["input_proj+emb_add"] + [f"linear_gn_silu_{i}" for i in range(10)] + ["output_proj+reverse_update"]
         by_kernel = {}
         for i, ms in enumerate(per):
-            by_kernel.setdefault(names[i % 12], []).append(float(ms))
+            by_kernel.setdefault(names[i % len(names)], []).append(float(ms))
         step_ms = float(per.sum())
         kernels = {k: {"ms_per_step": sum(v), "share": sum(v) / step_ms} for k, v in by_kernel.items()}
         dom = max(kernels, key=lambda k: kernels[k]["ms_per_step"])
         launches_of_dom = len(by_kernel[dom])
         dom_ms = kernels[dom]["ms_per_step"] / launches_of_dom
         rows_per_launch = rows / launches_of_dom
-        if dom == "output_proj+reverse_update":
+        if dom.startswith("output_proj+reverse_update"):
             algo = ALGO_BYTES_PER_PATIENT_STEP * rows_per_launch
             ach = algo / (dom_ms / 1e3) / 1e9
             roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
@@ -311,7 +314,7 @@ def run_ours(args):
             roofline = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                         "algorithmic_bytes_per_launch": algo, "avg_launch_ms": dom_ms, "peak_source": peak_src}
         else:
-            flops = ALGO_FLOPS_PER_PATIENT_STEP * rows_per_launch / 12
+            flops = ALGO_FLOPS_PER_PATIENT_STEP * rows_per_launch / 12      # coarse: one of 12 equal shares
             ach = flops / (dom_ms / 1e3) / 1e12
             roofline = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
                         "avg_launch_ms": dom_ms, "peak_source": peak_src}

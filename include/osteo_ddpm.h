@@ -62,6 +62,13 @@ long long osteo_ddpm_workspace_bytes(const osteo_ddpm_ctx* ctx);
 /* Rows per internal pass (activations of one pass stay L2-resident). 0 = all rows at once. */
 int osteo_ddpm_set_chunk_rows(osteo_ddpm_ctx* ctx, int chunk_rows);
 int osteo_ddpm_set_precision(osteo_ddpm_ctx* ctx, int precision);
+/* bf16 mode with hidden_dims[0] <= 256 runs the FUSED reverse step by default: output_proj, the reverse update
+ * (models/diffusion.py:400-423) and the NEXT step's input_proj + embedding add (models/diffusion.py:229-232) in one
+ * kernel, so the fp32 state is read once and written once per step and no bf16 copy of it goes through HBM.
+ * enable = 0 selects the unfused kernels (always used in FP32X3 mode). Takes effect at the next load_state /
+ * init_noise. osteo_ddpm_step_is_fused reports which path the current settings select. */
+int osteo_ddpm_set_fused(osteo_ddpm_ctx* ctx, int enable);
+int osteo_ddpm_step_is_fused(const osteo_ddpm_ctx* ctx);
 
 /* ---- parameters: replaces nn.Module.load_state_dict / optimizer updates.
  * `weights_dev[i]` are fp32 device tensors in state_dict order (SURVEY.md §8a layer table):

@@ -37,6 +37,8 @@ SIGNATURES = {
     "osteo_ddpm_workspace_bytes": (_ll, [_vp]),
     "osteo_ddpm_set_chunk_rows": (_i, [_vp, _i]),
     "osteo_ddpm_set_precision": (_i, [_vp, _i]),
+    "osteo_ddpm_set_fused": (_i, [_vp, _i]),
+    "osteo_ddpm_step_is_fused": (_i, [_vp]),
     "osteo_ddpm_set_weights": (_i, [_vp, C.POINTER(_vp), _i, _vp]),
     "osteo_ddpm_set_schedule": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "osteo_ddpm_set_time_embedding": (_i, [_vp, _vp]),

@@ -138,6 +138,7 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
     }
     c->launches += 3;
     OSTEO_TRY(launch_input_proj(c, 0, n, t_idx_dev, s, &w.xt_tmap));
+    c->h0_primed = false;      // acts[0] now belongs to this training batch, not to a sampling state
     for (int i = 0; i < H; ++i) {
         HalfOpts o;
         o.train = train != 0;

@@ -58,15 +58,17 @@ __global__ void pack_bf16_hilo_transposed_kernel(const float* __restrict__ src, 
 // Blocked state layouts (each TMA box is one contiguous 16 KB chunk, so a tile load walks DRAM pages sequentially instead of
 // touching 128 pages 20 KB apart):
 //   fp32 state  [m_tile][x_nbox ][128 rows][32 cols]     bf16 shadow [m_tile][xb_nbox][128 rows][64 cols]
-__host__ __device__ __forceinline__ size_t x_blocked_off(long long r, int c, int x_nbox) {
-    return ((static_cast<size_t>(r >> 7) * x_nbox + (c >> 5)) * 128 + (r & 127)) * 32 + (c & 31);
+// The fused bf16 step (fused_step.cuh) uses 8-column boxes instead ("c8": [m_tile][DP / 8][128 rows][8 cols], x_shift = 3), so that a
+// warp-wide 256-bit access of 32 consecutive rows is 1 KB contiguous; the TMA-staged path keeps 32-column boxes (x_shift = 5).
+__host__ __device__ __forceinline__ size_t x_blocked_off(long long r, int c, int x_nbox, int x_shift) {
+    return (((static_cast<size_t>(r >> 7) * x_nbox + (c >> x_shift)) * 128 + (r & 127)) << x_shift) + (c & ((1 << x_shift) - 1));
 }
 __host__ __device__ __forceinline__ size_t xb_blocked_off(long long r, int c, int xb_nbox) {
     return ((static_cast<size_t>(r >> 7) * xb_nbox + (c >> 6)) * 128 + (r & 127)) * 64 + (c & 63);
 }
 
 // Caller x [n, d] -> padded fp32 state [n, x_ld] + bf16 shadow [n, xb_ld] (hi | lo). One thread per 4 columns.
-__global__ void load_state_kernel(const float* __restrict__ src, long long n, int d, int dp, float* __restrict__ x, int x_nbox,
+__global__ void load_state_kernel(const float* __restrict__ src, long long n, int d, int dp, float* __restrict__ x, int x_nbox, int x_shift,
                                   __nv_bfloat16* __restrict__ xb, int xb_nbox, int lo_boxes) {
     const int q = dp / 4;
     const long long total = n * q;
@@ -76,7 +78,7 @@ __global__ void load_state_kernel(const float* __restrict__ src, long long n, in
         float v[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) v[j] = (c + j < d) ? src[r * d + c + j] : 0.0f;
-        if (x) *reinterpret_cast<float4*>(x + x_blocked_off(r, c, x_nbox)) = make_float4(v[0], v[1], v[2], v[3]);
+        if (x) *reinterpret_cast<float4*>(x + x_blocked_off(r, c, x_nbox, x_shift)) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<uint2*>(xb + xb_blocked_off(r, c, xb_nbox)) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
         if (lo_boxes > 0)
             *reinterpret_cast<uint2*>(xb + xb_blocked_off(r, c + lo_boxes * 64, xb_nbox)) =
@@ -84,17 +86,30 @@ __global__ void load_state_kernel(const float* __restrict__ src, long long n, in
     }
 }
 
-__global__ void store_state_kernel(const float* __restrict__ x, int x_nbox, float* __restrict__ dst, long long n, int d) {
+// bf16 shadow rebuilt from the fp32 state (hi half only): needed when the fused step, which does not maintain the shadow, is
+// followed by a step that has to recompute input_proj from scratch (a different timestep, new conditions or new weights).
+__global__ void reshadow_kernel(const float* __restrict__ x, int x_nbox, int x_shift, int dp, __nv_bfloat16* __restrict__ xb, int xb_nbox, long long n) {
+    const int q = dp / 4;
+    const long long total = n * q;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / q;
+        const int c = static_cast<int>(i % q) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + x_blocked_off(r, c, x_nbox, x_shift));
+        *reinterpret_cast<uint2*>(xb + xb_blocked_off(r, c, xb_nbox)) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+    }
+}
+
+__global__ void store_state_kernel(const float* __restrict__ x, int x_nbox, int x_shift, float* __restrict__ dst, long long n, int d) {
     const long long total = n * d;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long r = i / d;
         const int c = static_cast<int>(i % d);
-        dst[i] = x[x_blocked_off(r, c, x_nbox)];
+        dst[i] = x[x_blocked_off(r, c, x_nbox, x_shift)];
     }
 }
 
 // x_T ~ N(0, I): models/diffusion.py:443. One Philox call per 4 columns.
-__global__ void init_noise_kernel(float* __restrict__ x, int x_nbox, int dp, __nv_bfloat16* __restrict__ xb, int xb_nbox, int lo_boxes, long long n, int d,
+__global__ void init_noise_kernel(float* __restrict__ x, int x_nbox, int x_shift, int dp, __nv_bfloat16* __restrict__ xb, int xb_nbox, int lo_boxes, long long n, int d,
                                   unsigned long long seed, long long row_base, uint32_t stream_id, uint32_t step) {
     const int q = dp / 4;
     const long long total = n * q;
@@ -109,7 +124,7 @@ __global__ void init_noise_kernel(float* __restrict__ x, int x_nbox, int dp, __n
             if (c + 2 >= d) z.z = 0.f;
             if (c + 3 >= d) z.w = 0.f;
         }
-        *reinterpret_cast<float4*>(x + x_blocked_off(r, c, x_nbox)) = z;
+        *reinterpret_cast<float4*>(x + x_blocked_off(r, c, x_nbox, x_shift)) = z;
         *reinterpret_cast<uint2*>(xb + xb_blocked_off(r, c, xb_nbox)) = make_uint2(pack2(z.x, z.y), pack2(z.z, z.w));
         if (lo_boxes > 0)
             *reinterpret_cast<uint2*>(xb + xb_blocked_off(r, c + lo_boxes * 64, xb_nbox)) =

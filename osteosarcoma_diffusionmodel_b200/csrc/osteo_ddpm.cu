@@ -8,6 +8,7 @@
 #include "../../include/osteo_ddpm.h"
 #include "common.cuh"
 #include "elem_kernels.cuh"
+#include "fused_step.cuh"
 #include "gemm_host.cuh"
 #include "train_kernels.cuh"
 #include "validators.cuh"
@@ -182,6 +183,14 @@ struct osteo_ddpm_ctx {
     DevBuf xb;                           // bf16 shadow, blocked [cap/128][xb_nbox][128][64] (hi boxes then lo boxes)
     CUtensorMap xb_tmap;
     int x_nbox = 0, xb_nbox = 0;
+    // fused bf16 step (fused_step.cuh): output_proj + reverse update + the NEXT step's input_proj in one kernel
+    CUtensorMap wout_tmap64, win_tmap;   // W_out as [64 x 64] boxes, W_in as [h0 x 64] boxes
+    int fused_enable = 1;
+    bool x_c8 = false;                   // layout the state was loaded in: c8 (fused path) or 32-column boxes (TMA-staged path)
+    bool shadow_valid = false;           // xb == bf16(x)? (the fused step does not maintain the shadow)
+    bool h0_primed = false;              // acts[0] holds input_proj(x) + embeddings for timestep h0_t over rows [0, h0_n)
+    int h0_t = -1;
+    long long h0_n = 0;
     std::vector<std::unique_ptr<ActBuf>> acts;   // [0] = h0, then one per half block
     DevBuf cproj;                        // fp32 [cap, h0]
     DevBuf step_dev, status_dev;
@@ -193,11 +202,14 @@ struct osteo_ddpm_ctx {
     long long graph_n = -1;
     unsigned long long graph_seed = 0;
     long long graph_row_base = 0;
-    int graph_precision = -1, graph_chunk = -1;
+    int graph_precision = -1, graph_chunk = -1, graph_fused = -1;
     long long graph_launches_per_step = 0;
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every GEMM launch
 
     bool x3() const { return precision == OSTEO_PREC_FP32X3; }
+    bool fused_ok() const { return fused_enable && precision == OSTEO_PREC_BF16 && hidden[0] <= 256; }
+    int xs_nbox() const { return x_c8 ? DP / 8 : x_nbox; }
+    int xs_shift() const { return x_c8 ? 3 : 5; }
     int h0() const { return hidden[0]; }
     int lo(int width) const { return x3() ? width : 0; }
     int lo_boxes() const { return x3() ? DP / BK : 0; }
@@ -375,6 +387,53 @@ static int launch_output_eps(osteo_ddpm_ctx* c, long long row0, long long row1, 
     return after_launch(c, launch_gemm(EPI_LINEAR, 64, p, c->sms, s), s);
 }
 
+// Fused tail of a bf16 reverse step: output_proj + reverse update + next step's input_proj (fused_step.cuh).
+static int launch_fused(osteo_ddpm_ctx* c, long long row0, long long row1, const float* noise, float* eps_out, unsigned long long seed, long long row_base,
+                        cudaStream_t s) {
+    static bool configured = false;
+    if (!configured) {
+        OSTEO_CUDA(cudaFuncSetAttribute(ddpm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+        configured = true;
+    }
+    FusedParams p;
+    std::memset(&p, 0, sizeof p);
+    p.tma_a = c->acts.back()->tmap;
+    p.tma_wout = c->wout_tmap64;
+    p.tma_win = c->win_tmap;
+    p.M = static_cast<int>(row1);
+    p.N = c->D;
+    p.m_tile0 = static_cast<int>(row0 / BM);
+    p.m_tiles = static_cast<int>((row1 - row0 + BM - 1) / BM);
+    p.n_tiles = c->DP / FT;
+    p.nkb = c->h0() / BK;
+    p.h0 = c->h0();
+    p.status = c->status_dev.as<int>();
+    p.step = c->step_dev.as<int>();
+    p.coef_x = c->coef_x.as<float>();
+    p.coef_eps = c->coef_eps.as<float>();
+    p.coef_sigma = c->coef_sigma.as<float>();
+    p.x = c->x.as<float>();
+    p.x_c8 = c->DP / 8;
+    p.bias_out = c->out_proj.bias.as<float>();
+    p.noise = noise;
+    p.noise_ld = c->D;
+    p.eps_out = eps_out;
+    p.eps_ld = c->D;
+    p.seed = seed;
+    p.row_base = row_base;
+    p.bias_in = c->in_proj.bias.as<float>();
+    p.time_table = c->time_table.as<float>();
+    p.cproj = c->cproj.as<float>();
+    p.h0_out = c->acts[0]->ptr();
+    p.h0_ld = 2 * c->h0();
+    if (const char* e = getenv("OSTEO_DDPM_DBG")) p.dbg = atoi(e);
+    if (p.m_tiles <= 0) return 0;
+    const int grid = p.m_tiles < c->sms ? p.m_tiles : c->sms;
+    ddpm_fused_kernel<<<grid, F_THREADS, F_SMEM_BYTES, s>>>(p);
+    OSTEO_CUDA(cudaGetLastError());
+    return after_launch(c, 0, s);
+}
+
 static long long chunk_of(const osteo_ddpm_ctx* c, long long n) {
     long long ch = c->chunk_rows > 0 ? c->chunk_rows : n;
     ch = round_up(ch, BM);
@@ -382,16 +441,47 @@ static long long chunk_of(const osteo_ddpm_ctx* c, long long n) {
 }
 
 // Enqueue one full reverse step over rows [0, n); the timestep is read from the device word.
+// Fused path: acts[0] must already hold this step's h0 (ensure_primed); the step leaves the NEXT step's h0 there.
 static int enqueue_reverse_step(osteo_ddpm_ctx* c, long long n, const float* noise, float* eps_out, unsigned long long seed, long long row_base, cudaStream_t s) {
+    if (c->x_c8 != c->fused_ok())
+        return fail("the state was loaded under a different precision / fused setting: call load_state or init_noise again");
     const long long ch = chunk_of(c, n);
     HalfOpts o;
     for (long long r0 = 0; r0 < n; r0 += ch) {
         const long long r1 = r0 + ch < n ? r0 + ch : n;
-        OSTEO_TRY(launch_input_proj(c, r0, r1, nullptr, s));
+        if (!c->x_c8) OSTEO_TRY(launch_input_proj(c, r0, r1, nullptr, s));
         for (size_t i = 0; i < c->halves.size(); ++i) OSTEO_TRY(launch_half(c, static_cast<int>(i), r0, r1, o, s));
-        OSTEO_TRY(launch_output_ddpm(c, r0, r1, noise, eps_out, seed, row_base, s));
+        if (c->x_c8) OSTEO_TRY(launch_fused(c, r0, r1, noise, eps_out, seed, row_base, s));
+        else OSTEO_TRY(launch_output_ddpm(c, r0, r1, noise, eps_out, seed, row_base, s));
     }
     return 0;
+}
+
+// Fused path only: make acts[0] = input_proj(x) + b + time_proj[t] + cond_proj for rows [0, n) at the timestep in the device
+// step word (== t). The first step after load_state / init_noise contracts the bf16 shadow those kernels wrote; if fused steps
+// have run since (the shadow is stale) it is rebuilt from the fp32 state first.
+static int ensure_primed(osteo_ddpm_ctx* c, long long n, int t, cudaStream_t s) {
+    if (!c->x_c8) return 0;
+    if (c->h0_primed && c->h0_t == t && c->h0_n == n) return 0;
+    if (!c->shadow_valid) {
+        const long long items = n * (c->DP / 4);
+        reshadow_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->xs_nbox(), c->xs_shift(), c->DP, c->xb_ptr(), c->xb_nbox, n);
+        OSTEO_CUDA(cudaGetLastError());
+        ++c->launches;
+        c->shadow_valid = true;
+    }
+    const long long ch = chunk_of(c, n);
+    for (long long r0 = 0; r0 < n; r0 += ch) OSTEO_TRY(launch_input_proj(c, r0, r0 + ch < n ? r0 + ch : n, nullptr, s));
+    c->h0_primed = true;
+    c->h0_t = t;
+    c->h0_n = n;
+    return 0;
+}
+// Bookkeeping after `steps` fused steps that started at timestep t.
+static void after_steps(osteo_ddpm_ctx* c, int t, int steps) {
+    if (!c->x_c8) return;
+    c->shadow_valid = false;
+    c->h0_t = t - steps;
 }
 
 static int require_ready(const osteo_ddpm_ctx* c, long long n) {
@@ -479,6 +569,10 @@ int osteo_ddpm_create(osteo_ddpm_ctx** out, int device, int data_dim, int cond_d
 
     OSTEO_TRY(c->in_proj.init(h0, data_dim));
     OSTEO_TRY(c->out_proj.init(data_dim, h0));
+    if (h0 <= 256) {
+        OSTEO_TRY(make_tmap_bf16(&c->wout_tmap64, c->out_proj.w.p, c->out_proj.np, 2 * c->out_proj.kp, 2 * c->out_proj.kp, FT));
+        OSTEO_TRY(make_tmap_bf16(&c->win_tmap, c->in_proj.w.p, c->in_proj.np, 2 * c->in_proj.kp, 2 * c->in_proj.kp, h0));
+    }
 
     // Block structure of DiffusionUNet.__init__ (models/diffusion.py:171-193). Activation 0 = h0.
     int act_count = 1;
@@ -557,6 +651,13 @@ int osteo_ddpm_set_precision(osteo_ddpm_ctx* c, int precision) {
     return 0;
 }
 
+int osteo_ddpm_set_fused(osteo_ddpm_ctx* c, int enable) {
+    OSTEO_TRY(check_ctx(c));
+    c->fused_enable = enable ? 1 : 0;
+    return 0;
+}
+int osteo_ddpm_step_is_fused(const osteo_ddpm_ctx* c) { return c && c->fused_ok() ? 1 : 0; }
+
 int osteo_ddpm_reserve(osteo_ddpm_ctx* c, long long rows) {
     OSTEO_TRY(check_ctx(c));
     if (rows <= c->cap) return 0;
@@ -594,6 +695,8 @@ int osteo_ddpm_reserve(osteo_ddpm_ctx* c, long long rows) {
     }
     c->train.release();
     c->cap = cap;
+    c->h0_primed = false;
+    c->shadow_valid = false;
     return 0;
 }
 
@@ -633,6 +736,7 @@ int osteo_ddpm_set_weights(osteo_ddpm_ctx* c, const float* const* w, int n_tenso
     OSTEO_TRY(c->out_proj.upload(w[idx], w[idx + 1], c->sms, s));
     c->launches += 2 + static_cast<long long>(c->halves.size());
     c->have_weights = true;
+    c->h0_primed = false;
     return rebuild_time_table(c, s);
 }
 
@@ -667,9 +771,13 @@ int osteo_ddpm_load_state(osteo_ddpm_ctx* c, const float* x_dev, long long n, vo
     if (n <= 0 || n > c->cap) return fail("load_state: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long items = n * (c->DP / 4);
-    load_state_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(x_dev, n, c->D, c->DP, c->x.as<float>(), c->x_nbox, c->xb_ptr(), c->xb_nbox, c->lo_boxes());
+    c->x_c8 = c->fused_ok();
+    load_state_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(x_dev, n, c->D, c->DP, c->x.as<float>(), c->xs_nbox(), c->xs_shift(), c->xb_ptr(), c->xb_nbox,
+                                                                  c->lo_boxes());
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
+    c->shadow_valid = true;
+    c->h0_primed = false;
     return 0;
 }
 
@@ -677,7 +785,7 @@ int osteo_ddpm_store_state(osteo_ddpm_ctx* c, float* out_dev, long long n, void*
     OSTEO_TRY(check_ctx(c));
     if (n <= 0 || n > c->cap) return fail("store_state: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    store_state_kernel<<<grid_for(n * c->D, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->x_nbox, out_dev, n, c->D);
+    store_state_kernel<<<grid_for(n * c->D, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->xs_nbox(), c->xs_shift(), out_dev, n, c->D);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -688,10 +796,13 @@ int osteo_ddpm_init_noise(osteo_ddpm_ctx* c, long long n, uint64_t seed, long lo
     if (n <= 0 || n > c->cap) return fail("init_noise: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long items = n * (c->DP / 4);
-    init_noise_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->x_nbox, c->DP, c->xb_ptr(), c->xb_nbox, c->lo_boxes(), n, c->D, seed, row_base,
-                                                                  STREAM_XT, 0u);
+    c->x_c8 = c->fused_ok();
+    init_noise_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->xs_nbox(), c->xs_shift(), c->DP, c->xb_ptr(), c->xb_nbox, c->lo_boxes(), n, c->D,
+                                                                  seed, row_base, STREAM_XT, 0u);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
+    c->shadow_valid = true;
+    c->h0_primed = false;
     return 0;
 }
 
@@ -706,6 +817,7 @@ int osteo_ddpm_set_conditions(osteo_ddpm_ctx* c, const float* cond_dev, long lon
                                                                            c->cproj.as<float>(), nullptr, nullptr);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
+    c->h0_primed = false;
     return 0;
 }
 
@@ -717,7 +829,10 @@ int osteo_ddpm_reverse_step(osteo_ddpm_ctx* c, long long n, int t, const float* 
     set_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), t);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
-    return enqueue_reverse_step(c, n, noise_dev, eps_out_dev, seed, row_base, s);
+    OSTEO_TRY(ensure_primed(c, n, t, s));
+    OSTEO_TRY(enqueue_reverse_step(c, n, noise_dev, eps_out_dev, seed, row_base, s));
+    after_steps(c, t, 1);
+    return 0;
 }
 
 int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_end, const float* noise_dev, uint64_t seed, long long row_base, int use_graph,
@@ -730,6 +845,8 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
     set_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), t_start);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
+    if (c->x_c8 != c->fused_ok()) return fail("the state was loaded under a different precision / fused setting: call load_state or init_noise again");
+    OSTEO_TRY(ensure_primed(c, n, t_start, s));
     if (noise_dev || !use_graph) {
         for (int i = 0; i < steps; ++i) {
             const float* nz = noise_dev ? noise_dev + static_cast<size_t>(i) * n * c->D : nullptr;
@@ -738,11 +855,12 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
             OSTEO_CUDA(cudaGetLastError());
             ++c->launches;
         }
+        after_steps(c, t_start, steps);
         return 0;
     }
     // One step captured once, replayed `steps` times; the device-resident step word is the only thing that changes.
     const bool reuse = c->graph_exec && c->graph_n == n && c->graph_seed == seed && c->graph_row_base == row_base &&
-                       c->graph_precision == c->precision && c->graph_chunk == c->chunk_rows;
+                       c->graph_precision == c->precision && c->graph_chunk == c->chunk_rows && c->graph_fused == (c->x_c8 ? 1 : 0);
     const long long before = c->launches;
     if (!reuse) {
         if (c->graph_exec) {
@@ -773,6 +891,7 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
         c->graph_row_base = row_base;
         c->graph_precision = c->precision;
         c->graph_chunk = c->chunk_rows;
+        c->graph_fused = c->x_c8 ? 1 : 0;
     }
     if (!reuse) {
         c->graph_launches_per_step = c->launches - before;
@@ -780,6 +899,7 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
     }
     for (int i = 0; i < steps; ++i) OSTEO_CUDA(cudaGraphLaunch(c->graph_exec, s));
     c->launches += c->graph_launches_per_step * steps;
+    after_steps(c, t_start, steps);
     return 0;
 }
 
@@ -788,9 +908,11 @@ int osteo_ddpm_denoise(osteo_ddpm_ctx* c, const float* xt_dev, const int* t_idx_
     OSTEO_TRY(require_ready(c, n));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long items = n * (c->DP / 4);
-    load_state_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(xt_dev, n, c->D, c->DP, nullptr, c->x_nbox, c->xb_ptr(), c->xb_nbox, c->lo_boxes());
+    load_state_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(xt_dev, n, c->D, c->DP, nullptr, c->x_nbox, 5, c->xb_ptr(), c->xb_nbox, c->lo_boxes());
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
+    c->shadow_valid = false;      // the shadow now holds the caller's x_t, and acts[0] its projection
+    c->h0_primed = false;
     const long long ch = chunk_of(c, n);
     HalfOpts o;
     for (long long r0 = 0; r0 < n; r0 += ch) {
@@ -841,6 +963,7 @@ int osteo_ddpm_profile_step(osteo_ddpm_ctx* c, long long n, int t, uint64_t seed
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     set_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), t);
     OSTEO_CUDA(cudaGetLastError());
+    OSTEO_TRY(ensure_primed(c, n, t, s));
     std::vector<cudaEvent_t> ev;
     cudaEvent_t e0;
     OSTEO_CUDA(cudaEventCreate(&e0));
@@ -849,6 +972,7 @@ int osteo_ddpm_profile_step(osteo_ddpm_ctx* c, long long n, int t, uint64_t seed
     c->prof = &ev;
     const int rc = enqueue_reverse_step(c, n, nullptr, nullptr, seed, row_base, s);
     c->prof = nullptr;
+    if (rc == 0) after_steps(c, t, 1);
     int count = -1;
     if (rc == 0 && cudaStreamSynchronize(s) == cudaSuccess) {
         count = static_cast<int>(ev.size()) - 1;

@@ -141,6 +141,7 @@ class BiologyAwareDiffusionModel(nn.Module):
             raise ValueError(f"unknown precision {self._precision!r} (bf16 | fp32x3)")
         self._chunk_rows = int(os.environ.get("OSTEO_DDPM_CHUNK_ROWS", b200.get("chunk_rows", 131072)))
         self._use_graph = bool(int(os.environ.get("OSTEO_DDPM_GRAPH", b200.get("use_graph", 1))))
+        self._fused = bool(int(os.environ.get("OSTEO_DDPM_FUSED", b200.get("fused", 1))))
         self._seed = int(b200.get("seed", 0))
         self._draws = 0                 # counter mixed into the seed of un-seeded calls
         self._ctx = None                # C context handle
@@ -194,6 +195,14 @@ class BiologyAwareDiffusionModel(nn.Module):
             self._weights_sig = None
         return self
 
+    def set_fused(self, enable: bool) -> "BiologyAwareDiffusionModel":
+        """bf16 sampling runs the fused step kernel (output_proj + reverse update + next input_proj) by default;
+        set_fused(False) selects the unfused kernels (always used by 'fp32x3')."""
+        self._fused = bool(enable)
+        if self._ctx is not None:
+            _lib.check(_lib.load().osteo_ddpm_set_fused(self._ctx, int(self._fused)))
+        return self
+
     def set_chunk_rows(self, rows: int) -> None:
         self._chunk_rows = int(rows)
         if self._ctx is not None:
@@ -239,6 +248,7 @@ class BiologyAwareDiffusionModel(nn.Module):
             self._weights_sig = self._schedule_sig = None
             self._train_enabled = False
             _lib.check(lib.osteo_ddpm_set_chunk_rows(self._ctx, self._chunk_rows))
+            _lib.check(lib.osteo_ddpm_set_fused(self._ctx, int(self._fused)))
             emb = self.unet.time_embed.table(self.num_steps).numpy()
             _lib.check(lib.osteo_ddpm_set_time_embedding(self._ctx, emb.ctypes.data))
         if rows > lib.osteo_ddpm_capacity(self._ctx):

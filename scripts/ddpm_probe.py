@@ -1,5 +1,6 @@
-"""Diagnostic: per-kernel times of one reverse step at t=500 (Philox noise) vs t=0 (sigma = 0: no RNG at all)."""
-import sys, ctypes as C
+"""Diagnostic: per-kernel times of one reverse step at t=500 under the OSTEO_DDPM_DBG switches (comma-separated list in PROBE_DBG).
+Fused step (fused_step.cuh) bits: 1 = no L2 prefetch of the state, 4 = no state store, 8 = no noise (sigma = 0), 16 = no state load."""
+import os, sys, ctypes as C
 sys.path.insert(0, ".")
 import torch
 from osteosarcoma_diffusionmodel_b200 import synthetic as synth
@@ -13,8 +14,9 @@ model = model.to("cuda").eval()
 cond = synth.scenario_conditions(rows, 3).cuda()
 model.sample(cond, rows, seed=1, t_stop=998)
 lib = _lib.load()
+fused = bool(lib.osteo_ddpm_step_is_fused(model._ctx))
+per_chunk = 11 if fused else 12
 buf = (C.c_float * 4096)()
-import os
 for t, dbg in [(500, int(d)) for d in os.environ.get('PROBE_DBG', '0').split(',')]:
     os.environ['OSTEO_DDPM_DBG'] = str(dbg)
     acc = None
@@ -24,6 +26,7 @@ for t, dbg in [(500, int(d)) for d in os.environ.get('PROBE_DBG', '0').split(','
         if rep:
             acc = v if acc is None else [a + b for a, b in zip(acc, v)]
     acc = [a / 3 for a in acc]
-    k = len(acc) // 12 if len(acc) >= 12 else 1
-    ddpm = sum(acc[11::12]); inp = sum(acc[0::12]); hid = sum(acc) - ddpm - inp
-    print(f"dbg={dbg:2d} t={t}: step {sum(acc):.3f} ms  input_proj {inp:.3f}  hidden {hid:.3f}  output_proj+update {ddpm:.3f}", flush=True)
+    ddpm = sum(acc[per_chunk - 1::per_chunk])
+    inp = 0.0 if fused else sum(acc[0::per_chunk])
+    hid = sum(acc) - ddpm - inp
+    print(f"dbg={dbg:2d} t={t} fused={int(fused)}: step {sum(acc):.3f} ms  input_proj {inp:.3f}  hidden {hid:.3f}  output_proj+update {ddpm:.3f}", flush=True)
