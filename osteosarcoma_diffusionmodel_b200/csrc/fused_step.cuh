@@ -10,6 +10,7 @@
 // against W_in[:, 64 columns] into a per-row-block TMEM accumulator.
 //
 // Work unit = one 128-row block, all DP / 64 column tiles. Roles (640 threads, 1 CTA / SM):
+//   (logical warps; physically the four role warps are 16..19 and the epilogue warps 0..15, see the kernel)
 //   warp 0      TMA producer: resident A (h_final, 128 x h0 bf16) once per unit, W_out tile [64 x h0] per column tile
 //   warp 1      MMA issuer: eps(j) = A . W_out[j]^T  (M128 N64),  acc_in += xbf(j-2) . W_in[j-2]^T  (M128 N=h0)
 //   warp 2      TMEM allocator (512 columns: acc_in 256 | 4 eps stages of 64)
@@ -36,7 +37,9 @@ constexpr int F_STAGES = 2;
 constexpr int F_EPS_ACC = 4;
 constexpr int F_LAG = 2;                                // the next-step contraction trails the eps GEMM by two tiles
 constexpr int F_TMEM_EPS0 = 256;                        // first TMEM column of the eps stages
-constexpr int F_SMEM_BYTES = F_ARES_BYTES + F_STAGES * (F_WOUT_STAGE + F_WIN_STAGE + F_XBF_STAGE) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int F_BIAS_SLOTS = 6;                         // output_proj bias of a tile (64 floats) rides along with its W_out tile
+constexpr int F_BIAS_BYTES = FT * 4;
+constexpr int F_SMEM_BYTES = F_ARES_BYTES + F_STAGES * (F_WOUT_STAGE + F_WIN_STAGE + F_XBF_STAGE) + 1024 /*align*/ + 256 /*barriers*/ + F_BIAS_SLOTS * F_BIAS_BYTES;
 
 struct FusedParams {
     CUtensorMap tma_a;        // h_final bf16 [rows, 2*h0], box 128 x 64
@@ -75,6 +78,12 @@ __device__ __forceinline__ void ld_global_v8(const void* ptr, uint32_t (&w)[8]) 
                  : "l"(ptr)
                  : "memory");
 }
+// 1-D bulk copy global -> shared (size a multiple of 16 B), completion counted on `bar` like a tensor load.
+__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
 __device__ __forceinline__ void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
@@ -93,12 +102,15 @@ __device__ __forceinline__ void philox_scaled_normal16(uint64_t seed, uint64_t r
         const uint32_t w[4] = {c[i].x, c[i].y, c[i].z, c[i].w};
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
+            // u1 = 2 - f in (0, 1] is never subnormal (>= 2^-23): the .ftz forms drop the denormal pre-scaling __log2f emits.
+            // The angle is 2 pi f with f in [1, 2): one full turn more than 2 pi (f - 1), same sine and cosine, one FMUL instead of an FFMA.
             const float u1 = 2.0f - unit_1_2(w[2 * h]);
-            const float th = fmaf(unit_1_2(w[2 * h + 1]), 6.283185307179586f, -6.283185307179586f);
-            float r;
-            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(k2 * __log2f(u1)));
-            float s, co;
-            __sincosf(th, &s, &co);
+            const float th = unit_1_2(w[2 * h + 1]) * 6.283185307179586f;
+            float l2, r, s, co;
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(k2 * l2));
+            asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
+            asm("cos.approx.ftz.f32 %0, %1;" : "=f"(co) : "f"(th));
             z[4 * i + 2 * h] = r * co;
             z[4 * i + 2 * h + 1] = r * s;
         }
@@ -126,8 +138,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
     uint64_t* accin_full = bars + 22;
     uint64_t* accin_empty = bars + 23;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    uint8_t* s_bias = reinterpret_cast<uint8_t*>(bars) + 256;      // F_BIAS_SLOTS x 256 B
 
-    const int warp = threadIdx.x >> 5;
+    // Role warps take the HIGHEST warp ids: the SMSP arbiter favours high warp ids, and a starved MMA issuer / TMA producer stalls
+    // all sixteen epilogue warps. Epilogue warps are 0..15 (TMEM lane quadrant = warp % 4).
+    const int warp_phys = threadIdx.x >> 5;
+    const int warp = warp_phys < F_EPI_WARPS ? warp_phys + 4 : warp_phys - F_EPI_WARPS;      // logical: 0..3 roles, 4..19 epilogue
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -164,19 +180,24 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
     if (warp == 0) {
         // ------------------------------------------------ producer: resident A + W_out tiles
         if (lane == 0) {
-            int itw = 0, k = 0;
+            int itw = 0, k = 0, bslot = 0;
             bool ok = true;
             for (int u = blockIdx.x; ok && u < p.m_tiles; u += gridDim.x, ++k) {
                 const int m_blk = p.m_tile0 + u;
-                if (!mbar_wait(a_empty, (static_cast<uint32_t>(k) & 1u) ^ 1u)) { ok = false; break; }
+                if (!mbar_wait_relaxed(a_empty, (static_cast<uint32_t>(k) & 1u) ^ 1u)) { ok = false; break; }
                 mbar_arrive_expect_tx(a_full, p.nkb * A_TILE_BYTES);
                 for (int kb = 0; kb < p.nkb; ++kb) tma_load_2d(&p.tma_a, s_a + kb * A_TILE_BYTES, a_full, kb * BK, m_blk * BM);
                 for (int j = 0; j < nt; ++j, ++itw) {
                     const int s = itw & 1;
-                    if (!mbar_wait(&wout_empty[s], ((static_cast<uint32_t>(itw) >> 1) & 1u) ^ 1u)) { ok = false; break; }
-                    mbar_arrive_expect_tx(&wout_full[s], p.nkb * F_WOUT_KB_BYTES);
+                    // stage s was last read by eps(itw - 2): its completion is that tile's tfull barrier (no separate "empty" commit)
+                    if (itw >= 2 && !mbar_wait_relaxed(&tfull[(itw - 2) & (F_EPS_ACC - 1)], (static_cast<uint32_t>(itw - 2) >> 2) & 1u)) { ok = false; break; }
+                    // the bias slot of tile itw - 6 is free: eps(itw - 2) has completed, so the epilogue of tile itw - 6 has arrived on
+                    // tempty, which it does only after reading its bias
+                    mbar_arrive_expect_tx(&wout_full[s], p.nkb * F_WOUT_KB_BYTES + F_BIAS_BYTES);
                     for (int kb = 0; kb < p.nkb; ++kb)
                         tma_load_2d(&p.tma_wout, s_wout + s * F_WOUT_STAGE + kb * F_WOUT_KB_BYTES, &wout_full[s], kb * BK, j * FT);
+                    bulk_load_1d(s_bias + bslot * F_BIAS_BYTES, p.bias_out + j * FT, F_BIAS_BYTES, &wout_full[s]);
+                    bslot = bslot + 1 == F_BIAS_SLOTS ? 0 : bslot + 1;
                 }
             }
             if (!ok) atomicExch(p.status, ERR_PRODUCER_TIMEOUT);
@@ -196,7 +217,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                 }
                 for (int j = 0; j < nt; ++j, ++iti) {
                     const int s = iti & 1;
-                    if (!mbar_wait(&win_empty[s], ((static_cast<uint32_t>(iti) >> 1) & 1u) ^ 1u)) { ok = false; break; }
+                    // stage s was last read by the next-step MMA of tile iti - 2, which also releases the bf16 tile buffer: one barrier
+                    if (!mbar_wait_relaxed(&xbf_empty[s], ((static_cast<uint32_t>(iti) >> 1) & 1u) ^ 1u)) { ok = false; break; }
                     if (j + 2 < nt && !(p.dbg & 1)) l2_prefetch_bulk(xblk + static_cast<size_t>(j + 2) * tile_floats, static_cast<uint32_t>(tile_floats * 4));
                     mbar_arrive_expect_tx(&win_full[s], p.h0 * BK * 2);
                     tma_load_2d(&p.tma_win, s_win + s * F_WIN_STAGE, &win_full[s], j * FT, 0);
@@ -206,69 +228,80 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc_eps = make_idesc_bf16(BM, FT, 0, 0);
-            const uint32_t idesc_in = make_idesc_bf16(BM, p.h0, 0, 0);
-            int it_eps = 0, it_in = 0, k = 0;
-            bool ok = true;
-            for (int u = blockIdx.x; ok && u < p.m_tiles; u += gridDim.x, ++k) {
-                if (!mbar_wait(a_full, static_cast<uint32_t>(k) & 1u)) { ok = false; break; }
-                tc_fence_after_sync();
-                for (int j = 0; j < nt + F_LAG && ok; ++j) {
-                    if (j < nt) {
-                        const int s = it_eps & 1, acc = it_eps & (F_EPS_ACC - 1);
-                        if (!mbar_wait(&wout_full[s], (static_cast<uint32_t>(it_eps) >> 1) & 1u)) { ok = false; break; }
-                        if (!mbar_wait(&tempty[acc], ((static_cast<uint32_t>(it_eps) >> 2) & 1u) ^ 1u)) { ok = false; break; }
-                        tc_fence_after_sync();
+        // The WHOLE warp runs this loop with warp-uniform control flow and only the tcgen05 instructions are predicated on one
+        // elected lane: inside an `if (lane == 0)` region the compiler wraps every UTCHMMA / UTCBAR in an ELECT + branch loop and
+        // rebuilds the descriptors through the vector registers, and the single issuing thread (~10 dependent instructions per MMA)
+        // cannot keep up with 32-cycle MMAs.
+        const uint32_t idesc_eps = make_idesc_bf16(BM, FT, 0, 0);
+        const uint32_t idesc_in = make_idesc_bf16(BM, p.h0, 0, 0);
+        const bool leader = elect_one();
+        const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(s_a));
+        const uint64_t wout_desc0 = make_kmajor_sw128_desc(smem_u32(s_wout));
+        const uint64_t win_desc0 = make_kmajor_sw128_desc(smem_u32(s_win));
+        const uint64_t xbf_desc0 = make_kmajor_sw128_desc(smem_u32(s_xbf));
+        int it_eps = 0, it_in = 0, k = 0;
+        bool ok = true;
+        for (int u = blockIdx.x; ok && u < p.m_tiles; u += gridDim.x, ++k) {
+            if (!mbar_wait_relaxed(a_full, static_cast<uint32_t>(k) & 1u)) { ok = false; break; }
+            tc_fence_after_sync();
+            for (int j = 0; j < nt + F_LAG && ok; ++j) {
+                if (j < nt) {
+                    const int s = it_eps & 1, acc = it_eps & (F_EPS_ACC - 1);
+                    if (!mbar_wait_relaxed(&wout_full[s], (static_cast<uint32_t>(it_eps) >> 1) & 1u)) { ok = false; break; }
+                    if (!mbar_wait_relaxed(&tempty[acc], ((static_cast<uint32_t>(it_eps) >> 2) & 1u) ^ 1u)) { ok = false; break; }
+                    tc_fence_after_sync();
+                    if (leader && !(p.dbg & 64)) {
                         const uint32_t d = tmem_base + F_TMEM_EPS0 + static_cast<uint32_t>(acc * FT);
-                        uint32_t accumulate = 0;
+                        const uint64_t bdesc_s = wout_desc0 + static_cast<uint64_t>((s * F_WOUT_STAGE) >> 4);
                         for (int kb = 0; kb < p.nkb; ++kb) {
-                            const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(s_a + kb * A_TILE_BYTES));
-                            const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(s_wout + s * F_WOUT_STAGE + kb * F_WOUT_KB_BYTES));
+                            const uint64_t adesc = adesc0 + static_cast<uint64_t>((kb * A_TILE_BYTES) >> 4);
+                            const uint64_t bdesc = bdesc_s + static_cast<uint64_t>((kb * F_WOUT_KB_BYTES) >> 4);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 16; ++kk) {
-                                umma_bf16(d, adesc + 2u * kk, bdesc + 2u * kk, idesc_eps, accumulate);
-                                accumulate = 1;
-                            }
+                            for (int kk = 0; kk < BK / 16; ++kk) umma_bf16(d, adesc + 2u * kk, bdesc + 2u * kk, idesc_eps, (kb | kk) != 0 ? 1u : 0u);
                         }
-                        umma_commit(&wout_empty[s]);
-                        umma_commit(&tfull[acc]);
-                        ++it_eps;
                     }
-                    if (j >= F_LAG) {
-                        const int jj = j - F_LAG;
-                        const int s = it_in & 1;
-                        if (jj == 0 && !mbar_wait(accin_empty, (static_cast<uint32_t>(k) & 1u) ^ 1u)) { ok = false; break; }
-                        if (!mbar_wait(&xbf_full[s], (static_cast<uint32_t>(it_in) >> 1) & 1u)) { ok = false; break; }
-                        if (!mbar_wait(&win_full[s], (static_cast<uint32_t>(it_in) >> 1) & 1u)) { ok = false; break; }
-                        tc_fence_after_sync();
-                        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(s_xbf + s * F_XBF_STAGE));
-                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(s_win + s * F_WIN_STAGE));
-#pragma unroll
-                        for (int kk = 0; kk < BK / 16; ++kk) umma_bf16(tmem_base, adesc + 2u * kk, bdesc + 2u * kk, idesc_in, (jj | kk) != 0 ? 1u : 0u);
-                        umma_commit(&xbf_empty[s]);
-                        umma_commit(&win_empty[s]);
-                        ++it_in;
-                    }
+                    if (leader) umma_commit(&tfull[acc]);
+                    __syncwarp();
+                    ++it_eps;
                 }
-                if (ok) {
-                    umma_commit(accin_full);
-                    umma_commit(a_empty);
+                if (j >= F_LAG) {
+                    const int jj = j - F_LAG;
+                    const int s = it_in & 1;
+                    if (jj == 0 && !mbar_wait_relaxed(accin_empty, (static_cast<uint32_t>(k) & 1u) ^ 1u)) { ok = false; break; }
+                    if (!mbar_wait_relaxed(&xbf_full[s], (static_cast<uint32_t>(it_in) >> 1) & 1u)) { ok = false; break; }
+                    if (!mbar_wait_relaxed(&win_full[s], (static_cast<uint32_t>(it_in) >> 1) & 1u)) { ok = false; break; }
+                    tc_fence_after_sync();
+                    if (leader) {
+                        const uint64_t adesc = xbf_desc0 + static_cast<uint64_t>((s * F_XBF_STAGE) >> 4);
+                        const uint64_t bdesc = win_desc0 + static_cast<uint64_t>((s * F_WIN_STAGE) >> 4);
+                        if (!(p.dbg & 128)) {
+#pragma unroll
+                            for (int kk = 0; kk < BK / 16; ++kk) umma_bf16(tmem_base, adesc + 2u * kk, bdesc + 2u * kk, idesc_in, (jj | kk) != 0 ? 1u : 0u);
+                        }
+                        umma_commit(&xbf_empty[s]);
+                    }
+                    __syncwarp();
+                    ++it_in;
                 }
             }
-            if (!ok) atomicExch(p.status, ERR_MMA_TIMEOUT);
+            if (ok && leader) {
+                umma_commit(accin_full);
+                umma_commit(a_empty);
+            }
+            __syncwarp();
         }
+        if (!ok && leader) atomicExch(p.status, ERR_MMA_TIMEOUT);
     } else if (warp >= 4) {
         // ------------------------------------------------ epilogue
-        const int q = warp & 3;                 // TMEM lane quadrant
-        const int part = (warp - 4) >> 2;       // 16-column quarter of the 64-column tile
+        const int q = warp_phys & 3;            // TMEM lane quadrant (hardware rule: physical warp id % 4)
+        const int part = warp_phys >> 2;        // 16-column quarter of the 64-column tile
         const int r_tile = q * 32 + lane;
         const int t = *p.step;
         const float cx = __ldg(p.coef_x + t), nce = -__ldg(p.coef_eps + t);
         const float sg = (p.dbg & 8) ? 0.0f : __ldg(p.coef_sigma + t);
         const float k2 = -1.3862943611198906f * sg * sg;
         const int t_next = t > 0 ? t - 1 : 0;
-        int it = 0, k = 0;
+        int it = 0, k = 0, bslot = 0;
         bool ok = true;
         for (int u = blockIdx.x; ok && u < p.m_tiles; u += gridDim.x, ++k) {
             const int m_blk = p.m_tile0 + u;
@@ -303,15 +336,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                 uint32_t vr[16];
                 tmem_ld_16_nowait(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(F_TMEM_EPS0 + acc * FT + part * 16), vr);
                 tmem_ld_wait();
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
+                // bias of this tile: staged in shared memory by the W_out producer (an L1 hit is not available: the whole L1 is carved out
+                // as shared memory, and an L2 round trip per tile on the critical path cost ~1000 cycles)
+                const float* sb = reinterpret_cast<const float*>(s_bias + bslot * F_BIAS_BYTES) + part * 16;
+                bslot = bslot + 1 == F_BIAS_SLOTS ? 0 : bslot + 1;
                 float xn[16];
                 if (nvalid >= 16) {
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias_out + c0);
+                    const float4* b4 = reinterpret_cast<const float4*>(sb);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 b = __ldg(b4 + i);
+                        const float4 b = b4[i];
                         const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -322,14 +356,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                     if (p.eps_out && live) {
                         float* eo = p.eps_out + static_cast<size_t>(row) * p.eps_ld + c0;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) eo[i] = __uint_as_float(vr[i]) + __ldg(p.bias_out + c0 + i);
+                        for (int i = 0; i < 16; ++i) eo[i] = __uint_as_float(vr[i]) + sb[i];
                     }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         float v = 0.0f;
                         if (i < nvalid) {
-                            const float ev = __uint_as_float(vr[i]) + __ldg(p.bias_out + c0 + i);
+                            const float ev = __uint_as_float(vr[i]) + sb[i];
                             if (p.eps_out && live) p.eps_out[static_cast<size_t>(row) * p.eps_ld + c0 + i] = ev;
                             v = fmaf(nce, ev, fmaf(cx, __uint_as_float(xw[i]), z[i]));
                         }
@@ -340,6 +374,10 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
 #pragma unroll
                     for (int i = 0; i < 16; ++i) xn[i] = 0.0f;
                 }
+                // accumulator and bias are in registers: hand the TMEM stage (and, transitively, the bias slot) back
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty[acc]);
                 uint32_t xo[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) xo[i] = __float_as_uint(xn[i]);

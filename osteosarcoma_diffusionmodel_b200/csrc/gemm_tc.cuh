@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
                     const int xb = xit & 1;
                     const uint32_t xphase = static_cast<uint32_t>(xit >> 1) & 1u;
                     ++xit;
-                    if (!mbar_wait(&xempty_bar[xb], xphase ^ 1u)) { ok = false; break; }
+                    if (!mbar_wait_relaxed(&xempty_bar[xb], xphase ^ 1u)) { ok = false; break; }
                     mbar_arrive_expect_tx(&xfull_bar[xb], X_TILE_BYTES);
 #pragma unroll
                     for (int b = 0; b < BN / X_BOX_COLS; ++b)
@@ -359,14 +359,14 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
                 if (XSTAGE && seq.ares) {
                     const KSeg sg = p.seg[0];
                     if (first) {
-                        if (!mbar_wait(aempty_bar, (static_cast<uint32_t>(uit) & 1u) ^ 1u)) { ok = false; break; }
+                        if (!mbar_wait_relaxed(aempty_bar, (static_cast<uint32_t>(uit) & 1u) ^ 1u)) { ok = false; break; }
                         ++uit;
                         mbar_arrive_expect_tx(afull_bar, sg.nkb * A_TILE_BYTES);
                         for (int kb = 0; kb < sg.nkb; ++kb)
                             tma_load_2d(&p.tma_a[0], smem + kb * A_TILE_BYTES, afull_bar, sg.a_col + kb * BK, ti.m_blk * BM);
                     }
                     for (int kb = 0; kb < sg.nkb; ++kb) {
-                        if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; break; }
+                        if (!mbar_wait_relaxed(&empty_bar[stage], phase ^ 1u)) { ok = false; break; }
                         mbar_arrive_expect_tx(&full_bar[stage], B_TILE_BYTES);
                         tma_load_2d(&p.tma_b[0], smem + 4 * A_TILE_BYTES + stage * B_TILE_BYTES, &full_bar[stage], sg.b_col + kb * BK, sg.b_row0 + ti.n_blk * BN);
                         if (++stage == ring) { stage = 0; phase ^= 1u; }
@@ -379,7 +379,7 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
                     const CUtensorMap* tb = &p.tma_b[sg.b_sel];
                     const int kb_begin = MN ? ti.kb0 : 0, kb_end = MN ? ti.kb1 : sg.nkb;
                     for (int kb = kb_begin; kb < kb_end; ++kb) {
-                        if (!mbar_wait(&empty_bar[stage], phase ^ 1u)) { ok = false; break; }
+                        if (!mbar_wait_relaxed(&empty_bar[stage], phase ^ 1u)) { ok = false; break; }
                         mbar_arrive_expect_tx(&full_bar[stage], A_TILE_BYTES + B_TILE_BYTES);
                         uint8_t* sa = smem_a + stage * A_TILE_BYTES;
                         uint8_t* sb = smem_b + stage * B_TILE_BYTES;
@@ -404,55 +404,62 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
         }
     } else if (warp == 1) {
         // -------------------------------------------------------------- MMA issuer
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MN ? 1 : 0, MN ? 1 : 0);
-            int stage = 0;
-            uint32_t phase = 0;
-            int it = 0, uit = 0;
-            bool ok = true;
-            TileSeq<EPI, MN> seq(p);
-            TileInfo ti;
-            bool first, last;
-            while (ok && seq.next(ti, first, last)) {
-                if (ti.skip) continue;
-                const int acc = it % NUM_ACC;
-                const uint32_t acc_phase = static_cast<uint32_t>(it / NUM_ACC) & 1u;
-                ++it;
-                if (!mbar_wait(&tempty_bar[acc], acc_phase ^ 1u)) { ok = false; break; }
-                tc_fence_after_sync();
-                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
-                uint32_t accumulate = 0;
-                if (XSTAGE && seq.ares) {
-                    if (first) {
-                        if (!mbar_wait(afull_bar, static_cast<uint32_t>(uit) & 1u)) { ok = false; break; }
-                        ++uit;
-                        tc_fence_after_sync();
-                    }
-                    const int nkb = p.seg[0].nkb;
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        if (!mbar_wait(&full_bar[stage], phase)) { ok = false; break; }
-                        tc_fence_after_sync();
+        // The whole warp walks the tile sequence with warp-uniform control flow; only the tcgen05 instructions are predicated on
+        // one elected lane. (Inside an `if (lane == 0)` region the compiler wraps every UTCHMMA / UTCBAR in an ELECT + branch loop
+        // and rebuilds the descriptors through vector registers: ~10 dependent instructions per MMA from a single thread, which
+        // cannot keep a 64-cycle MMA pipe full.)
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN, MN ? 1 : 0, MN ? 1 : 0);
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0, uit = 0;
+        bool ok = true;
+        TileSeq<EPI, MN> seq(p);
+        TileInfo ti;
+        bool first, last;
+        while (ok && seq.next(ti, first, last)) {
+            if (ti.skip) continue;
+            const int acc = it % NUM_ACC;
+            const uint32_t acc_phase = static_cast<uint32_t>(it / NUM_ACC) & 1u;
+            ++it;
+            if (!mbar_wait_relaxed(&tempty_bar[acc], acc_phase ^ 1u)) { ok = false; break; }
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+            uint32_t accumulate = 0;
+            if (XSTAGE && seq.ares) {
+                if (first) {
+                    if (!mbar_wait_relaxed(afull_bar, static_cast<uint32_t>(uit) & 1u)) { ok = false; break; }
+                    ++uit;
+                    tc_fence_after_sync();
+                }
+                const int nkb = p.seg[0].nkb;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    if (!mbar_wait_relaxed(&full_bar[stage], phase)) { ok = false; break; }
+                    tc_fence_after_sync();
+                    if (leader) {
                         const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(smem + kb * A_TILE_BYTES));
                         const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + 4 * A_TILE_BYTES + stage * B_TILE_BYTES));
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accumulate);
-                            accumulate = 1;
-                        }
+                        for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (accumulate | static_cast<uint32_t>(k)) != 0 ? 1u : 0u);
                         umma_commit(&empty_bar[stage]);
-                        if (++stage == 2) { stage = 0; phase ^= 1u; }
                     }
-                    if (ok) {
-                        umma_commit(&tfull_bar[acc]);
-                        if (last) umma_commit(aempty_bar);     // every MMA that reads the resident A tile has retired
-                    }
-                    continue;
+                    __syncwarp();
+                    accumulate = 1;
+                    if (++stage == 2) { stage = 0; phase ^= 1u; }
                 }
-                for (int s = 0; s < p.nseg && ok; ++s) {
-                    const int kb_begin = MN ? ti.kb0 : 0, kb_end = MN ? ti.kb1 : p.seg[s].nkb;
-                    for (int kb = kb_begin; kb < kb_end; ++kb) {
-                        if (!mbar_wait(&full_bar[stage], phase)) { ok = false; break; }
-                        tc_fence_after_sync();
+                if (ok && leader) {
+                    umma_commit(&tfull_bar[acc]);
+                    if (last) umma_commit(aempty_bar);     // every MMA that reads the resident A tile has retired
+                }
+                __syncwarp();
+                continue;
+            }
+            for (int s = 0; s < p.nseg && ok; ++s) {
+                const int kb_begin = MN ? ti.kb0 : 0, kb_end = MN ? ti.kb1 : p.seg[s].nkb;
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    if (!mbar_wait_relaxed(&full_bar[stage], phase)) { ok = false; break; }
+                    tc_fence_after_sync();
+                    if (leader) {
                         const uint32_t a_addr = smem_u32(smem_a + stage * A_TILE_BYTES);
                         const uint32_t b_addr = smem_u32(smem_b + stage * B_TILE_BYTES);
                         if (MN) {
@@ -461,8 +468,7 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {
                                 // 16 batch rows per UMMA_K step = 16 * 128 B inside each box
-                                umma_bf16(d_tmem, adesc + 128u * k, bdesc + 128u * k, idesc, accumulate);
-                                accumulate = 1;
+                                umma_bf16(d_tmem, adesc + 128u * k, bdesc + 128u * k, idesc, (accumulate | static_cast<uint32_t>(k)) != 0 ? 1u : 0u);
                             }
                         } else {
                             const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
@@ -470,18 +476,20 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
 #pragma unroll
                             for (int k = 0; k < BK / 16; ++k) {
                                 // +32 B per UMMA_K step inside the 128-byte swizzle row (start-address field is >>4)
-                                umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, accumulate);
-                                accumulate = 1;
+                                umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (accumulate | static_cast<uint32_t>(k)) != 0 ? 1u : 0u);
                             }
                         }
                         umma_commit(&empty_bar[stage]);
-                        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                     }
+                    __syncwarp();
+                    accumulate = 1;
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                if (ok) umma_commit(&tfull_bar[acc]);
             }
-            if (!ok) atomicExch(p.status, ERR_MMA_TIMEOUT);
+            if (ok && leader) umma_commit(&tfull_bar[acc]);
+            __syncwarp();
         }
+        if (!ok && leader) atomicExch(p.status, ERR_MMA_TIMEOUT);
     } else if (warp >= 4) {
         // ---------------------------------------------------------------- epilogue
         const int q = warp & 3;                 // TMEM lane quadrant this warp may access

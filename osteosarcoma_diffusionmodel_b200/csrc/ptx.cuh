@@ -26,6 +26,17 @@ __device__ __forceinline__ uint32_t lane_id() {
     return l;
 }
 
+// One lane of the (fully active) warp is elected; every lane gets the same answer on every call within a warp-uniform region.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ----------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -61,6 +72,19 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity) {
     const long long t0 = clock64();
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 63u) == 0 && clock64() - t0 > OSTEO_WAIT_LIMIT_CYCLES) return false;
+    }
+    return true;
+}
+
+// Same, for the single-purpose role warps (TMA producers, MMA issuer): sleep a few tens of ns between polls so that a role warp
+// that is far ahead of its consumers does not burn issue slots of the scheduler it shares with four epilogue warps.
+__device__ __forceinline__ bool mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return true;
+    const long long t0 = clock64();
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(40);
         if ((++spins & 63u) == 0 && clock64() - t0 > OSTEO_WAIT_LIMIT_CYCLES) return false;
     }
     return true;

@@ -1,5 +1,6 @@
 """Diagnostic: per-kernel times of one reverse step at t=500 under the OSTEO_DDPM_DBG switches (comma-separated list in PROBE_DBG).
-Fused step (fused_step.cuh) bits: 1 = no L2 prefetch of the state, 4 = no state store, 8 = no noise (sigma = 0), 16 = no state load."""
+Fused step (fused_step.cuh) bits: 1 = no L2 prefetch of the state, 4 = no state store, 8 = no noise (sigma = 0), 16 = no state load,
+64 / 128 = skip the eps / next-input_proj MMAs (timing probes only: results are wrong)."""
 import os, sys, ctypes as C
 sys.path.insert(0, ".")
 import torch
