@@ -9,14 +9,20 @@
 // x_{t-1} is rounded to bf16 into shared memory in the UMMA K-major layout and immediately contracted
 // against W_in[:, 64 columns] into a per-row-block TMEM accumulator.
 //
-// Work unit = one 128-row block, all DP / 64 column tiles. Roles (640 threads, 1 CTA / SM):
-//   (logical warps; physically the four role warps are 16..19 and the epilogue warps 0..15, see the kernel)
-//   warp 0      TMA producer: resident A (h_final, 128 x h0 bf16) once per unit, W_out tile [64 x h0] per column tile
-//   warp 1      MMA issuer: eps(j) = A . W_out[j]^T  (M128 N64),  acc_in += xbf(j-2) . W_in[j-2]^T  (M128 N=h0)
-//   warp 2      TMEM allocator (512 columns: acc_in 256 | 4 eps stages of 64)
-//   warp 3      TMA producer for W_in tiles [h0 x 64] + L2 prefetch of the state tile two tiles ahead
-//   warps 4-19  epilogue: thread <-> one row x 16 columns of the tile: Philox + Box-Muller noise, update,
-//               256-bit global load / store of the fp32 state, bf16 tile into shared memory
+// The noise never passes through the update warps either: NOISE warps preload every eps accumulator stage in TMEM
+// (tcgen05.st) with  b_out - (sigma / c_eps) z , the eps MMAs accumulate on top of it, and the update is then
+//   x_{t-1} = c_x x - c_eps acc            (one FMUL + one FFMA per element).
+// That splits the ALU-dense Philox / Box-Muller stream (16 warps, run up to four tiles ahead) from the latency-bound
+// path (8 warps: state load, TMEM read, state store, bf16 tile publish).
+//
+// Work unit = one 128-row block, all DP / 64 column tiles. 896 threads, 1 CTA / SM, physical warp ids:
+//   0-7    update warps   quadrant = warp % 4, 32 columns each (two passes of 16)
+//   8-23   noise warps    quadrant = warp % 4, 16 columns each
+//   24     TMA producer: resident A (h_final, 128 x h0 bf16) once per unit, W_out tile [64 x h0] per column tile
+//   25     MMA issuer: eps(j) += A . W_out[j]^T  (M128 N64),  acc_in += xbf(j-2) . W_in[j-2]^T  (M128 N=h0)
+//   26     TMEM allocator (512 columns: acc_in 256 | 4 eps stages of 64)
+//   27     TMA producer for W_in tiles [h0 x 64] + L2 prefetch of the state tile two tiles ahead
+// The role warps have the highest warp ids on purpose: the scheduler arbiter favours high warp ids.
 //
 // State layout ("c8"): x[m_block][DP / 8][128 rows][8 cols] fp32, so one warp-wide 256-bit access (32 rows x 32 B)
 // is 1 KB contiguous and a whole 128 x 64 tile is 32 KB contiguous.
@@ -26,8 +32,9 @@
 namespace osteo {
 
 constexpr int FT = 64;                                  // state columns per tile
-constexpr int F_EPI_WARPS = 16;
-constexpr int F_THREADS = 128 + 32 * F_EPI_WARPS;       // 640
+constexpr int F_UPD_WARPS = 8;
+constexpr int F_NOISE_WARPS = 16;
+constexpr int F_THREADS = 32 * (F_UPD_WARPS + F_NOISE_WARPS + 4);   // 896
 constexpr int F_ARES_BYTES = 4 * A_TILE_BYTES;          // 64 KB: up to 4 k-blocks of [128 x 64] bf16
 constexpr int F_WOUT_KB_BYTES = FT * BK * 2;            // 8 KB: one k-block of a W_out tile [64 x 64]
 constexpr int F_WOUT_STAGE = 4 * F_WOUT_KB_BYTES;       // 32 KB
@@ -37,9 +44,7 @@ constexpr int F_STAGES = 2;
 constexpr int F_EPS_ACC = 4;
 constexpr int F_LAG = 2;                                // the next-step contraction trails the eps GEMM by two tiles
 constexpr int F_TMEM_EPS0 = 256;                        // first TMEM column of the eps stages
-constexpr int F_BIAS_SLOTS = 6;                         // output_proj bias of a tile (64 floats) rides along with its W_out tile
-constexpr int F_BIAS_BYTES = FT * 4;
-constexpr int F_SMEM_BYTES = F_ARES_BYTES + F_STAGES * (F_WOUT_STAGE + F_WIN_STAGE + F_XBF_STAGE) + 1024 /*align*/ + 256 /*barriers*/ + F_BIAS_SLOTS * F_BIAS_BYTES;
+constexpr int F_SMEM_BYTES = F_ARES_BYTES + F_STAGES * (F_WOUT_STAGE + F_WIN_STAGE + F_XBF_STAGE) + 1024 /*align*/ + 256 /*barriers*/;
 
 struct FusedParams {
     CUtensorMap tma_a;        // h_final bf16 [rows, 2*h0], box 128 x 64
@@ -69,7 +74,8 @@ struct FusedParams {
     const float* cproj;       // [rows, h0]
     __nv_bfloat16* h0_out;    // [rows, h0_ld] bf16: the next step's first activation
     int h0_ld;
-    int dbg;
+    long long* trace;         // optional event trace of CTA 0 (diagnostics, OSTEO_DDPM_TRACE): [role 0..2][tile < 32][8] clock64 stamps
+    int dbg;                  // timing probes (scripts/ddpm_probe.py): 1 no L2 prefetch, 4 no state store, 8 no noise, 16 no state load
 };
 
 __device__ __forceinline__ void ld_global_v8(const void* ptr, uint32_t (&w)[8]) {
@@ -78,20 +84,28 @@ __device__ __forceinline__ void ld_global_v8(const void* ptr, uint32_t (&w)[8]) 
                  : "l"(ptr)
                  : "memory");
 }
-// 1-D bulk copy global -> shared (size a multiple of 16 B), completion counted on `bar` like a tensor load.
-__device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
+#define F_TRACE(role, tile, ev) do { if (p.trace && blockIdx.x == 0 && (tile) < 32 && lane == 0) p.trace[((role) * 32 + (tile)) * 8 + (ev)] = clock64(); } while (0)
 __device__ __forceinline__ void l2_prefetch_bulk(const void* ptr, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr), "r"(bytes) : "memory");
 }
+// registers -> TMEM: this warp's 32 lanes (rows) x 16 consecutive fp32 columns.
+__device__ __forceinline__ void tmem_st_16(uint32_t taddr, const float (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+          "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+          "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+          "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+        : "memory");
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
 
-// 16 scaled normals sg * z for columns [4*col4_0, 4*col4_0 + 16) of one row. Same Philox counters and uniforms as
-// philox_normal_row (philox.cuh); sigma is folded into the Box-Muller radius: sg * sqrt(-2 ln u1) = sqrt(k2 * lg2 u1),
-// k2 = -2 ln2 sg^2.
-__device__ __forceinline__ void philox_scaled_normal16(uint64_t seed, uint64_t row, uint32_t col4_0, uint32_t stream, uint32_t step, float k2, float (&z)[16]) {
+// out[i] = base[i] + kr * z_i for the 16 columns [4*col4_0, 4*col4_0 + 16) of one row, z_i the Philox4x32-10 + Box-Muller normals of
+// philox_normal_row (philox.cuh: same counters, same uniforms). |kr| is folded into the Box-Muller radius,
+// |kr| sqrt(-2 ln u1) = sqrt(k2 lg2 u1) with k2 = -2 ln2 kr^2; `neg` carries the sign of kr.
+__device__ __forceinline__ void philox_axpy_normal16(uint64_t seed, uint64_t row, uint32_t col4_0, uint32_t stream, uint32_t step, float k2, bool neg,
+                                                     const float (&base)[16], float (&out)[16]) {
     uint4 c[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -111,12 +125,16 @@ __device__ __forceinline__ void philox_scaled_normal16(uint64_t seed, uint64_t r
             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(k2 * l2));
             asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
             asm("cos.approx.ftz.f32 %0, %1;" : "=f"(co) : "f"(th));
-            z[4 * i + 2 * h] = r * co;
-            z[4 * i + 2 * h + 1] = r * s;
+            r = neg ? -r : r;
+            out[4 * i + 2 * h] = fmaf(r, co, base[4 * i + 2 * h]);
+            out[4 * i + 2 * h + 1] = fmaf(r, s, base[4 * i + 2 * h + 1]);
         }
     }
 }
 
+// HOOKS = true: the parity-test variant that can also write eps out (p.eps_out); the production variant carries none of that code,
+// which keeps the update warps inside the 72-register budget of an 896-thread CTA without spilling.
+template <bool HOOKS>
 __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -125,62 +143,57 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
     uint8_t* s_win = s_wout + F_STAGES * F_WOUT_STAGE;
     uint8_t* s_xbf = s_win + F_STAGES * F_WIN_STAGE;
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_xbf + F_STAGES * F_XBF_STAGE);
-    uint64_t* a_full = bars;
-    uint64_t* a_empty = bars + 1;
-    uint64_t* wout_full = bars + 2;
-    uint64_t* wout_empty = bars + 4;
-    uint64_t* win_full = bars + 6;
-    uint64_t* win_empty = bars + 8;
-    uint64_t* xbf_full = bars + 10;
-    uint64_t* xbf_empty = bars + 12;
-    uint64_t* tfull = bars + 14;
-    uint64_t* tempty = bars + 18;
+    uint64_t* a_full = bars;                // resident A landed
+    uint64_t* a_empty = bars + 1;           // every eps MMA of the unit has retired
+    uint64_t* wout_full = bars + 2;         // [2] W_out tile landed
+    uint64_t* win_full = bars + 4;          // [2] W_in tile landed
+    uint64_t* xbf_full = bars + 6;          // [2] bf16 tile of x_{t-1} written by the update warps
+    uint64_t* xbf_empty = bars + 8;         // [2] next-step MMA of that tile retired (frees the bf16 tile AND the W_in stage)
+    uint64_t* tfull = bars + 10;            // [4] eps accumulator complete (also frees the W_out stage)
+    uint64_t* tempty = bars + 14;           // [4] update warps have read the accumulator
+    uint64_t* zfull = bars + 18;            // [4] noise warps have preloaded the accumulator stage
     uint64_t* accin_full = bars + 22;
     uint64_t* accin_empty = bars + 23;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
-    uint8_t* s_bias = reinterpret_cast<uint8_t*>(bars) + 256;      // F_BIAS_SLOTS x 256 B
 
-    // Role warps take the HIGHEST warp ids: the SMSP arbiter favours high warp ids, and a starved MMA issuer / TMA producer stalls
-    // all sixteen epilogue warps. Epilogue warps are 0..15 (TMEM lane quadrant = warp % 4).
-    const int warp_phys = threadIdx.x >> 5;
-    const int warp = warp_phys < F_EPI_WARPS ? warp_phys + 4 : warp_phys - F_EPI_WARPS;      // logical: 0..3 roles, 4..19 epilogue
+    const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    constexpr int W_PROD = F_UPD_WARPS + F_NOISE_WARPS, W_MMA = W_PROD + 1, W_ALLOC = W_PROD + 2, W_WIN = W_PROD + 3;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == W_PROD && lane == 0) {
         tma_prefetch_desc(&p.tma_a);
         tma_prefetch_desc(&p.tma_wout);
         tma_prefetch_desc(&p.tma_win);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == W_MMA && lane == 0) {
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int i = 0; i < F_STAGES; ++i) {
             mbar_init(&wout_full[i], 1);
-            mbar_init(&wout_empty[i], 1);
             mbar_init(&win_full[i], 1);
-            mbar_init(&win_empty[i], 1);
-            mbar_init(&xbf_full[i], F_EPI_WARPS);
+            mbar_init(&xbf_full[i], F_UPD_WARPS);
             mbar_init(&xbf_empty[i], 1);
         }
         for (int i = 0; i < F_EPS_ACC; ++i) {
             mbar_init(&tfull[i], 1);
-            mbar_init(&tempty[i], F_EPI_WARPS);
+            mbar_init(&tempty[i], F_UPD_WARPS);
+            mbar_init(&zfull[i], F_NOISE_WARPS);
         }
         mbar_init(accin_full, 1);
-        mbar_init(accin_empty, F_EPI_WARPS);
+        mbar_init(accin_empty, F_UPD_WARPS);
         fence_mbar_init();
     }
-    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp == W_ALLOC) tmem_alloc(tmem_slot, 512);
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
     const int nt = p.n_tiles;
 
-    if (warp == 0) {
+    if (warp == W_PROD) {
         // ------------------------------------------------ producer: resident A + W_out tiles
         if (lane == 0) {
-            int itw = 0, k = 0, bslot = 0;
+            int itw = 0, k = 0;
             bool ok = true;
             for (int u = blockIdx.x; ok && u < p.m_tiles; u += gridDim.x, ++k) {
                 const int m_blk = p.m_tile0 + u;
@@ -191,18 +204,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                     const int s = itw & 1;
                     // stage s was last read by eps(itw - 2): its completion is that tile's tfull barrier (no separate "empty" commit)
                     if (itw >= 2 && !mbar_wait_relaxed(&tfull[(itw - 2) & (F_EPS_ACC - 1)], (static_cast<uint32_t>(itw - 2) >> 2) & 1u)) { ok = false; break; }
-                    // the bias slot of tile itw - 6 is free: eps(itw - 2) has completed, so the epilogue of tile itw - 6 has arrived on
-                    // tempty, which it does only after reading its bias
-                    mbar_arrive_expect_tx(&wout_full[s], p.nkb * F_WOUT_KB_BYTES + F_BIAS_BYTES);
+                    if ((p.dbg & 32) && itw >= 2) { mbar_arrive(&wout_full[s]); continue; }      // timing probe: no weight traffic (wrong results)
+                    mbar_arrive_expect_tx(&wout_full[s], p.nkb * F_WOUT_KB_BYTES);
                     for (int kb = 0; kb < p.nkb; ++kb)
                         tma_load_2d(&p.tma_wout, s_wout + s * F_WOUT_STAGE + kb * F_WOUT_KB_BYTES, &wout_full[s], kb * BK, j * FT);
-                    bulk_load_1d(s_bias + bslot * F_BIAS_BYTES, p.bias_out + j * FT, F_BIAS_BYTES, &wout_full[s]);
-                    bslot = bslot + 1 == F_BIAS_SLOTS ? 0 : bslot + 1;
                 }
             }
             if (!ok) atomicExch(p.status, ERR_PRODUCER_TIMEOUT);
         }
-    } else if (warp == 3) {
+    } else if (warp == W_WIN) {
         // ------------------------------------------------ producer: W_in tiles + L2 prefetch of the state
         if (lane == 0) {
             int iti = 0;
@@ -220,13 +230,14 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                     // stage s was last read by the next-step MMA of tile iti - 2, which also releases the bf16 tile buffer: one barrier
                     if (!mbar_wait_relaxed(&xbf_empty[s], ((static_cast<uint32_t>(iti) >> 1) & 1u) ^ 1u)) { ok = false; break; }
                     if (j + 2 < nt && !(p.dbg & 1)) l2_prefetch_bulk(xblk + static_cast<size_t>(j + 2) * tile_floats, static_cast<uint32_t>(tile_floats * 4));
+                    if ((p.dbg & 32) && iti >= 2) { mbar_arrive(&win_full[s]); continue; }
                     mbar_arrive_expect_tx(&win_full[s], p.h0 * BK * 2);
                     tma_load_2d(&p.tma_win, s_win + s * F_WIN_STAGE, &win_full[s], j * FT, 0);
                 }
             }
             if (!ok) atomicExch(p.status, ERR_PRODUCER_TIMEOUT);
         }
-    } else if (warp == 1) {
+    } else if (warp == W_MMA) {
         // ------------------------------------------------ MMA issuer
         // The WHOLE warp runs this loop with warp-uniform control flow and only the tcgen05 instructions are predicated on one
         // elected lane: inside an `if (lane == 0)` region the compiler wraps every UTCHMMA / UTCBAR in an ELECT + branch loop and
@@ -248,20 +259,23 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                 if (j < nt) {
                     const int s = it_eps & 1, acc = it_eps & (F_EPS_ACC - 1);
                     if (!mbar_wait_relaxed(&wout_full[s], (static_cast<uint32_t>(it_eps) >> 1) & 1u)) { ok = false; break; }
-                    if (!mbar_wait_relaxed(&tempty[acc], ((static_cast<uint32_t>(it_eps) >> 2) & 1u) ^ 1u)) { ok = false; break; }
+                    // the stage holds b_out - (sigma / c_eps) z, written by the noise warps after the update warps released it
+                    if (!mbar_wait_relaxed(&zfull[acc], (static_cast<uint32_t>(it_eps) >> 2) & 1u)) { ok = false; break; }
                     tc_fence_after_sync();
-                    if (leader && !(p.dbg & 64)) {
+                    F_TRACE(0, it_eps, 0);
+                    if (leader) {
                         const uint32_t d = tmem_base + F_TMEM_EPS0 + static_cast<uint32_t>(acc * FT);
                         const uint64_t bdesc_s = wout_desc0 + static_cast<uint64_t>((s * F_WOUT_STAGE) >> 4);
                         for (int kb = 0; kb < p.nkb; ++kb) {
                             const uint64_t adesc = adesc0 + static_cast<uint64_t>((kb * A_TILE_BYTES) >> 4);
                             const uint64_t bdesc = bdesc_s + static_cast<uint64_t>((kb * F_WOUT_KB_BYTES) >> 4);
 #pragma unroll
-                            for (int kk = 0; kk < BK / 16; ++kk) umma_bf16(d, adesc + 2u * kk, bdesc + 2u * kk, idesc_eps, (kb | kk) != 0 ? 1u : 0u);
+                            for (int kk = 0; kk < BK / 16; ++kk) umma_bf16(d, adesc + 2u * kk, bdesc + 2u * kk, idesc_eps, 1u);
                         }
+                        umma_commit(&tfull[acc]);
                     }
-                    if (leader) umma_commit(&tfull[acc]);
                     __syncwarp();
+                    F_TRACE(0, it_eps, 1);
                     ++it_eps;
                 }
                 if (j >= F_LAG) {
@@ -271,16 +285,16 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                     if (!mbar_wait_relaxed(&xbf_full[s], (static_cast<uint32_t>(it_in) >> 1) & 1u)) { ok = false; break; }
                     if (!mbar_wait_relaxed(&win_full[s], (static_cast<uint32_t>(it_in) >> 1) & 1u)) { ok = false; break; }
                     tc_fence_after_sync();
+                    F_TRACE(0, it_in, 2);
                     if (leader) {
                         const uint64_t adesc = xbf_desc0 + static_cast<uint64_t>((s * F_XBF_STAGE) >> 4);
                         const uint64_t bdesc = win_desc0 + static_cast<uint64_t>((s * F_WIN_STAGE) >> 4);
-                        if (!(p.dbg & 128)) {
 #pragma unroll
-                            for (int kk = 0; kk < BK / 16; ++kk) umma_bf16(tmem_base, adesc + 2u * kk, bdesc + 2u * kk, idesc_in, (jj | kk) != 0 ? 1u : 0u);
-                        }
+                        for (int kk = 0; kk < BK / 16; ++kk) umma_bf16(tmem_base, adesc + 2u * kk, bdesc + 2u * kk, idesc_in, (jj | kk) != 0 ? 1u : 0u);
                         umma_commit(&xbf_empty[s]);
                     }
                     __syncwarp();
+                    F_TRACE(0, it_in, 3);
                     ++it_in;
                 }
             }
@@ -291,17 +305,70 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
             __syncwarp();
         }
         if (!ok && leader) atomicExch(p.status, ERR_MMA_TIMEOUT);
-    } else if (warp >= 4) {
-        // ------------------------------------------------ epilogue
-        const int q = warp_phys & 3;            // TMEM lane quadrant (hardware rule: physical warp id % 4)
-        const int part = warp_phys >> 2;        // 16-column quarter of the 64-column tile
+    } else if (warp >= F_UPD_WARPS && warp < W_PROD) {
+        // ------------------------------------------------ noise warps: preload the eps accumulator stage
+        const int q = warp & 3;                             // TMEM lane quadrant (hardware rule: warp id % 4)
+        const int part = (warp - F_UPD_WARPS) >> 2;         // 16-column quarter of the 64-column tile
+        const int r_tile = q * 32 + lane;
+        const int t = *p.step;
+        const float ce = __ldg(p.coef_eps + t);
+        const float sg = (p.dbg & 8) ? 0.0f : __ldg(p.coef_sigma + t);
+        // eps_out (parity hook) needs the raw eps in the accumulator: the update warps then add the noise themselves
+        const float kr = (HOOKS && p.eps_out) ? 0.0f : -sg / ce;       // accumulator preload = b_out + kr z
+        const float k2 = -1.3862943611198906f * kr * kr;
+        int it = 0;
+        bool ok = true;
+        for (int u = blockIdx.x; ok && u < p.m_tiles; u += gridDim.x) {
+            const int m_blk = p.m_tile0 + u;
+            const int row = m_blk * BM + r_tile;
+            const bool live = row < p.M;
+            for (int j = 0; j < nt && ok; ++j, ++it) {
+                const int c0 = j * FT + part * 16;
+                const int nvalid = p.N - c0;
+                if (warp == F_UPD_WARPS) F_TRACE(1, it, 0);
+                float v[16];
+                {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.bias_out + c0);      // zero padded up to DP
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 b = __ldg(b4 + i);
+                        v[4 * i] = b.x; v[4 * i + 1] = b.y; v[4 * i + 2] = b.z; v[4 * i + 3] = b.w;
+                    }
+                }
+                if (live && nvalid > 0 && kr != 0.0f) {
+                    if (p.noise) {
+                        const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c0;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (i < nvalid) v[i] = fmaf(kr, nz[i], v[i]);
+                    } else {
+                        philox_axpy_normal16(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 2), STREAM_REVERSE, static_cast<uint32_t>(t), k2,
+                                             /*neg=*/true, v, v);
+                    }
+                }
+                const int acc = it & (F_EPS_ACC - 1);
+                if (warp == F_UPD_WARPS) F_TRACE(1, it, 1);
+                if (!mbar_wait(&tempty[acc], ((static_cast<uint32_t>(it) >> 2) & 1u) ^ 1u)) { ok = false; break; }
+                tc_fence_after_sync();
+                if (warp == F_UPD_WARPS) F_TRACE(1, it, 2);
+                tmem_st_16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(F_TMEM_EPS0 + acc * FT + part * 16), v);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&zfull[acc]);
+                if (warp == F_UPD_WARPS) F_TRACE(1, it, 3);
+            }
+        }
+        if (!ok && lane == 0) atomicExch(p.status, ERR_EPI_TIMEOUT);
+    } else if (warp < F_UPD_WARPS) {
+        // ------------------------------------------------ update warps
+        const int q = warp & 3;                 // TMEM lane quadrant
+        const int half = warp >> 2;             // 32-column half of the 64-column tile
         const int r_tile = q * 32 + lane;
         const int t = *p.step;
         const float cx = __ldg(p.coef_x + t), nce = -__ldg(p.coef_eps + t);
         const float sg = (p.dbg & 8) ? 0.0f : __ldg(p.coef_sigma + t);
-        const float k2 = -1.3862943611198906f * sg * sg;
         const int t_next = t > 0 ? t - 1 : 0;
-        int it = 0, k = 0, bslot = 0;
+        int it = 0, k = 0;
         bool ok = true;
         for (int u = blockIdx.x; ok && u < p.m_tiles; u += gridDim.x, ++k) {
             const int m_blk = p.m_tile0 + u;
@@ -309,105 +376,103 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
             const bool live = row < p.M;
             float* xrow = p.x + (static_cast<size_t>(m_blk) * p.x_c8 * BM + r_tile) * 8;      // + c8 * (BM * 8)
             for (int j = 0; j < nt && ok; ++j, ++it) {
-                const int c0 = j * FT + part * 16;
-                float* xp = xrow + static_cast<size_t>(c0 >> 3) * (BM * 8);
-                const int nvalid = p.N - c0;            // >= 16: all columns valid; <= 0: all padding
-                uint32_t xw[16];
-                float z[16];
+                if (warp == 0) F_TRACE(2, it, 0);
+                const int cb = j * FT + half * 32;
+                float* xp = xrow + static_cast<size_t>(cb >> 3) * (BM * 8);
+                // the state of this tile (L2-resident: prefetched two tiles ahead by the W_in producer)
+                uint32_t xw[32];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) { xw[i] = 0u; z[i] = 0.0f; }
-                if (live && nvalid > 0 && !(p.dbg & 16)) {
-                    ld_global_v8(xp, *reinterpret_cast<uint32_t(*)[8]>(&xw[0]));
-                    ld_global_v8(xp + BM * 8, *reinterpret_cast<uint32_t(*)[8]>(&xw[8]));
-                }
-                if (live && nvalid > 0 && sg != 0.0f) {
-                    if (p.noise) {
-                        const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c0;
+                for (int i = 0; i < 32; ++i) xw[i] = 0u;
+                if (live && p.N > cb && !(p.dbg & 16)) {
 #pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            if (i < nvalid) z[i] = sg * nz[i];
-                    } else {
-                        philox_scaled_normal16(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 2), STREAM_REVERSE, static_cast<uint32_t>(t), k2, z);
-                    }
+                    for (int g = 0; g < 4; ++g) ld_global_v8(xp + g * (BM * 8), *reinterpret_cast<uint32_t(*)[8]>(&xw[8 * g]));
                 }
                 const int acc = it & (F_EPS_ACC - 1);
                 if (!mbar_wait(&tfull[acc], (static_cast<uint32_t>(it) >> 2) & 1u)) { ok = false; break; }
                 tc_fence_after_sync();
-                uint32_t vr[16];
-                tmem_ld_16_nowait(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(F_TMEM_EPS0 + acc * FT + part * 16), vr);
-                tmem_ld_wait();
-                // bias of this tile: staged in shared memory by the W_out producer (an L1 hit is not available: the whole L1 is carved out
-                // as shared memory, and an L2 round trip per tile on the critical path cost ~1000 cycles)
-                const float* sb = reinterpret_cast<const float*>(s_bias + bslot * F_BIAS_BYTES) + part * 16;
-                bslot = bslot + 1 == F_BIAS_SLOTS ? 0 : bslot + 1;
-                float xn[16];
-                if (nvalid >= 16) {
-                    const float4* b4 = reinterpret_cast<const float4*>(sb);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b = b4[i];
-                        const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const float ev = __uint_as_float(vr[4 * i + e]) + bb[e];
-                            xn[4 * i + e] = fmaf(nce, ev, fmaf(cx, __uint_as_float(xw[4 * i + e]), z[4 * i + e]));
-                        }
-                    }
-                    if (p.eps_out && live) {
-                        float* eo = p.eps_out + static_cast<size_t>(row) * p.eps_ld + c0;
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) eo[i] = __uint_as_float(vr[i]) + sb[i];
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        float v = 0.0f;
-                        if (i < nvalid) {
-                            const float ev = __uint_as_float(vr[i]) + sb[i];
-                            if (p.eps_out && live) p.eps_out[static_cast<size_t>(row) * p.eps_ld + c0 + i] = ev;
-                            v = fmaf(nce, ev, fmaf(cx, __uint_as_float(xw[i]), z[i]));
-                        }
-                        xn[i] = v;
-                    }
-                }
-                if (!live) {
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) xn[i] = 0.0f;
-                }
-                // accumulator and bias are in registers: hand the TMEM stage (and, transitively, the bias slot) back
-                tc_fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty[acc]);
-                uint32_t xo[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) xo[i] = __float_as_uint(xn[i]);
-                if (live && !(p.dbg & 4)) {
-                    st_global_v8(xp, *reinterpret_cast<uint32_t(*)[8]>(&xo[0]));
-                    st_global_v8(xp + BM * 8, *reinterpret_cast<uint32_t(*)[8]>(&xo[8]));
-                }
-                // bf16 tile for the next step's input_proj: row r_tile, 16-byte chunks 2*part and 2*part+1 of the 128-byte swizzled row
+                if (warp == 0) F_TRACE(2, it, 1);
                 const int s = it & 1;
-                if (!mbar_wait(&xbf_empty[s], ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u)) { ok = false; break; }
-                {
-                    uint8_t* rowp = s_xbf + s * F_XBF_STAGE + (r_tile >> 3) * 1024 + (r_tile & 7) * 128;
-                    const int sw = r_tile & 7;
+                uint8_t* rowp = s_xbf + s * F_XBF_STAGE + (r_tile >> 3) * 1024 + (r_tile & 7) * 128;
+                const int sw = r_tile & 7;
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                    const int c0 = cb + 16 * hh;
+                    const int nvalid = p.N - c0;            // >= 16: all columns valid; <= 0: all padding
+                    uint32_t vr[16];
+                    tmem_ld_16_nowait(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(F_TMEM_EPS0 + acc * FT + half * 32 + 16 * hh), vr);
+                    tmem_ld_wait();
+                    if (hh == 1) {
+                        // accumulator fully in registers: hand the TMEM stage back to the noise warps
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty[acc]);
+                        if (warp == 0) F_TRACE(2, it, 2);
+                    }
+                    float xn[16];
+                    if (!HOOKS || !p.eps_out) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) xn[i] = fmaf(nce, __uint_as_float(vr[i]), cx * __uint_as_float(xw[16 * hh + i]));
+                    } else {
+                        // parity hook: the accumulator holds the raw eps (+ bias); write it out and add the noise here
+                        float z[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) z[i] = 0.0f;
+                        if (live && nvalid > 0 && sg != 0.0f) {
+                            if (p.noise) {
+                                const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c0;
+#pragma unroll
+                                for (int i = 0; i < 16; ++i)
+                                    if (i < nvalid) z[i] = sg * nz[i];
+                            } else {
+                                philox_axpy_normal16(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 2), STREAM_REVERSE, static_cast<uint32_t>(t),
+                                                     -1.3862943611198906f * sg * sg, /*neg=*/false, z, z);
+                            }
+                        }
+                        if (live) {
+                            float* eo = p.eps_out + static_cast<size_t>(row) * p.eps_ld + c0;
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                if (i < nvalid) eo[i] = __uint_as_float(vr[i]);
+                        }
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) xn[i] = fmaf(nce, __uint_as_float(vr[i]), fmaf(cx, __uint_as_float(xw[16 * hh + i]), z[i]));
+                    }
+                    if (nvalid < 16 || !live) {      // keep the padding columns (and rows past the batch) at exactly zero
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            if (!live || i >= nvalid) xn[i] = 0.0f;
+                    }
+                    uint32_t xo[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) xo[i] = __float_as_uint(xn[i]);
+                    if (live && nvalid > 0 && !(p.dbg & 4)) {
+                        st_global_v8(xp + (2 * hh) * (BM * 8), *reinterpret_cast<uint32_t(*)[8]>(&xo[0]));
+                        st_global_v8(xp + (2 * hh + 1) * (BM * 8), *reinterpret_cast<uint32_t(*)[8]>(&xo[8]));
+                    }
+                    // bf16 tile for the next step's input_proj: row r_tile, 16-byte chunks of the 128-byte swizzled row
+                    if (hh == 0 && !mbar_wait(&xbf_empty[s], ((static_cast<uint32_t>(it) >> 1) & 1u) ^ 1u)) { ok = false; break; }
+                    if (hh == 0 && warp == 0) F_TRACE(2, it, 3);
                     uint4 w0, w1;
                     w0.x = pack_bf16x2(xn[0], xn[1]);   w0.y = pack_bf16x2(xn[2], xn[3]);   w0.z = pack_bf16x2(xn[4], xn[5]);   w0.w = pack_bf16x2(xn[6], xn[7]);
                     w1.x = pack_bf16x2(xn[8], xn[9]);   w1.y = pack_bf16x2(xn[10], xn[11]); w1.z = pack_bf16x2(xn[12], xn[13]); w1.w = pack_bf16x2(xn[14], xn[15]);
-                    *reinterpret_cast<uint4*>(rowp + (((2 * part) ^ sw) << 4)) = w0;
-                    *reinterpret_cast<uint4*>(rowp + (((2 * part + 1) ^ sw) << 4)) = w1;
+                    const int ch = 4 * half + 2 * hh;
+                    *reinterpret_cast<uint4*>(rowp + ((ch ^ sw) << 4)) = w0;
+                    *reinterpret_cast<uint4*>(rowp + (((ch + 1) ^ sw) << 4)) = w1;
                 }
+                if (!ok) break;
+                if (warp == 0) F_TRACE(2, it, 4);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&xbf_full[s]);
+                if (warp == 0) F_TRACE(2, it, 5);
             }
             if (!ok) break;
             // ---- unit end: h0 of the next step = acc_in + b_in + time_proj[t-1] + cond_proj  -> bf16
             if (!mbar_wait(accin_full, static_cast<uint32_t>(k) & 1u)) { ok = false; break; }
             tc_fence_after_sync();
-            const int cpw = p.h0 >> 2;              // columns per warp quarter (32 or 64)
+            const int cpw = p.h0 >> 1;              // columns per warp half (64 or 128)
             for (int cc = 0; cc < cpw; cc += 16) {
-                const int c = part * cpw + cc;
+                const int c = half * cpw + cc;
                 uint32_t vr[16];
                 tmem_ld_16_nowait(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(c), vr);
                 tmem_ld_wait();
@@ -438,7 +503,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(tmem_base, 512);
+    if (warp == W_ALLOC) tmem_dealloc(tmem_base, 512);
 }
 
 }  // namespace osteo

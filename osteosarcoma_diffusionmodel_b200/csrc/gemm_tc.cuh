@@ -33,9 +33,13 @@ constexpr int X_BUFFERS = 2;
 constexpr int NUM_ACC = 4;
 // Epilogue warps: 8 (thread <-> row x 64 columns: a whole GroupNorm group per thread) except for the RNG-heavy
 // reverse-update epilogue, which runs 16 (thread <-> row x 32 columns) to double the warps per scheduler.
-// ... and for Linear+GroupNorm+SiLU with groups of <= 32 columns (a group still fits one thread's 32 columns).
+// ... and for Linear+GroupNorm+SiLU: with 8 warps (2 per scheduler) its epilogue is latency-bound at a fifth of the issue rate.
+// A 64-wide group is then split over two warps (same rows, adjacent 32-column spans) that swap partial sums through shared memory.
 template <int EPI, int GW>
-__host__ __device__ constexpr int epi_warps_of() { return (EPI == 2 /*EPI_DDPM*/ || (EPI == 1 /*EPI_GN_SILU*/ && GW <= 32)) ? 16 : 8; }
+__host__ __device__ constexpr int epi_warps_of() { return (EPI == 2 /*EPI_DDPM*/ || EPI == 1 /*EPI_GN_SILU*/) ? 16 : 8; }
+constexpr int GN_PAR_MAX = 512;                         // widest layer whose bias / gamma / beta are kept in shared memory
+constexpr int GN_PAR_BYTES = 3 * GN_PAR_MAX * 4;        // [bias | gamma | beta]
+constexpr int GN_XCH_BYTES = 2 * 16 * 32 * 4;           // two exchange buffers, one float per epilogue thread
 template <int EPI, int GW>
 __host__ __device__ constexpr int gemm_threads() { return 128 + 32 * epi_warps_of<EPI, GW>(); }
 constexpr int A_TILE_BYTES = BM * BK * 2;
@@ -44,7 +48,8 @@ template <int EPI>
 __host__ __device__ constexpr int stages_of() { return EPI == 2 /*EPI_DDPM*/ ? STAGES_DDPM : STAGES_DEFAULT; }
 template <int EPI>
 __host__ __device__ constexpr int gemm_smem_bytes() {
-    return stages_of<EPI>() * (A_TILE_BYTES + B_TILE_BYTES) + (EPI == 2 ? X_BUFFERS * X_TILE_BYTES : 0) + 1024 /*align*/ + 256 /*barriers*/;
+    return stages_of<EPI>() * (A_TILE_BYTES + B_TILE_BYTES) + (EPI == 2 ? X_BUFFERS * X_TILE_BYTES : 0) + 1024 /*align*/ + 256 /*barriers*/ +
+           (EPI == 1 ? GN_PAR_BYTES + GN_XCH_BYTES : 0);
 }
 constexpr int MAX_KSEG = 8;
 
@@ -153,39 +158,35 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 __device__ __forceinline__ float bf16_round(float a) { return __bfloat162float(__float2bfloat16_rn(a)); }
 
 // Store 32 consecutive values of this thread's row as bf16 (and the bf16 residual at +lo_off).
-__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float (&v)[32], int lo_off) {
-    uint4* d = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        uint4 w;
-        w.x = pack_bf16x2(v[8 * j + 0], v[8 * j + 1]);
-        w.y = pack_bf16x2(v[8 * j + 2], v[8 * j + 3]);
-        w.z = pack_bf16x2(v[8 * j + 4], v[8 * j + 5]);
-        w.w = pack_bf16x2(v[8 * j + 6], v[8 * j + 7]);
-        d[j] = w;
-    }
-    if (lo_off > 0) {
-        uint4* dl = reinterpret_cast<uint4*>(dst + lo_off);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            float r[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) r[i] = v[8 * j + i] - bf16_round(v[8 * j + i]);
-            uint4 w;
-            w.x = pack_bf16x2(r[0], r[1]);
-            w.y = pack_bf16x2(r[2], r[3]);
-            w.z = pack_bf16x2(r[4], r[5]);
-            w.w = pack_bf16x2(r[6], r[7]);
-            dl[j] = w;
-        }
-    }
-}
-
 // 256-bit global store (sm_100+): one full 32-byte sector per lane.
 __device__ __forceinline__ void st_global_v8(void* ptr, const uint32_t (&w)[8]) {
     asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]),
                  "r"(w[7])
                  : "memory");
+}
+
+// dst must be 32-byte aligned (activation pitches and column offsets are multiples of 16 elements). Two 256-bit stores: each lane
+// writes full 32-byte sectors (its row is a different cache line from its neighbours', so narrower stores only half-fill sectors).
+__device__ __forceinline__ void store_row32_bf16(__nv_bfloat16* dst, const float (&v)[32], int lo_off) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[16 * j + 2 * i], v[16 * j + 2 * i + 1]);
+        st_global_v8(dst + 16 * j, w);
+    }
+    if (lo_off > 0) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float a = v[16 * j + 2 * i], b = v[16 * j + 2 * i + 1];
+                w[i] = pack_bf16x2(a - bf16_round(a), b - bf16_round(b));
+            }
+            st_global_v8(dst + lo_off + 16 * j, w);
+        }
+    }
 }
 
 // v[j] += src[j], j < 32, through eight 128-bit read-only loads (src 16-byte aligned).
@@ -295,6 +296,8 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
     uint64_t* afull_bar = xempty_bar + X_BUFFERS;      // A-resident mode: A tile landed / A tile no longer read by any MMA
     uint64_t* aempty_bar = afull_bar + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 1);
+    float* gn_par = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);      // EPI_GN_SILU: [bias | gamma | beta], GN_PAR_MAX each
+    float* gn_xch = gn_par + 3 * GN_PAR_MAX;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -327,6 +330,17 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if constexpr (EPI == EPI_GN_SILU) {
+        // The layer's bias / gamma / beta (N <= 512) live in shared memory for the whole kernel: the L1 is carved out as shared memory,
+        // so per-tile __ldg loads of them were L2 round trips on the epilogue's critical path.
+        if (warp >= 4 && p.N <= GN_PAR_MAX) {
+            for (int i = threadIdx.x - 128; i < p.N; i += NUM_EPI_WARPS * 32) {
+                gn_par[i] = p.bias[i];
+                gn_par[GN_PAR_MAX + i] = p.gamma[i];
+                gn_par[2 * GN_PAR_MAX + i] = p.beta[i];
+            }
+        }
+    }
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -569,7 +583,7 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-                Epilogue<EPI>::template run32<GW>(p, row, col, v);
+                Epilogue<EPI>::template run32<GW>(p, row, col, v, gn_par, gn_xch, q, part, lane);
             } else {
                 if (!mbar_wait(&tfull_bar[acc], acc_phase)) { ok = false; break; }
                 tc_fence_after_sync();
@@ -683,42 +697,70 @@ struct Epilogue<EPI_LINEAR> {
 
 template <>
 struct Epilogue<EPI_GN_SILU> {
-    // 32-column variant (16 epilogue warps, GW <= 32): same arithmetic as run<GW> below on one 32-column span.
+    // 16 epilogue warps: this thread owns 32 consecutive columns [col, col + 32) of one row.
+    // GroupNorm(8, N) -> group width GW = N / 8 (16 / 32 / 64). Biased variance (two-pass), eps inside the sqrt
+    // (torch.nn.GroupNorm, models/diffusion.py:202,206), then SiLU (:203,207) and the block's Dropout (:204) when drop_p > 0.
+    // GW == 64: the group spans this warp and its neighbour (part ^ 1, same quadrant, same rows); the two swap their partial
+    // sums through shared memory behind a 64-thread named barrier.
     template <int GW>
-    __device__ static __forceinline__ void run32(const GemmParams& p, int row, int col, float (&v)[32]) {
-        if (row >= p.M) return;
-        static_assert(GW <= 32, "a GroupNorm group must fit the thread's 32 columns");
-        constexpr int NG = 32 / GW;
-        add_row32(v, p.bias + col);
+    __device__ static __forceinline__ void run32(const GemmParams& p, int row, int col, float (&v)[32], const float* par, float* xch, int q, int part, int lane) {
+        const bool live = row < p.M;
+        constexpr int NG = GW >= 32 ? 1 : 32 / GW;       // groups (or the half group) inside this thread's 32 columns
+        constexpr int W = GW >= 32 ? 32 : GW;            // columns of one group held by this thread
+        const bool in_smem = p.N <= GN_PAR_MAX;
+        const float* bias = in_smem ? par + col : p.bias + col;
+        const float* gamma = in_smem ? par + GN_PAR_MAX + col : p.gamma + col;
+        const float* beta = in_smem ? par + 2 * GN_PAR_MAX + col : p.beta + col;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 b = reinterpret_cast<const float4*>(bias)[j];
+            v[4 * j + 0] += b.x;
+            v[4 * j + 1] += b.y;
+            v[4 * j + 2] += b.z;
+            v[4 * j + 3] += b.w;
+        }
         float mean[NG], rstd[NG];
+        const int me = (q * 4 + part) * 32 + lane, other = (q * 4 + (part ^ 1)) * 32 + lane;
+        const int bar_id = 1 + q * 2 + (part >> 1);
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             float s = 0.0f;
 #pragma unroll
-            for (int j = 0; j < GW; ++j) s += v[g * GW + j];
+            for (int j = 0; j < W; ++j) s += v[g * W + j];
+            if constexpr (GW == 64) {
+                xch[me] = s;
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                s += xch[other];
+            }
             const float mu = s * (1.0f / GW);
             float ss = 0.0f;
 #pragma unroll
-            for (int j = 0; j < GW; ++j) {
-                const float d = v[g * GW + j] - mu;
+            for (int j = 0; j < W; ++j) {
+                const float d = v[g * W + j] - mu;
                 ss = fmaf(d, d, ss);
+            }
+            if constexpr (GW == 64) {
+                xch[512 + me] = ss;
+                asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                ss += xch[512 + other];
             }
             mean[g] = mu;
             rstd[g] = rsqrtf(ss * (1.0f / GW) + p.gn_eps);
         }
+        if (!live) return;          // after the barriers: rows past the batch take part in the exchange but store nothing
         if (p.rstd_out) {
-            const int g0 = col / GW;
+            if (GW < 64 || (part & 1) == 0) {
+                const int g0 = col / GW;
 #pragma unroll
-            for (int g = 0; g < NG; ++g) p.rstd_out[static_cast<size_t>(row) * 8 + g0 + g] = rstd[g];
+                for (int g = 0; g < NG; ++g) p.rstd_out[static_cast<size_t>(row) * 8 + g0 + g] = rstd[g];
+            }
         }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean[j / GW]) * rstd[j / GW];
+        for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean[j / W]) * rstd[j / W];
         if (p.xhat_bf) store_row32_bf16(p.xhat_bf + static_cast<size_t>(row) * p.out_bf_ld + col, v, p.out_lo_off);
-        const float4* g4 = reinterpret_cast<const float4*>(p.gamma + col);
-        const float4* b4 = reinterpret_cast<const float4*>(p.beta + col);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+            const float4 g = reinterpret_cast<const float4*>(gamma)[j], b = reinterpret_cast<const float4*>(beta)[j];
             v[4 * j + 0] = silu_f(fmaf(v[4 * j + 0], g.x, b.x));
             v[4 * j + 1] = silu_f(fmaf(v[4 * j + 1], g.y, b.y));
             v[4 * j + 2] = silu_f(fmaf(v[4 * j + 2], g.z, b.z));
@@ -742,81 +784,6 @@ struct Epilogue<EPI_GN_SILU> {
             }
         }
         store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + col, v, p.out_lo_off);
-    }
-
-    // GroupNorm(8, N) -> group width GW = N / 8. Biased variance, eps inside the sqrt
-    // (torch.nn.GroupNorm, models/diffusion.py:202,206), then SiLU (:203,207) and the
-    // block's Dropout (:204) when drop_p > 0.
-    template <int GW>
-    __device__ static __forceinline__ void run(const GemmParams& p, int row, int col, float (&v0)[32], float (&v1)[32], double&) {
-        if (row >= p.M) return;
-        add_row32(v0, p.bias + col);
-        add_row32(v1, p.bias + col + 32);
-        float mean[64 / GW], rstd[64 / GW];
-        constexpr int NG = 64 / GW;   // groups inside this thread's 64 columns
-#pragma unroll
-        for (int g = 0; g < NG; ++g) {
-            float s = 0.0f;
-#pragma unroll
-            for (int j = 0; j < GW; ++j) {
-                const int idx = g * GW + j;
-                s += (idx < 32) ? v0[idx & 31] : v1[idx & 31];
-            }
-            const float mu = s * (1.0f / GW);
-            float ss = 0.0f;
-#pragma unroll
-            for (int j = 0; j < GW; ++j) {
-                const int idx = g * GW + j;
-                const float d = ((idx < 32) ? v0[idx & 31] : v1[idx & 31]) - mu;
-                ss = fmaf(d, d, ss);
-            }
-            mean[g] = mu;
-            rstd[g] = rsqrtf(ss * (1.0f / GW) + p.gn_eps);
-        }
-        if (p.rstd_out) {
-            const int g0 = col / GW;
-#pragma unroll
-            for (int g = 0; g < NG; ++g) p.rstd_out[static_cast<size_t>(row) * 8 + g0 + g] = rstd[g];
-        }
-        const float keep_scale = p.drop_p > 0.0f ? 1.0f / (1.0f - p.drop_p) : 1.0f;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            float(&v)[32] = h ? v1 : v0;
-            const int c0 = col + 32 * h;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const int g = (32 * h + j) / GW;
-                v[j] = (v[j] - mean[g]) * rstd[g];
-            }
-            if (p.xhat_bf) store_row32_bf16(p.xhat_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
-            const float4* g4 = reinterpret_cast<const float4*>(p.gamma + c0);
-            const float4* b4 = reinterpret_cast<const float4*>(p.beta + c0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
-                v[4 * j + 0] = silu_f(fmaf(v[4 * j + 0], g.x, b.x));
-                v[4 * j + 1] = silu_f(fmaf(v[4 * j + 1], g.y, b.y));
-                v[4 * j + 2] = silu_f(fmaf(v[4 * j + 2], g.z, b.z));
-                v[4 * j + 3] = silu_f(fmaf(v[4 * j + 3], g.w, b.w));
-            }
-            if (p.drop_p > 0.0f) {
-                if (p.drop_mask) {
-                    const uint8_t* mk = p.drop_mask + static_cast<size_t>(row) * p.N + c0;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) v[j] = mk[j] ? v[j] * keep_scale : 0.0f;
-                } else {
-#pragma unroll
-                    for (int j4 = 0; j4 < 8; ++j4) {
-                        const uint4 w = philox_words(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>((c0 >> 2) + j4), p.drop_stream, p.step ? static_cast<uint32_t>(*p.step) : 0u);
-                        v[4 * j4 + 0] = (u01(w.x) >= p.drop_p) ? v[4 * j4 + 0] * keep_scale : 0.0f;
-                        v[4 * j4 + 1] = (u01(w.y) >= p.drop_p) ? v[4 * j4 + 1] * keep_scale : 0.0f;
-                        v[4 * j4 + 2] = (u01(w.z) >= p.drop_p) ? v[4 * j4 + 2] * keep_scale : 0.0f;
-                        v[4 * j4 + 3] = (u01(w.w) >= p.drop_p) ? v[4 * j4 + 3] * keep_scale : 0.0f;
-                    }
-                }
-            }
-            store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + c0, v, p.out_lo_off);
-        }
     }
 };
 

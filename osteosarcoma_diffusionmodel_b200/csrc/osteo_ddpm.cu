@@ -186,6 +186,7 @@ struct osteo_ddpm_ctx {
     // fused bf16 step (fused_step.cuh): output_proj + reverse update + the NEXT step's input_proj in one kernel
     CUtensorMap wout_tmap64, win_tmap;   // W_out as [64 x 64] boxes, W_in as [h0 x 64] boxes
     int fused_enable = 1;
+    DevBuf fused_trace;
     bool x_c8 = false;                   // layout the state was loaded in: c8 (fused path) or 32-column boxes (TMA-staged path)
     bool shadow_valid = false;           // xb == bf16(x)? (the fused step does not maintain the shadow)
     bool h0_primed = false;              // acts[0] holds input_proj(x) + embeddings for timestep h0_t over rows [0, h0_n)
@@ -392,7 +393,8 @@ static int launch_fused(osteo_ddpm_ctx* c, long long row0, long long row1, const
                         cudaStream_t s) {
     static bool configured = false;
     if (!configured) {
-        OSTEO_CUDA(cudaFuncSetAttribute(ddpm_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+        OSTEO_CUDA(cudaFuncSetAttribute(ddpm_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+        OSTEO_CUDA(cudaFuncSetAttribute(ddpm_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
         configured = true;
     }
     FusedParams p;
@@ -428,9 +430,30 @@ static int launch_fused(osteo_ddpm_ctx* c, long long row0, long long row1, const
     p.h0_ld = 2 * c->h0();
     if (const char* e = getenv("OSTEO_DDPM_DBG")) p.dbg = atoi(e);
     if (p.m_tiles <= 0) return 0;
+    const bool want_trace = getenv("OSTEO_DDPM_TRACE") != nullptr;      // diagnostics: synchronises, prints CTA 0's event timeline
+    if (want_trace) {
+        if (!c->fused_trace.p) OSTEO_TRY(c->fused_trace.alloc(3 * 32 * 8 * sizeof(long long)));
+        OSTEO_CUDA(cudaMemsetAsync(c->fused_trace.p, 0, c->fused_trace.bytes, s));
+        p.trace = c->fused_trace.as<long long>();
+    }
     const int grid = p.m_tiles < c->sms ? p.m_tiles : c->sms;
-    ddpm_fused_kernel<<<grid, F_THREADS, F_SMEM_BYTES, s>>>(p);
+    if (eps_out) ddpm_fused_kernel<true><<<grid, F_THREADS, F_SMEM_BYTES, s>>>(p);
+    else ddpm_fused_kernel<false><<<grid, F_THREADS, F_SMEM_BYTES, s>>>(p);
     OSTEO_CUDA(cudaGetLastError());
+    if (want_trace) {
+        static long long h[3 * 32 * 8];
+        OSTEO_CUDA(cudaMemcpyAsync(h, c->fused_trace.p, sizeof h, cudaMemcpyDeviceToHost, s));
+        OSTEO_CUDA(cudaStreamSynchronize(s));
+        long long t0 = h[(2 * 32 + 0) * 8 + 0];
+        for (int tile = 0; tile < 24; ++tile) {
+            fprintf(stderr, "[trace] tile %2d | MMA eps_rdy %6lld eps_iss %6lld in_rdy %6lld in_iss %6lld | NOISE start %6lld vals %6lld tempty %6lld pub %6lld | "
+                            "UPD start %6lld tfull %6lld tmem %6lld xbfe %6lld prefence %6lld pub %6lld\n", tile,
+                    h[(0 * 32 + tile) * 8 + 0] - t0, h[(0 * 32 + tile) * 8 + 1] - t0, h[(0 * 32 + tile) * 8 + 2] - t0, h[(0 * 32 + tile) * 8 + 3] - t0,
+                    h[(1 * 32 + tile) * 8 + 0] - t0, h[(1 * 32 + tile) * 8 + 1] - t0, h[(1 * 32 + tile) * 8 + 2] - t0, h[(1 * 32 + tile) * 8 + 3] - t0,
+                    h[(2 * 32 + tile) * 8 + 0] - t0, h[(2 * 32 + tile) * 8 + 1] - t0, h[(2 * 32 + tile) * 8 + 2] - t0, h[(2 * 32 + tile) * 8 + 3] - t0,
+                    h[(2 * 32 + tile) * 8 + 4] - t0, h[(2 * 32 + tile) * 8 + 5] - t0);
+        }
+    }
     return after_launch(c, 0, s);
 }
 

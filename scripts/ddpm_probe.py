@@ -15,6 +15,8 @@ model = model.to("cuda").eval()
 cond = synth.scenario_conditions(rows, 3).cuda()
 model.sample(cond, rows, seed=1, t_stop=998)
 lib = _lib.load()
+if os.environ.get("PROBE_TRACE"):
+    os.environ["OSTEO_DDPM_TRACE"] = "1"      # event timeline of CTA 0 on stderr (not legal under graph capture: set after the warm-up)
 fused = bool(lib.osteo_ddpm_step_is_fused(model._ctx))
 per_chunk = 11 if fused else 12
 buf = (C.c_float * 4096)()
