@@ -26,6 +26,10 @@ NVCC_FLAGS = [
 ]
 
 
+# extra nvcc flags for diagnostics builds, e.g. OSTEO_NVCC_EXTRA="-DOSTEO_FUSED_TRACE"
+NVCC_FLAGS += os.environ.get("OSTEO_NVCC_EXTRA", "").split()
+
+
 def _sources():
     files = sorted(CSRC.glob("*.cu")) + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.inl"))
     files.append(HERE.parent / "include" / "osteo_ddpm.h")

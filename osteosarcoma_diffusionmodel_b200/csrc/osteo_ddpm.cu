@@ -199,7 +199,7 @@ struct osteo_ddpm_ctx {
     TrainWorkspace train;
 
     // graph cache for sample_loop
-    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphExec_t graph_exec = nullptr, graph_exec_multi = nullptr;   // 1 step / GRAPH_UNROLL steps
     long long graph_n = -1;
     unsigned long long graph_seed = 0;
     long long graph_row_base = 0;
@@ -217,6 +217,7 @@ struct osteo_ddpm_ctx {
     __nv_bfloat16* xb_ptr() const { return xb.as<__nv_bfloat16>(); }
     ~osteo_ddpm_ctx() {
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
+        if (graph_exec_multi) cudaGraphExecDestroy(graph_exec_multi);
     }
 };
 
@@ -507,6 +508,35 @@ static void after_steps(osteo_ddpm_ctx* c, int t, int steps) {
     c->h0_t = t - steps;
 }
 
+constexpr int GRAPH_UNROLL = 10;
+
+// Capture `count` consecutive reverse steps (each followed by the decrement of the device step word) into an executable graph.
+static int capture_steps(osteo_ddpm_ctx* c, long long n, unsigned long long seed, long long row_base, int count, cudaGraphExec_t* out) {
+    cudaStream_t cs;
+    OSTEO_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    OSTEO_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (int i = 0; i < count && rc == 0; ++i) {
+        rc = enqueue_reverse_step(c, n, nullptr, nullptr, seed, row_base, cs);
+        if (rc == 0) {
+            add_int_kernel<<<1, 1, 0, cs>>>(c->step_dev.as<int>(), -1);
+            ++c->launches;
+        }
+    }
+    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
+    cudaStreamDestroy(cs);
+    if (rc != 0) {
+        if (graph) cudaGraphDestroy(graph);
+        return rc;
+    }
+    if (ce != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(ce));
+    ce = cudaGraphInstantiate(out, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
+    return 0;
+}
+
 static int require_ready(const osteo_ddpm_ctx* c, long long n) {
     if (!c->have_weights) return fail("weights not set (osteo_ddpm_set_weights)");
     if (!c->have_schedule) return fail("schedule not set (osteo_ddpm_set_schedule)");
@@ -689,6 +719,8 @@ int osteo_ddpm_reserve(osteo_ddpm_ctx* c, long long rows) {
     if (c->graph_exec) {
         cudaGraphExecDestroy(c->graph_exec);
         c->graph_exec = nullptr;
+        if (c->graph_exec_multi) cudaGraphExecDestroy(c->graph_exec_multi);
+        c->graph_exec_multi = nullptr;
         c->graph_n = -1;
     }
     const long long cap = round_up(rows, BM);
@@ -881,34 +913,20 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
         after_steps(c, t_start, steps);
         return 0;
     }
-    // One step captured once, replayed `steps` times; the device-resident step word is the only thing that changes.
+    // One step (and a block of GRAPH_UNROLL steps) captured once and replayed; the device-resident step word is the only thing that
+    // changes between replays. The unrolled graph amortises the per-graph-launch gap over GRAPH_UNROLL steps.
     const bool reuse = c->graph_exec && c->graph_n == n && c->graph_seed == seed && c->graph_row_base == row_base &&
                        c->graph_precision == c->precision && c->graph_chunk == c->chunk_rows && c->graph_fused == (c->x_c8 ? 1 : 0);
-    const long long before = c->launches;
     if (!reuse) {
-        if (c->graph_exec) {
-            cudaGraphExecDestroy(c->graph_exec);
-            c->graph_exec = nullptr;
+        for (cudaGraphExec_t* g : {&c->graph_exec, &c->graph_exec_multi}) {
+            if (*g) cudaGraphExecDestroy(*g);
+            *g = nullptr;
         }
-        cudaStream_t cs;
-        OSTEO_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-        cudaGraph_t graph = nullptr;
-        OSTEO_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_reverse_step(c, n, nullptr, nullptr, seed, row_base, cs);
-        if (rc == 0) {
-            add_int_kernel<<<1, 1, 0, cs>>>(c->step_dev.as<int>(), -1);
-            ++c->launches;
-        }
-        cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-        cudaStreamDestroy(cs);
-        if (rc != 0) {
-            if (graph) cudaGraphDestroy(graph);
-            return rc;
-        }
-        if (ce != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(ce));
-        ce = cudaGraphInstantiate(&c->graph_exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
+        const long long before = c->launches;
+        OSTEO_TRY(capture_steps(c, n, seed, row_base, 1, &c->graph_exec));
+        c->graph_launches_per_step = c->launches - before;
+        OSTEO_TRY(capture_steps(c, n, seed, row_base, GRAPH_UNROLL, &c->graph_exec_multi));
+        c->launches = before;   // capture enqueued nothing; the replays below are what runs
         c->graph_n = n;
         c->graph_seed = seed;
         c->graph_row_base = row_base;
@@ -916,11 +934,9 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
         c->graph_chunk = c->chunk_rows;
         c->graph_fused = c->x_c8 ? 1 : 0;
     }
-    if (!reuse) {
-        c->graph_launches_per_step = c->launches - before;
-        c->launches = before;   // capture enqueued nothing; the replays below are what runs
-    }
-    for (int i = 0; i < steps; ++i) OSTEO_CUDA(cudaGraphLaunch(c->graph_exec, s));
+    int left = steps;
+    for (; left >= GRAPH_UNROLL; left -= GRAPH_UNROLL) OSTEO_CUDA(cudaGraphLaunch(c->graph_exec_multi, s));
+    for (; left > 0; --left) OSTEO_CUDA(cudaGraphLaunch(c->graph_exec, s));
     c->launches += c->graph_launches_per_step * steps;
     after_steps(c, t_start, steps);
     return 0;
