@@ -203,6 +203,14 @@ __device__ __forceinline__ void add_row32(float (&v)[32], const float* __restric
 }
 
 __device__ __forceinline__ float silu_f(float y) { return __fdividef(y, 1.0f + __expf(-y)); }
+// SiLU through one MUFU instead of two: y sigmoid(y) = h + h tanh(h), h = y / 2. tanh.approx is good to ~5e-4 absolute, far below the
+// 2^-9 relative rounding of the bf16 value the result is stored as: used only when the output is plain bf16 (no [hi|lo] residual).
+__device__ __forceinline__ float silu_fast(float y) {
+    const float h = 0.5f * y;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+    return fmaf(h, t, h);
+}
 
 // One epilogue pass over 32 columns [col, col+32) of row `row` held in v[].
 // GW = GroupNorm group width (16 / 32 / 64); a 64-wide group is handled by the caller
@@ -252,7 +260,11 @@ struct TileSeq {
     }
     __device__ bool next(TileInfo& ti, bool& first, bool& last) {
         if (!ares) {
-            tile += gridDim.x;
+            // the grid size is re-read from the special register every tile: kept in a register it was the value ptxas chose to spill,
+            // and a local-memory reload per tile is an L2 round trip here (the L1 is carved out as shared memory)
+            uint32_t nctas;
+            asm volatile("mov.u32 %0, %%nctaid.x;" : "=r"(nctas));
+            tile += static_cast<int>(nctas);
             if (tile >= num_tiles) return false;
             ti = decode_tile<EPI, MN>(p, tile);
             first = last = true;
@@ -299,7 +311,12 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
     float* gn_par = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 256);      // EPI_GN_SILU: [bias | gamma | beta], GN_PAR_MAX each
     float* gn_xch = gn_par + 3 * GN_PAR_MAX;
 
-    const int warp = threadIdx.x >> 5;
+    // Physical warp ids: epilogue warps first (0 .. NUM_EPI_WARPS-1), the four role warps LAST: the scheduler arbiter favours high warp
+    // ids, and a TMA producer / MMA issuer starved by four busy epilogue warps on its scheduler stalls the whole pipeline.
+    // `warp` is the logical id the code below uses (0 producer, 1 MMA, 2 TMEM allocator, 3 idle, 4.. epilogue); the TMEM lane quadrant
+    // of an epilogue warp is physical id % 4 == logical id % 4.
+    const int warp_phys = threadIdx.x >> 5;
+    const int warp = warp_phys < NUM_EPI_WARPS ? warp_phys + 4 : warp_phys - NUM_EPI_WARPS;
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -334,7 +351,7 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
         // The layer's bias / gamma / beta (N <= 512) live in shared memory for the whole kernel: the L1 is carved out as shared memory,
         // so per-tile __ldg loads of them were L2 round trips on the epilogue's critical path.
         if (warp >= 4 && p.N <= GN_PAR_MAX) {
-            for (int i = threadIdx.x - 128; i < p.N; i += NUM_EPI_WARPS * 32) {
+            for (int i = threadIdx.x; i < p.N; i += NUM_EPI_WARPS * 32) {
                 gn_par[i] = p.bias[i];
                 gn_par[GN_PAR_MAX + i] = p.gamma[i];
                 gn_par[2 * GN_PAR_MAX + i] = p.beta[i];
@@ -758,13 +775,24 @@ struct Epilogue<EPI_GN_SILU> {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = (v[j] - mean[j / W]) * rstd[j / W];
         if (p.xhat_bf) store_row32_bf16(p.xhat_bf + static_cast<size_t>(row) * p.out_bf_ld + col, v, p.out_lo_off);
+        if (p.out_lo_off == 0) {          // bf16 throughput mode (warp-uniform)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 g = reinterpret_cast<const float4*>(gamma)[j], b = reinterpret_cast<const float4*>(beta)[j];
-            v[4 * j + 0] = silu_f(fmaf(v[4 * j + 0], g.x, b.x));
-            v[4 * j + 1] = silu_f(fmaf(v[4 * j + 1], g.y, b.y));
-            v[4 * j + 2] = silu_f(fmaf(v[4 * j + 2], g.z, b.z));
-            v[4 * j + 3] = silu_f(fmaf(v[4 * j + 3], g.w, b.w));
+            for (int j = 0; j < 8; ++j) {
+                const float4 g = reinterpret_cast<const float4*>(gamma)[j], b = reinterpret_cast<const float4*>(beta)[j];
+                v[4 * j + 0] = silu_fast(fmaf(v[4 * j + 0], g.x, b.x));
+                v[4 * j + 1] = silu_fast(fmaf(v[4 * j + 1], g.y, b.y));
+                v[4 * j + 2] = silu_fast(fmaf(v[4 * j + 2], g.z, b.z));
+                v[4 * j + 3] = silu_fast(fmaf(v[4 * j + 3], g.w, b.w));
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 g = reinterpret_cast<const float4*>(gamma)[j], b = reinterpret_cast<const float4*>(beta)[j];
+                v[4 * j + 0] = silu_f(fmaf(v[4 * j + 0], g.x, b.x));
+                v[4 * j + 1] = silu_f(fmaf(v[4 * j + 1], g.y, b.y));
+                v[4 * j + 2] = silu_f(fmaf(v[4 * j + 2], g.z, b.z));
+                v[4 * j + 3] = silu_f(fmaf(v[4 * j + 3], g.w, b.w));
+            }
         }
         if (p.drop_p > 0.0f) {
             const float keep_scale = 1.0f / (1.0f - p.drop_p);
