@@ -1,0 +1,201 @@
+// Weight-stationary variant of the Linear + GroupNorm + SiLU GEMM (models/diffusion.py:198-208) for the bf16 throughput mode.
+//
+// The generic kernel (gemm_tc.cuh) streams a 128 x 64 A tile AND a 128 x 64 W tile per k-block for every 128 x 128 output tile:
+// 64 FLOP per byte of L2 -> shared-memory traffic. At 100k rows the 512-wide layers then move ~800 MB per launch through the L2 at
+// 10-12 TB/s, which is the L2's limit (ncu: DRAM 20-40 %, tensor pipe 21-38 %, nothing else saturated): they are L2-bandwidth bound.
+// Here a CTA owns ONE 128-column slice of the layer for the whole launch and keeps that slice of W (128 x K bf16, K <= 512: <= 128 KB)
+// resident in shared memory; only the A tiles of the row blocks it walks are streamed. That halves the L2 traffic and leaves the whole
+// TMA ring (5 to 9 stages of 16 KB) to A.
+//
+// Roles and epilogue are those of gemm_tc_kernel<EPI_GN_SILU, GW> (16 epilogue warps + TMA producer, MMA issuer, TMEM allocator; the
+// role warps have the highest warp ids). Launch parameters are the same GemmParams.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace osteo {
+
+constexpr int WS_MAX_KB = 8;                            // resident W slice: at most 8 k-blocks of [128 x 64] bf16 = 128 KB
+constexpr int WS_RING_PLUS_RES = 13;                    // 16 KB slots shared by the resident slice and the A ring (208 KB)
+constexpr int WS_MAX_STAGES = 12;
+constexpr int WS_THREADS = 128 + 32 * 16;
+constexpr int WS_SMEM_BYTES = WS_RING_PLUS_RES * A_TILE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + GN_PAR_BYTES + GN_XCH_BYTES;
+
+template <int GW>
+__global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __grid_constant__ GemmParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    int total_kb = 0;
+    for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
+    const int stages = WS_RING_PLUS_RES - total_kb;     // 5 (K = 512) .. 9 (K = 256)
+    uint8_t* s_w = smem;                                // resident W slice, k-block major
+    uint8_t* s_a = smem + total_kb * B_TILE_BYTES;      // A ring
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WS_RING_PLUS_RES * A_TILE_BYTES);
+    uint64_t* empty_bar = full_bar + WS_MAX_STAGES;
+    uint64_t* tfull_bar = empty_bar + WS_MAX_STAGES;
+    uint64_t* tempty_bar = tfull_bar + NUM_ACC;
+    uint64_t* wres_bar = tempty_bar + NUM_ACC;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wres_bar + 1);
+    float* gn_par = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 512);
+    float* gn_xch = gn_par + 3 * GN_PAR_MAX;
+
+    constexpr int NUM_EPI_WARPS = 16;
+    const int warp_phys = threadIdx.x >> 5;
+    const int warp = warp_phys < NUM_EPI_WARPS ? warp_phys + 4 : warp_phys - NUM_EPI_WARPS;      // logical: 0 producer, 1 MMA, 2 alloc, 4.. epilogue
+    const int lane = threadIdx.x & 31;
+
+    // this CTA's column slice and its row blocks m = m_first, m_first + m_step, ...
+    const int n_blk = static_cast<int>(blockIdx.x) % p.n_tiles;
+    const int m_first = static_cast<int>(blockIdx.x) / p.n_tiles;
+    const int m_step = static_cast<int>(gridDim.x) / p.n_tiles;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tma_a[0]);
+        tma_prefetch_desc(&p.tma_a[1]);
+        tma_prefetch_desc(&p.tma_b[0]);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < stages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < NUM_ACC; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], NUM_EPI_WARPS);
+        }
+        mbar_init(wres_bar, 1);
+        fence_mbar_init();
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 512);
+    if (warp >= 4 && p.N <= GN_PAR_MAX) {
+        for (int i = threadIdx.x; i < p.N; i += NUM_EPI_WARPS * 32) {
+            gn_par[i] = p.bias[i];
+            gn_par[GN_PAR_MAX + i] = p.gamma[i];
+            gn_par[2 * GN_PAR_MAX + i] = p.beta[i];
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            bool ok = true;
+            mbar_arrive_expect_tx(wres_bar, total_kb * B_TILE_BYTES);
+            int idx = 0;
+            for (int s = 0; s < p.nseg; ++s) {
+                const KSeg sg = p.seg[s];
+                for (int kb = 0; kb < sg.nkb; ++kb, ++idx)
+                    tma_load_2d(&p.tma_b[sg.b_sel], s_w + idx * B_TILE_BYTES, wres_bar, sg.b_col + kb * BK, sg.b_row0 + n_blk * BN);
+            }
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int m = m_first; ok && m < p.m_tiles; m += m_step) {
+                const int m_blk = p.m_tile0 + m;
+                for (int s = 0; s < p.nseg && ok; ++s) {
+                    const KSeg sg = p.seg[s];
+                    const CUtensorMap* ta = &p.tma_a[sg.a_sel];
+                    for (int kb = 0; kb < sg.nkb; ++kb) {
+                        if (!mbar_wait_relaxed(&empty_bar[stage], phase ^ 1u)) { ok = false; break; }
+                        mbar_arrive_expect_tx(&full_bar[stage], A_TILE_BYTES);
+                        tma_load_2d(ta, s_a + stage * A_TILE_BYTES, &full_bar[stage], sg.a_col + kb * BK, m_blk * BM);
+                        if (++stage == stages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+            if (!ok) atomicExch(p.status, ERR_PRODUCER_TIMEOUT);
+        }
+    } else if (warp == 1) {
+        // -------------------------------------------------------------- MMA issuer (whole warp, one elected lane issues)
+        constexpr uint32_t idesc = make_idesc_bf16(BM, BN, 0, 0);
+        const bool leader = elect_one();
+        const uint64_t wdesc0 = make_kmajor_sw128_desc(smem_u32(s_w));
+        const uint64_t adesc0 = make_kmajor_sw128_desc(smem_u32(s_a));
+        bool ok = mbar_wait_relaxed(wres_bar, 0);
+        tc_fence_after_sync();
+        int stage = 0, it = 0;
+        uint32_t phase = 0;
+        for (int m = m_first; ok && m < p.m_tiles; m += m_step, ++it) {
+            const int acc = it % NUM_ACC;
+            if (!mbar_wait_relaxed(&tempty_bar[acc], (static_cast<uint32_t>(it / NUM_ACC) & 1u) ^ 1u)) { ok = false; break; }
+            tc_fence_after_sync();
+            const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
+            for (int idx = 0; idx < total_kb; ++idx) {
+                if (!mbar_wait_relaxed(&full_bar[stage], phase)) { ok = false; break; }
+                tc_fence_after_sync();
+                if (leader) {
+                    const uint64_t adesc = adesc0 + static_cast<uint64_t>((stage * A_TILE_BYTES) >> 4);
+                    const uint64_t bdesc = wdesc0 + static_cast<uint64_t>((idx * B_TILE_BYTES) >> 4);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (idx | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty_bar[stage]);
+                }
+                __syncwarp();
+                if (++stage == stages) { stage = 0; phase ^= 1u; }
+            }
+            if (ok && leader) umma_commit(&tfull_bar[acc]);
+            __syncwarp();
+        }
+        if (!ok && leader) atomicExch(p.status, ERR_MMA_TIMEOUT);
+    } else if (warp >= 4) {
+        // ---------------------------------------------------------------- epilogue (the generic kernel's 32-column GroupNorm epilogue)
+        const int q = warp_phys & 3;
+        const int part = warp_phys >> 2;
+        bool ok = true;
+        int it = 0;
+        for (int m = m_first; ok && m < p.m_tiles; m += m_step, ++it) {
+            const int acc = it % NUM_ACC;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + part * 32);
+            const int row = (p.m_tile0 + m) * BM + q * 32 + lane;
+            const int col = n_blk * BN + part * 32;
+            if (!mbar_wait(&tfull_bar[acc], static_cast<uint32_t>(it / NUM_ACC) & 1u)) { ok = false; break; }
+            tc_fence_after_sync();
+            float v[32];
+            tmem_ld_32(taddr, v);
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            Epilogue<EPI_GN_SILU>::template run32<GW>(p, row, col, v, gn_par, gn_xch, q, part, lane);
+        }
+        if (!ok && lane == 0) atomicExch(p.status, ERR_EPI_TIMEOUT);
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// Eligible: bf16 mode (no hi/lo passes), at most WS_MAX_KB k-blocks in total, the un-blocked A layout, enough row blocks to fill the grid.
+inline bool gemm_ws_eligible(const GemmParams& p) {
+    int total_kb = 0;
+    for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
+    return total_kb > 0 && total_kb <= WS_MAX_KB && p.a_blocked_nbox == 0 && p.out_lo_off == 0 && p.n_tiles >= 1 && p.n_tiles <= 8;
+}
+
+template <int GW>
+int launch_gemm_ws_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        OSTEO_CUDA(cudaFuncSetAttribute(gemm_ws_gn_silu_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
+        configured = true;
+    }
+    if (p.m_tiles <= 0) return 0;
+    int per_slice = num_sms / p.n_tiles;                // CTAs per column slice
+    if (per_slice > p.m_tiles) per_slice = p.m_tiles;
+    if (per_slice < 1) return -2;
+    gemm_ws_gn_silu_kernel<GW><<<per_slice * p.n_tiles, WS_THREADS, WS_SMEM_BYTES, stream>>>(p);
+    OSTEO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+inline int launch_gemm_ws(int gw, const GemmParams& p, int num_sms, cudaStream_t stream) {
+    switch (gw) {
+        case 16: return launch_gemm_ws_inst<16>(p, num_sms, stream);
+        case 32: return launch_gemm_ws_inst<32>(p, num_sms, stream);
+        case 64: return launch_gemm_ws_inst<64>(p, num_sms, stream);
+        default: return -2;
+    }
+}
+
+}  // namespace osteo

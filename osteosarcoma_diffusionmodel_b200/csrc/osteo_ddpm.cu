@@ -10,6 +10,7 @@
 #include "elem_kernels.cuh"
 #include "fused_step.cuh"
 #include "gemm_host.cuh"
+#include "gemm_ws.cuh"
 #include "train_kernels.cuh"
 #include "validators.cuh"
 
@@ -186,6 +187,7 @@ struct osteo_ddpm_ctx {
     // fused bf16 step (fused_step.cuh): output_proj + reverse update + the NEXT step's input_proj in one kernel
     CUtensorMap wout_tmap64, win_tmap;   // W_out as [64 x 64] boxes, W_in as [h0 x 64] boxes
     int fused_enable = 1;
+    int ws_enable = getenv("OSTEO_DDPM_NO_WS") ? 0 : 1;
     DevBuf fused_trace;
     bool x_c8 = false;                   // layout the state was loaded in: c8 (fused path) or 32-column boxes (TMA-staged path)
     bool shadow_valid = false;           // xb == bf16(x)? (the fused step does not maintain the shadow)
@@ -333,6 +335,11 @@ static int launch_half(osteo_ddpm_ctx* c, int hi, long long row0, long long row1
     if (o.save) {
         p.xhat_bf = c->train.xhat[hi]->as<__nv_bfloat16>();
         p.rstd_out = c->train.rstd[hi]->as<float>();
+    }
+    // bf16 mode, K <= 512: weight-stationary kernel (the column slice of W stays in shared memory, only A streams: half the L2 traffic)
+    if (c->ws_enable && gemm_ws_eligible(p)) {
+        const int rc = launch_gemm_ws(hb.gw, p, c->sms, s);
+        if (rc != -2) return after_launch(c, rc, s);
     }
     return after_launch(c, launch_gemm(EPI_GN_SILU, hb.gw, p, c->sms, s), s);
 }

@@ -50,8 +50,12 @@ def report(path, out, traffic):
             tr.setdefault(r[idx["Kernel Name"]], []).append(val("dram__bytes_read.sum") + val("dram__bytes_write.sum"))
     print(open(out).read())
     if traffic:
-        names = {"gemm_tc_kernel<2,": "output_proj+reverse_update", "gemm_tc_kernel<0,": "input_proj+emb_add"}
-        outj = {}
+        names = {"gemm_tc_kernel<2,": "output_proj+reverse_update", "gemm_tc_kernel<0,": "input_proj+emb_add",
+                 "ddpm_fused_kernel": "output_proj+reverse_update+next_input_proj"}
+        try:
+            outj = json.load(open(traffic))      # keep the entries of kernels this report does not contain
+        except Exception:
+            outj = {}
         for k, v in tr.items():
             for pat, nice in names.items():
                 if pat in k:
