@@ -96,3 +96,43 @@ def test_fused_continues_across_sample_loop_calls():
     _lib.check(lib.osteo_ddpm_store_state(model._ctx, out.data_ptr(), rows, s))
     assert torch.equal(out, full)
     model.check_status()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("rows,t", [(300, 500), (129, 1), (64, 999)])
+def test_in_kernel_noise_is_the_oracle_philox_stream(fused, rows, t):
+    """With every weight zero the denoiser predicts eps = 0, so one reverse step is x <- c_x x + sigma z: z can be read back and must be
+    the Philox4x32-10 + Box-Muller normals of the numpy oracle for (seed, global row, column, t) - in both step kernels, with a row
+    offset (sharding) and a ragged last row block. Also checks the moments of the extracted noise."""
+    import numpy as np
+    from oracle import philox_oracle as P
+    from osteosarcoma_diffusionmodel_b200.diffusion import BiologyAwareDiffusionModel
+
+    case = load_case("config")
+    model = build_model(case, "bf16")
+    with torch.no_grad():
+        for p_ in model.parameters():
+            p_.zero_()
+    model.set_fused(fused)
+    D = case["D"]
+    seed, row_base = 0x1234_5678_9ABC, 1_000_003
+    cond = synth.scenario_conditions(rows, 3)
+    x = synth.noise_stream(5)(1, (rows, D))
+    from osteosarcoma_diffusionmodel_b200 import _lib
+    lib, s = _lib.load(), _lib.stream_handle()
+    xd = x.cuda().contiguous()
+    cd = cond.cuda().contiguous()
+    model._ensure_ctx(rows)
+    _lib.check(lib.osteo_ddpm_set_conditions(model._ctx, cd.data_ptr(), rows, s))
+    _lib.check(lib.osteo_ddpm_load_state(model._ctx, xd.data_ptr(), rows, s))
+    _lib.check(lib.osteo_ddpm_reverse_step(model._ctx, rows, t, None, None, seed, row_base, s))
+    out = torch.empty_like(xd)
+    _lib.check(lib.osteo_ddpm_store_state(model._ctx, out.data_ptr(), rows, s))
+    model.check_status()
+    cx, ce, sg = BiologyAwareDiffusionModel.reverse_coefficients(model.betas, model.alphas_cumprod)
+    z = (out.cpu().double().numpy() - np.float32(cx[t]).astype(np.float64) * x.double().numpy()) / np.float32(sg[t]).astype(np.float64)
+    ref = P.normals(seed, np.arange(row_base, row_base + rows, dtype=np.uint64), D, 0, t)      # stream 0 = STREAM_REVERSE
+    # fp32 arithmetic of the update on |x| ~ c_x: absolute error ~ 1e-6 * c_x / sigma
+    tol = 4e-6 * (1.0 + abs(cx[t])) / sg[t] + 5e-5      # + the MUFU lg2 / sqrt / sin / cos approximations (~1e-6 relative, |z| <= 5.7)
+    assert np.abs(z - ref).max() < tol, (np.abs(z - ref).max(), tol)
+    assert abs(z.mean()) < 4.0 / np.sqrt(z.size) and abs(z.var() - 1.0) < 6.0 / np.sqrt(z.size)
