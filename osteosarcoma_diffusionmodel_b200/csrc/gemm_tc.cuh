@@ -739,6 +739,50 @@ struct Epilogue<EPI_GN_SILU> {
         float mean[NG], rstd[NG];
         const int me = (q * 4 + part) * 32 + lane, other = (q * 4 + (part ^ 1)) * 32 + lane;
         const int bar_id = 1 + q * 2 + (part >> 1);
+        if (p.out_lo_off == 0 && !p.xhat_bf && !p.rstd_out && p.drop_p == 0.0f) {
+            // bf16 inference fast path (warp-uniform): one-pass moments (sum and sum of squares in one sweep, one exchange for a 64-wide
+            // group) and normalise + affine + the 0.5 of the tanh form of SiLU folded into one FFMA per element:
+            //   h = v * (0.5 gamma rstd) + (0.5 beta - mean * 0.5 gamma rstd),   silu = h + h tanh(h).
+            // 10 instructions per element instead of 13; the results go to bf16 (2^-9 relative), far above the ~1e-6 the one-pass
+            // variance and the folded constants can move them.
+#pragma unroll
+            for (int g = 0; g < NG; ++g) {
+                float s = 0.0f, ss = 0.0f;
+#pragma unroll
+                for (int j = 0; j < W; ++j) {
+                    s += v[g * W + j];
+                    ss = fmaf(v[g * W + j], v[g * W + j], ss);
+                }
+                if constexpr (GW == 64) {
+                    xch[me] = s;
+                    xch[512 + me] = ss;
+                    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+                    s += xch[other];
+                    ss += xch[512 + other];
+                    asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // the partner has read before the next tile overwrites
+                }
+                const float mu = s * (1.0f / GW);
+                mean[g] = mu;
+                rstd[g] = 0.5f * rsqrtf(fmaxf(fmaf(-mu, mu, ss * (1.0f / GW)), 0.0f) + p.gn_eps);      // 0.5 / sigma
+            }
+            if (!live) return;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float4 g = reinterpret_cast<const float4*>(gamma)[j], b = reinterpret_cast<const float4*>(beta)[j];
+                const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 4 * j + e;
+                    const float a = gg[e] * rstd[i / W];
+                    const float h = fmaf(v[i], a, fmaf(-mean[i / W], a, 0.5f * bb[e]));
+                    float t;
+                    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+                    v[i] = fmaf(h, t, h);
+                }
+            }
+            store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + col, v, 0);
+            return;
+        }
 #pragma unroll
         for (int g = 0; g < NG; ++g) {
             float s = 0.0f;
