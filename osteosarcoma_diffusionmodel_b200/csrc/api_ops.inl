@@ -166,34 +166,42 @@ int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long 
     pack_center_norm_kernel<<<sms * 8, 256, 0, s>>>(x_dev, n, d, center_dev, xb.as<__nv_bfloat16>(), np, kp, lo, nx.as<float>());
     pack_center_norm_kernel<<<sms * 8, 256, 0, s>>>(y_dev, m, d, center_dev, yb.as<__nv_bfloat16>(), mp, kp, lo, ny.as<float>());
     OSTEO_CUDA(cudaGetLastError());
-    CUtensorMap tx, ty;
+    // A-side maps (128-row boxes) and B-side maps (256-row boxes) of the same two packed operands: gemm_rbf.cuh, 128 x 256 tiles
+    CUtensorMap tx, ty, txb, tyb;
     OSTEO_TRY(make_tmap_bf16(&tx, xb.p, np, 2 * kp, 2 * kp, BM));
     OSTEO_TRY(make_tmap_bf16(&ty, yb.p, mp, 2 * kp, 2 * kp, BM));
+    OSTEO_TRY(make_tmap_bf16(&txb, xb.p, np, 2 * kp, 2 * kp, RB_BN));
+    OSTEO_TRY(make_tmap_bf16(&tyb, yb.p, mp, 2 * kp, 2 * kp, RB_BN));
     auto gram = [&](const CUtensorMap& ta, const CUtensorMap& tb, const float* na, const float* nb, long long rb, long long re, long long cols, bool symmetric,
                     double* acc) -> int {
         if (re <= rb) return 0;
-        GemmParams p;
+        RbfParams p;
         std::memset(&p, 0, sizeof p);
-        p.tma_a[0] = p.tma_a[1] = ta;
-        p.tma_b[0] = p.tma_b[1] = tb;
-        OSTEO_TRY(add_segments(p, 0, 0, kp, 0, kp, kp, x3));
+        p.tma_a = ta;
+        p.tma_b = tb;
+        const int nkb = kp / BK;
+        p.seg[p.nseg++] = KSeg{0, 0, 0, nkb, 0, 0};                 // hi . hi
+        if (x3) {
+            p.seg[p.nseg++] = KSeg{0, 0, kp, nkb, 0, 0};            // hi . lo
+            p.seg[p.nseg++] = KSeg{0, kp, 0, nkb, 0, 0};            // lo . hi
+        }
         p.M = static_cast<int>(re);
         p.N = static_cast<int>(cols);
         p.m_tile0 = static_cast<int>(rb / BM);
         p.m_tiles = static_cast<int>((re - rb + BM - 1) / BM);
-        p.n_tiles = static_cast<int>((cols + BN - 1) / BN);
+        p.n_tiles = static_cast<int>((cols + RB_BN - 1) / RB_BN);
         p.status = status.as<int>();
         p.norm_a = na;
         p.norm_b = nb;
-        p.rbf_gamma = gamma;
-        p.rbf_symmetric = symmetric ? 1 : 0;
-        p.rbf_acc = acc;
-        return launch_gemm(EPI_RBF, 64, p, sms, s);
+        p.gamma = gamma;
+        p.symmetric = symmetric ? 1 : 0;
+        p.acc = acc;
+        return launch_rbf_gram(p, sms, s);
     };
     // K(X,X) rows [row_begin,row_end): the symmetric half-Gram is only valid when this call owns every row
-    OSTEO_TRY(gram(tx, tx, nx.as<float>(), nx.as<float>(), row_begin, row_end, n, row_begin == 0 && row_end == n, sums_dev + 0));
-    OSTEO_TRY(gram(ty, ty, ny.as<float>(), ny.as<float>(), yrow_begin, yrow_end, m, yrow_begin == 0 && yrow_end == m, sums_dev + 1));
-    OSTEO_TRY(gram(tx, ty, nx.as<float>(), ny.as<float>(), row_begin, row_end, m, false, sums_dev + 2));
+    OSTEO_TRY(gram(tx, txb, nx.as<float>(), nx.as<float>(), row_begin, row_end, n, row_begin == 0 && row_end == n, sums_dev + 0));
+    OSTEO_TRY(gram(ty, tyb, ny.as<float>(), ny.as<float>(), yrow_begin, yrow_end, m, yrow_begin == 0 && yrow_end == m, sums_dev + 1));
+    OSTEO_TRY(gram(tx, tyb, nx.as<float>(), ny.as<float>(), row_begin, row_end, m, false, sums_dev + 2));
     int h = 0;
     OSTEO_CUDA(cudaMemcpyAsync(&h, status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     OSTEO_CUDA(cudaStreamSynchronize(s));

@@ -11,6 +11,7 @@
 #include "fused_step.cuh"
 #include "gemm_host.cuh"
 #include "gemm_ws.cuh"
+#include "gemm_rbf.cuh"
 #include "train_kernels.cuh"
 #include "validators.cuh"
 
