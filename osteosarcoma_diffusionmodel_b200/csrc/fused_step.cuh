@@ -143,7 +143,9 @@ __device__ __forceinline__ void philox_axpy_normal16(uint64_t seed, uint64_t row
 template <bool HOOKS>
 __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_constant__ FusedParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment by pointer arithmetic ON the __shared__ array: an integer round trip would turn every later access into a
+    // generic LD / ST (address-space lookup in the LSU, several times slower than LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* s_a = smem;
     uint8_t* s_wout = s_a + F_ARES_BYTES;
     uint8_t* s_win = s_wout + F_STAGES * F_WOUT_STAGE;

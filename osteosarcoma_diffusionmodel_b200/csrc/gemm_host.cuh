@@ -28,6 +28,7 @@ inline int launch_gemm(int epi, int gw, const GemmParams& p, int num_sms, cudaSt
         case EPI_MSE: return launch_gemm_inst<EPI_MSE, 64>(p, num_sms, stream);
         case EPI_RBF: return launch_gemm_inst<EPI_RBF, 64>(p, num_sms, stream);
         case EPI_GN_SILU:
+            if (p.N > GN_PAR_MAX) return fail("Linear+GroupNorm layer of width %d: the epilogue keeps bias / gamma / beta of at most %d columns in shared memory", p.N, GN_PAR_MAX);
             switch (gw) {
                 case 16: return launch_gemm_inst<EPI_GN_SILU, 16>(p, num_sms, stream);
                 case 32: return launch_gemm_inst<EPI_GN_SILU, 32>(p, num_sms, stream);

@@ -42,7 +42,9 @@ struct RbfParams {
 
 __global__ void __launch_bounds__(RB_THREADS, 1) rbf_gram_kernel(const __grid_constant__ RbfParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment by pointer arithmetic ON the __shared__ array: an integer round trip would turn every later access into a
+    // generic LD / ST (address-space lookup in the LSU, several times slower than LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + RB_STAGES * RB_STAGE_BYTES);
     uint64_t* empty_bar = full_bar + RB_STAGES;
     uint64_t* tfull_bar = empty_bar + RB_STAGES;

@@ -292,7 +292,9 @@ struct TileSeq {
 template <int EPI, int GW, bool MN = false>
 __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment by pointer arithmetic ON the __shared__ array: an integer round trip would turn every later access into a
+    // generic LD / ST (address-space lookup in the LSU, several times slower than LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     constexpr int STAGES = stages_of<EPI>();
     constexpr bool XSTAGE = (EPI == EPI_DDPM);
     constexpr int NUM_EPI_WARPS = epi_warps_of<EPI, GW>();
@@ -350,8 +352,8 @@ __global__ void __launch_bounds__(gemm_threads<EPI, GW>(), 1) gemm_tc_kernel(con
     if constexpr (EPI == EPI_GN_SILU) {
         // The layer's bias / gamma / beta (N <= 512) live in shared memory for the whole kernel: the L1 is carved out as shared memory,
         // so per-tile __ldg loads of them were L2 round trips on the epilogue's critical path.
-        if (warp >= 4 && p.N <= GN_PAR_MAX) {
-            for (int i = threadIdx.x; i < p.N; i += NUM_EPI_WARPS * 32) {
+        if (warp >= 4) {
+            for (int i = threadIdx.x; i < p.N && i < GN_PAR_MAX; i += NUM_EPI_WARPS * 32) {
                 gn_par[i] = p.bias[i];
                 gn_par[GN_PAR_MAX + i] = p.gamma[i];
                 gn_par[2 * GN_PAR_MAX + i] = p.beta[i];
@@ -712,6 +714,9 @@ struct Epilogue<EPI_LINEAR> {
     }
 };
 
+#ifdef OSTEO_WS_TRACE
+__device__ long long g_gn_stamp[4];      // diagnostics build: last writer wins, good enough to see the split inside one epilogue pass
+#endif
 template <>
 struct Epilogue<EPI_GN_SILU> {
     // 16 epilogue warps: this thread owns 32 consecutive columns [col, col + 32) of one row.
@@ -724,10 +729,11 @@ struct Epilogue<EPI_GN_SILU> {
         const bool live = row < p.M;
         constexpr int NG = GW >= 32 ? 1 : 32 / GW;       // groups (or the half group) inside this thread's 32 columns
         constexpr int W = GW >= 32 ? 32 : GW;            // columns of one group held by this thread
-        const bool in_smem = p.N <= GN_PAR_MAX;
-        const float* bias = in_smem ? par + col : p.bias + col;
-        const float* gamma = in_smem ? par + GN_PAR_MAX + col : p.gamma + col;
-        const float* beta = in_smem ? par + 2 * GN_PAR_MAX + col : p.beta + col;
+        // the layer's parameters are ALWAYS in shared memory (N <= GN_PAR_MAX is enforced at launch): selecting between a shared and a
+        // global pointer at run time would make every access a generic load
+        const float* bias = par + col;
+        const float* gamma = par + GN_PAR_MAX + col;
+        const float* beta = par + 2 * GN_PAR_MAX + col;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 b = reinterpret_cast<const float4*>(bias)[j];
@@ -739,6 +745,12 @@ struct Epilogue<EPI_GN_SILU> {
         float mean[NG], rstd[NG];
         const int me = (q * 4 + part) * 32 + lane, other = (q * 4 + (part ^ 1)) * 32 + lane;
         const int bar_id = 1 + q * 2 + (part >> 1);
+#ifdef OSTEO_WS_TRACE
+#define GN_STAMP(i) g_gn_stamp[i] = clock64()
+#else
+#define GN_STAMP(i) do { } while (0)
+#endif
+        GN_STAMP(0);
         if (p.out_lo_off == 0 && !p.xhat_bf && !p.rstd_out && p.drop_p == 0.0f) {
             // bf16 inference fast path (warp-uniform): one-pass moments (sum and sum of squares in one sweep, one exchange for a 64-wide
             // group) and normalise + affine + the 0.5 of the tanh form of SiLU folded into one FFMA per element:
@@ -765,6 +777,7 @@ struct Epilogue<EPI_GN_SILU> {
                 mean[g] = mu;
                 rstd[g] = 0.5f * rsqrtf(fmaxf(fmaf(-mu, mu, ss * (1.0f / GW)), 0.0f) + p.gn_eps);      // 0.5 / sigma
             }
+            GN_STAMP(1);
             if (!live) return;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -780,7 +793,9 @@ struct Epilogue<EPI_GN_SILU> {
                     v[i] = fmaf(h, t, h);
                 }
             }
+            GN_STAMP(2);
             store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + col, v, 0);
+            GN_STAMP(3);
             return;
         }
 #pragma unroll

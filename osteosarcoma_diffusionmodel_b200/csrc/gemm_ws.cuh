@@ -20,10 +20,19 @@ constexpr int WS_MAX_STAGES = 12;
 constexpr int WS_THREADS = 128 + 32 * 16;
 constexpr int WS_SMEM_BYTES = WS_RING_PLUS_RES * A_TILE_BYTES + 1024 /*align*/ + 512 /*barriers*/ + GN_PAR_BYTES + GN_XCH_BYTES;
 
+#ifdef OSTEO_WS_TRACE
+__device__ long long g_ws_trace[3 * 32 * 4];      // [role][tile < 32][event] clock64 stamps of CTA 0 (diagnostics build only)
+#define WS_TRACE(role, tile, ev) do { if (blockIdx.x == 0 && (tile) < 32 && lane == 0) g_ws_trace[((role) * 32 + (tile)) * 4 + (ev)] = clock64(); } while (0)
+#else
+#define WS_TRACE(role, tile, ev) do { } while (0)
+#endif
+
 template <int GW>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+    // 1024-byte alignment by pointer arithmetic ON the __shared__ array: an integer round trip would turn every later access into a
+    // generic LD / ST (address-space lookup in the LSU, several times slower than LDS / STS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     int total_kb = 0;
     for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
     const int stages = WS_RING_PLUS_RES - total_kb;     // 5 (K = 512) .. 9 (K = 256)
@@ -66,8 +75,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
         fence_mbar_init();
     }
     if (warp == 2) tmem_alloc(tmem_slot, 512);
-    if (warp >= 4 && p.N <= GN_PAR_MAX) {
-        for (int i = threadIdx.x; i < p.N; i += NUM_EPI_WARPS * 32) {
+    if (warp >= 4) {
+        for (int i = threadIdx.x; i < p.N && i < GN_PAR_MAX; i += NUM_EPI_WARPS * 32) {
             gn_par[i] = p.bias[i];
             gn_par[GN_PAR_MAX + i] = p.gamma[i];
             gn_par[2 * GN_PAR_MAX + i] = p.beta[i];
@@ -91,8 +100,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
             }
             int stage = 0;
             uint32_t phase = 0;
-            for (int m = m_first; ok && m < p.m_tiles; m += m_step) {
+            int tcount = 0;
+            for (int m = m_first; ok && m < p.m_tiles; m += m_step, ++tcount) {
                 const int m_blk = p.m_tile0 + m;
+                WS_TRACE(0, tcount, 0);
                 for (int s = 0; s < p.nseg && ok; ++s) {
                     const KSeg sg = p.seg[s];
                     const CUtensorMap* ta = &p.tma_a[sg.a_sel];
@@ -103,6 +114,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                 }
+                WS_TRACE(0, tcount, 1);
             }
             if (!ok) atomicExch(p.status, ERR_PRODUCER_TIMEOUT);
         }
@@ -120,10 +132,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
             const int acc = it % NUM_ACC;
             if (!mbar_wait_relaxed(&tempty_bar[acc], (static_cast<uint32_t>(it / NUM_ACC) & 1u) ^ 1u)) { ok = false; break; }
             tc_fence_after_sync();
+            WS_TRACE(1, it, 0);
             const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BN);
             for (int idx = 0; idx < total_kb; ++idx) {
                 if (!mbar_wait_relaxed(&full_bar[stage], phase)) { ok = false; break; }
                 tc_fence_after_sync();
+                if (idx == 0) WS_TRACE(1, it, 1);
                 if (leader) {
                     const uint64_t adesc = adesc0 + static_cast<uint64_t>((stage * A_TILE_BYTES) >> 4);
                     const uint64_t bdesc = wdesc0 + static_cast<uint64_t>((idx * B_TILE_BYTES) >> 4);
@@ -136,6 +150,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
             }
             if (ok && leader) umma_commit(&tfull_bar[acc]);
             __syncwarp();
+            WS_TRACE(1, it, 2);
         }
         if (!ok && leader) atomicExch(p.status, ERR_MMA_TIMEOUT);
     } else if (warp >= 4) {
@@ -149,14 +164,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + part * 32);
             const int row = (p.m_tile0 + m) * BM + q * 32 + lane;
             const int col = n_blk * BN + part * 32;
+            if (warp_phys == 0) WS_TRACE(2, it, 0);
             if (!mbar_wait(&tfull_bar[acc], static_cast<uint32_t>(it / NUM_ACC) & 1u)) { ok = false; break; }
             tc_fence_after_sync();
+            if (warp_phys == 0) WS_TRACE(2, it, 1);
             float v[32];
             tmem_ld_32(taddr, v);
             tc_fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (warp_phys == 0) WS_TRACE(2, it, 2);
             Epilogue<EPI_GN_SILU>::template run32<GW>(p, row, col, v, gn_par, gn_xch, q, part, lane);
+            if (warp_phys == 0) WS_TRACE(2, it, 3);
         }
         if (!ok && lane == 0) atomicExch(p.status, ERR_EPI_TIMEOUT);
     }
@@ -170,7 +189,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
 inline bool gemm_ws_eligible(const GemmParams& p) {
     int total_kb = 0;
     for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
-    return total_kb > 0 && total_kb <= WS_MAX_KB && p.a_blocked_nbox == 0 && p.out_lo_off == 0 && p.n_tiles >= 1 && p.n_tiles <= 8;
+    return total_kb > 0 && total_kb <= WS_MAX_KB && p.a_blocked_nbox == 0 && p.out_lo_off == 0 && p.n_tiles >= 1 && p.n_tiles <= 8 && p.N <= GN_PAR_MAX;
 }
 
 template <int GW>
@@ -186,6 +205,22 @@ int launch_gemm_ws_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
     if (per_slice < 1) return -2;
     gemm_ws_gn_silu_kernel<GW><<<per_slice * p.n_tiles, WS_THREADS, WS_SMEM_BYTES, stream>>>(p);
     OSTEO_CUDA(cudaGetLastError());
+#ifdef OSTEO_WS_TRACE
+    if (getenv("OSTEO_DDPM_TRACE")) {      // diagnostics build: print CTA 0's timeline of this launch (synchronises)
+        static long long h[3 * 32 * 4];
+        OSTEO_CUDA(cudaStreamSynchronize(stream));
+        OSTEO_CUDA(cudaMemcpyFromSymbol(h, g_ws_trace, sizeof h));
+        const long long t0 = h[0];
+        long long g[4];
+        OSTEO_CUDA(cudaMemcpyFromSymbol(g, g_gn_stamp, sizeof g));
+        fprintf(stderr, "[ws trace] N=%d nseg=%d nkb0=%d GW=%d | last epilogue pass: bias+moments %lld  elementwise %lld  store %lld cycles\n", p.N, p.nseg, p.seg[0].nkb, GW,
+                g[1] - g[0], g[2] - g[1], g[3] - g[2]);
+        for (int t = 0; t < 12; ++t)
+            fprintf(stderr, "[ws trace] tile %2d | PROD start %6lld end %6lld | MMA acc_free %6lld first_full %6lld issued %6lld | EPI arrive %6lld tfull %6lld tmem %6lld done %6lld\n", t,
+                    h[(0 * 32 + t) * 4 + 0] - t0, h[(0 * 32 + t) * 4 + 1] - t0, h[(1 * 32 + t) * 4 + 0] - t0, h[(1 * 32 + t) * 4 + 1] - t0, h[(1 * 32 + t) * 4 + 2] - t0,
+                    h[(2 * 32 + t) * 4 + 0] - t0, h[(2 * 32 + t) * 4 + 1] - t0, h[(2 * 32 + t) * 4 + 2] - t0, h[(2 * 32 + t) * 4 + 3] - t0);
+    }
+#endif
     return 0;
 }
 
