@@ -454,7 +454,9 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
     members = [list(range(15 * p, 15 * p + 15)) for p in range(10)]
     val = BiologicalValidator({"evaluation": {}})
     ms = timed(lambda: val.pathway_coherence_from_tensors(cohort[: rows // 2], cohort[rows // 2:], members), 1, 3)
-    out["coherence"] = {"rows": rows, "genes": 371, "pathways": 10, "ms": ms, "gathered_gb_per_s": rows * 150 * 4 / (ms / 1e3) / 1e9}
+    out["coherence"] = {"rows": rows, "genes": 371, "pathways": 10, "ms": ms, "gathered_gb_per_s": rows * 150 * 4 / (ms / 1e3) / 1e9,
+                        "streamed_gb_per_s": rows * 371 * 4 / (ms / 1e3) / 1e9, "hbm_frac": rows * 371 * 4 / (ms / 1e3) / 1e9 / hbm_peak,
+                        "note": "one pass over whole rows for all pathways (osteo_corr_moments_batched); includes the host-side finish of both cohorts"}
     return out
 
 

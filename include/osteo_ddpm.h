@@ -197,6 +197,12 @@ int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long 
 int osteo_corr_moments(const float* data_dev, long long n, int ld, const int* cols_dev, int k,
                        const float* shift_dev, long long row_begin, long long row_end,
                        double* out_dev, void* stream);
+/* The same moment blocks for up to 32 column sets in ONE pass over the rows (validate_pathway_coherence, utils/validation.py:144-157:
+ * ten pathways x ~15 genes out of the same 371 columns).  data_dev [n, ld] fp32 of which the first `ncols` columns are staged;
+ * cols_dev int32 [n_sets, 32], each row = the set's column indices (< ncols) packed at the front, -1 padded; shift_dev fp32 [n_sets, 32];
+ * out_dev fp64 [n_sets, 1057] = per set {count, sum (x-s) [32], sum (x-s)(x-s)^T [32][32]} over rows [row_begin,row_end), overwritten. */
+int osteo_corr_moments_batched(const float* data_dev, long long n, int ld, int ncols, const int* cols_dev, int n_sets,
+                               const float* shift_dev, long long row_begin, long long row_end, double* out_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -226,4 +226,32 @@ int osteo_corr_moments(const float* data_dev, long long n, int ld, const int* co
     return 0;
 }
 
+int osteo_corr_moments_batched(const float* data_dev, long long n, int ld, int ncols, const int* cols_dev, int n_sets, const float* shift_dev, long long row_begin,
+                               long long row_end, double* out_dev, void* stream) {
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (n_sets <= 0 || n_sets > 32) return fail("corr_moments_batched: %d column sets outside [1, 32]", n_sets);
+    if (ncols <= 0 || ncols > ld) return fail("corr_moments_batched: ncols=%d outside [1, ld=%d]", ncols, ld);
+    if (row_begin < 0 || row_end > n || row_begin > row_end) return fail("corr_moments_batched: bad row range");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OSTEO_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * n_sets * CM_STRIDE, s));
+    if (row_end == row_begin) return 0;
+    // rows per chunk: as many whole rows as fit in 96 KB of shared memory, at most 64
+    int chunk_rows = static_cast<int>((96 * 1024) / (static_cast<size_t>(ncols) * 4));
+    if (chunk_rows > 64) chunk_rows = 64;
+    if (chunk_rows < 1) return fail("corr_moments_batched: a row of %d columns does not fit the 96 KB staging buffer", ncols);
+    const size_t smem = static_cast<size_t>(chunk_rows) * ncols * 4;
+    static bool configured = false;
+    if (!configured) {
+        OSTEO_CUDA(cudaFuncSetAttribute(corr_moments_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        configured = true;
+    }
+    const long long nchunks = (row_end - row_begin + chunk_rows - 1) / chunk_rows;
+    const int sms = current_sms();
+    const long long blocks = nchunks < 2LL * sms ? nchunks : 2LL * sms;
+    corr_moments_batched_kernel<<<static_cast<unsigned>(blocks), 32 * n_sets, smem, s>>>(data_dev, ld, ncols, cols_dev, n_sets, shift_dev, row_begin, row_end, chunk_rows,
+                                                                                          out_dev);
+    OSTEO_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // extern "C"

@@ -79,4 +79,89 @@ __global__ void corr_moments_kernel(const float* __restrict__ data, int ld, cons
         if (red[i] != 0.0) atomicAdd(out + i, red[i]);
 }
 
+// All pathways in ONE pass over the cohort (validate_pathway_coherence gathers ~15 genes for each of 10 pathways out of 371 columns:
+// ten separate gathers re-read the same rows ten times, one 4-byte element per 32-byte sector). A block = P warps, warp p owns
+// pathway p for the whole launch (its fp64 moment block stays in registers); the block streams chunks of whole rows through shared
+// memory with coalesced loads and every warp gathers its columns from there.
+//   cols [P][32] int32, -1 padded; shift [P][32]; out [P][CM_STRIDE] fp64 = {count, s1[32], s2[32][32]} (accumulated: zero it first)
+constexpr int CM_STRIDE = 1 + 32 + 32 * 32;
+__global__ void corr_moments_batched_kernel(const float* __restrict__ data, int ld, int ncols, const int* __restrict__ cols, int P, const float* __restrict__ shift,
+                                            long long rb, long long re, int chunk_rows, double* __restrict__ out) {
+    extern __shared__ float rows_sm[];                       // [chunk_rows][ncols]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int col = cols[warp * 32 + lane];
+    const bool has = col >= 0;
+    int k = __popc(__ballot_sync(0xffffffffu, has));          // columns are packed at the front
+    const float s = has ? shift[warp * 32 + lane] : 0.0f;
+    double s1 = 0.0;
+    double s2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) s2[i] = 0.0;
+    long long count = 0;
+    const long long nchunks = (re - rb + chunk_rows - 1) / chunk_rows;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const long long r0 = rb + c * chunk_rows;
+        const int nr = static_cast<int>(re - r0 < chunk_rows ? re - r0 : chunk_rows);
+        __syncthreads();                                      // the previous chunk has been consumed
+        if (ld == ncols) {
+            // rows are contiguous: one flat coalesced copy, 128-bit and unrolled (8 independent loads per thread in flight: a scalar
+            // load -> store loop has one, and the staging of a chunk then costs 70 DRAM round trips)
+            const float* src = data + r0 * ld;
+            const int total = nr * ncols;
+            if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                const int n4 = total >> 2;
+                const float4* s4 = reinterpret_cast<const float4*>(src);
+                float4* d4 = reinterpret_cast<float4*>(rows_sm);
+                int i = threadIdx.x;
+                for (; i + 7 * static_cast<int>(blockDim.x) < n4; i += 8 * blockDim.x) {
+                    float4 t[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) t[u] = __ldg(s4 + i + u * blockDim.x);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) d4[i + u * blockDim.x] = t[u];
+                }
+                for (; i < n4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+                for (int j = (n4 << 2) + threadIdx.x; j < total; j += blockDim.x) rows_sm[j] = src[j];
+            } else {
+                for (int i = threadIdx.x; i < total; i += blockDim.x) rows_sm[i] = src[i];
+            }
+        } else {
+            for (int i = threadIdx.x; i < nr * ncols; i += blockDim.x) rows_sm[i] = data[(r0 + i / ncols) * ld + i % ncols];
+        }
+        __syncthreads();
+        // products of one chunk (<= 64 rows of shifted, O(1) values) are accumulated in fp32 and flushed to the fp64 moment block once
+        // per chunk: per-product fp32 -> fp64 conversions run on the 16-lane XU pipe and made the loop 10x slower than its FMAs
+        float a1 = 0.0f, a2[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) a2[i] = 0.0f;
+        if (k <= 16) {
+            for (int r = 0; r < nr; ++r) {
+                const float v = has ? rows_sm[r * ncols + col] - s : 0.0f;
+                a1 += v;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) a2[i] = fmaf(v, __shfl_sync(0xffffffffu, v, i), a2[i]);
+            }
+        } else {
+            for (int r = 0; r < nr; ++r) {
+                const float v = has ? rows_sm[r * ncols + col] - s : 0.0f;
+                a1 += v;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) a2[i] = fmaf(v, __shfl_sync(0xffffffffu, v, i), a2[i]);
+            }
+        }
+        s1 += static_cast<double>(a1);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s2[i] += static_cast<double>(a2[i]);
+        count += nr;
+    }
+    double* o = out + static_cast<size_t>(warp) * CM_STRIDE;
+    if (lane == 0 && count) atomicAdd(o, static_cast<double>(count));
+    if (has && count) {
+        atomicAdd(o + 1 + lane, s1);
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+            if (i < k) atomicAdd(o + 33 + lane * 32 + i, s2[i]);
+    }
+}
+
 }  // namespace osteo

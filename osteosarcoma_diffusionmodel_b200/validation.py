@@ -48,6 +48,9 @@ def _moments(data: torch.Tensor, cols: Sequence[int], shift: torch.Tensor, rows)
     return out
 
 
+_CM_STRIDE = 1 + 32 + 32 * 32      # osteo_corr_moments_batched: {count, s1[32], s2[32][32]} per column set
+
+
 def _corr_from_moments(mom: np.ndarray, k: int) -> np.ndarray:
     """Pearson correlation matrix from shifted moments (float64, host; k <= 32)."""
     n = mom[0]
@@ -102,21 +105,32 @@ class BiologicalValidator:
 
     # ------------------------------------------------------------------ utils/validation.py:125-175
     def _coherence_scores(self, data: torch.Tensor, member_cols: List[List[int]]) -> List[float]:
-        """One moment kernel per pathway, all enqueued before a single all-reduce and a single device->host copy."""
+        """All pathways in one pass over the cohort (osteo_corr_moments_batched: warp p owns pathway p, whole rows are streamed
+        through shared memory), then a single all-reduce and a single device->host copy."""
         rank, ws = D.world()
         rows = D.shard_rows(data.shape[0], rank, ws)
+        if any(len(c) > 32 for c in member_cols):
+            raise ValueError("a pathway with more than 32 member genes is not supported by the moment kernel")
         parts = []
-        for cols in member_cols:
-            ci = torch.tensor(cols, dtype=torch.long, device=data.device)
-            shift = data[0, ci].contiguous()            # any value near the column mean conditions the fp64 moments
-            parts.append(_moments(data, cols, shift, rows))
+        for b0 in range(0, len(member_cols), 32):
+            sets = member_cols[b0:b0 + 32]
+            ci = np.full((len(sets), 32), -1, dtype=np.int32)
+            for i, cols in enumerate(sets):
+                ci[i, :len(cols)] = cols
+            ci_t = torch.from_numpy(ci).to(data.device)
+            # any value near the column mean conditions the fp64 moments: the first row's
+            shift = data[0, ci_t.clamp(min=0).long()].contiguous()
+            out = torch.empty((len(sets), _CM_STRIDE), dtype=torch.float64, device=data.device)
+            _lib.check(_lib.load().osteo_corr_moments_batched(data.data_ptr(), data.shape[0], data.stride(0), data.shape[1], ci_t.data_ptr(), len(sets),
+                                                              shift.data_ptr(), rows[0], rows[1], out.data_ptr(), _lib.stream_handle()))
+            parts.append(out)
         flat = D.all_reduce_sum_(torch.cat(parts)).cpu().numpy()
-        scores, o = [], 0
-        for cols in member_cols:
+        scores = []
+        for i, cols in enumerate(member_cols):
             k = len(cols)
-            n = 1 + k + k * k
-            corr = _corr_from_moments(flat[o:o + n], k)
-            o += n
+            blk = flat[i]
+            mom = np.concatenate([blk[:1], blk[1:1 + k], blk[33:].reshape(32, 32)[:k, :k].reshape(-1)])
+            corr = _corr_from_moments(mom, k)
             scores.append(float(corr[np.triu_indices(k, k=1)].mean()))
         return scores
 
