@@ -122,20 +122,72 @@ __global__ void outer_accum_kernel(const float* __restrict__ G, int gm, const fl
     float* sx = sm + R * gm;    // [R, xk]
     const long long r0 = static_cast<long long>(blockIdx.x) * R;
     const int rows = static_cast<int>((n - r0) < R ? (n - r0) : R);
-    for (int i = threadIdx.x; i < R * gm; i += blockDim.x) {
-        const int rr = i / gm;
-        sg[i] = rr < rows ? G[(r0 + rr) * gm + i % gm] : 0.0f;
-    }
-    for (int i = threadIdx.x; i < R * xk; i += blockDim.x) {
-        const int rr = i / xk;
-        float v = 0.0f;
-        if (rr < rows) {
-            const long long xr = x_idx ? x_idx[r0 + rr] : (r0 + rr);
-            v = X[xr * xk + i % xk];
+    // staging: eight independent loads per thread in flight before the first store (a load -> store loop keeps ONE in flight, and the
+    // 96 dependent DRAM / L2 round trips of such a loop were most of this kernel's 71 us)
+    for (int i0 = threadIdx.x; i0 < R * gm; i0 += 8 * blockDim.x) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            const int rr = i / gm;
+            t[u] = (i < R * gm && rr < rows) ? __ldg(G + (r0 + rr) * gm + i % gm) : 0.0f;
         }
-        sx[i] = v;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < R * gm) sg[i] = t[u];
+        }
+    }
+    for (int i0 = threadIdx.x; i0 < R * xk; i0 += 8 * blockDim.x) {
+        float t[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            const int rr = i / xk;
+            float v = 0.0f;
+            if (i < R * xk && rr < rows) {
+                const long long xr = x_idx ? __ldg(x_idx + r0 + rr) : (r0 + rr);
+                v = __ldg(X + xr * xk + i % xk);
+            }
+            t[u] = v;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < R * xk) sx[i] = t[u];
+        }
     }
     __syncthreads();
+    if ((gm & 3) == 0 && (xk & 7) == 0) {
+        // register-tiled: a thread owns 4 x 8 patches of dW, three 128-bit shared loads feed 32 FMAs per staged row (one entry per thread
+        // and two scalar shared loads per FMA made the 256 x 128 time_proj gradient shared-memory bound: 111 us)
+        const int tb = xk >> 3;
+        for (int tile = threadIdx.x; tile < (gm >> 2) * tb; tile += blockDim.x) {
+            const int a0 = (tile / tb) << 2, b0 = (tile % tb) << 3;
+            float acc[4][8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+#pragma unroll 4
+            for (int rr = 0; rr < R; ++rr) {
+                const float4 g = *reinterpret_cast<const float4*>(sg + rr * gm + a0);
+                const float4 x0 = *reinterpret_cast<const float4*>(sx + rr * xk + b0);
+                const float4 x1 = *reinterpret_cast<const float4*>(sx + rr * xk + b0 + 4);
+                const float gg[4] = {g.x, g.y, g.z, g.w};
+                const float xx[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(gg[i], xx[j], acc[i][j]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) atomicAdd(dW + (a0 + i) * xk + b0 + j, acc[i][j]);
+        }
+        return;
+    }
     for (int e = threadIdx.x; e < gm * xk; e += blockDim.x) {
         const int a = e / xk, b = e % xk;
         float acc = 0.0f;
