@@ -129,29 +129,32 @@ __global__ void corr_moments_batched_kernel(const float* __restrict__ data, int 
             for (int i = threadIdx.x; i < nr * ncols; i += blockDim.x) rows_sm[i] = data[(r0 + i / ncols) * ld + i % ncols];
         }
         __syncthreads();
-        // products of one chunk (<= 64 rows of shifted, O(1) values) are accumulated in fp32 and flushed to the fp64 moment block once
-        // per chunk: per-product fp32 -> fp64 conversions run on the 16-lane XU pipe and made the loop 10x slower than its FMAs
-        float a1 = 0.0f, a2[32];
+        // products are accumulated in fp32 over sub-blocks of 16 rows (shifted, O(1) values) and flushed to the fp64 moment block:
+        // per-product fp32 -> fp64 conversions run on the 16-lane XU pipe and made the loop 10x slower than its FMAs
+        for (int rs = 0; rs < nr; rs += 16) {
+            const int re16 = rs + 16 < nr ? rs + 16 : nr;
+            float a1 = 0.0f, a2[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) a2[i] = 0.0f;
-        if (k <= 16) {
-            for (int r = 0; r < nr; ++r) {
-                const float v = has ? rows_sm[r * ncols + col] - s : 0.0f;
-                a1 += v;
+            for (int i = 0; i < 32; ++i) a2[i] = 0.0f;
+            if (k <= 16) {
+                for (int r = rs; r < re16; ++r) {
+                    const float v = has ? rows_sm[r * ncols + col] - s : 0.0f;
+                    a1 += v;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) a2[i] = fmaf(v, __shfl_sync(0xffffffffu, v, i), a2[i]);
+                    for (int i = 0; i < 16; ++i) a2[i] = fmaf(v, __shfl_sync(0xffffffffu, v, i), a2[i]);
+                }
+            } else {
+                for (int r = rs; r < re16; ++r) {
+                    const float v = has ? rows_sm[r * ncols + col] - s : 0.0f;
+                    a1 += v;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) a2[i] = fmaf(v, __shfl_sync(0xffffffffu, v, i), a2[i]);
+                }
             }
-        } else {
-            for (int r = 0; r < nr; ++r) {
-                const float v = has ? rows_sm[r * ncols + col] - s : 0.0f;
-                a1 += v;
+            s1 += static_cast<double>(a1);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) a2[i] = fmaf(v, __shfl_sync(0xffffffffu, v, i), a2[i]);
-            }
+            for (int i = 0; i < 32; ++i) s2[i] += static_cast<double>(a2[i]);
         }
-        s1 += static_cast<double>(a1);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s2[i] += static_cast<double>(a2[i]);
         count += nr;
     }
     double* o = out + static_cast<size_t>(warp) * CM_STRIDE;

@@ -102,3 +102,42 @@ def test_moments_large_cohort_against_numpy():
     corr = val._corr_from_moments(mom, len(cols))
     ref = np.corrcoef(data[:, cols].astype(np.float64), rowvar=False)
     assert np.abs(corr - ref).max() < 1e-9
+
+
+@pytest.mark.parametrize("n,ncols,pitch", [(200_000, 371, 371), (1001, 50, 64), (63, 33, 33)])
+def test_batched_moments_match_numpy_and_the_single_set_kernel(n, ncols, pitch):
+    """osteo_corr_moments_batched (one pass, warp per column set) against numpy and against the per-set kernel: set sizes 1 / 15 / 17 /
+    32, a padded row pitch (scalar staging path), ragged last chunk, and row sharding (partial sums add up)."""
+    from osteosarcoma_diffusionmodel_b200 import _lib, validation as val
+    rs = np.random.RandomState(11)
+    full = (rs.standard_normal((n, pitch)) * 1.5 + 4).astype(np.float32)
+    full[:, 7] = 0.5 * full[:, 2] + 0.5 * full[:, 7]
+    t = torch.from_numpy(full).cuda()
+    sets = [sorted(rs.choice(ncols, k, replace=False).tolist()) for k in (1, 15, 17, 32)]
+    ci = np.full((len(sets), 32), -1, dtype=np.int32)
+    for i, c in enumerate(sets):
+        ci[i, :len(c)] = c
+    ci_t = torch.from_numpy(ci).cuda()
+    shift = t[0, ci_t.clamp(min=0).long()].contiguous()
+    lib, s = _lib.load(), _lib.stream_handle()
+
+    def run(rb, re):
+        out = torch.empty((len(sets), val._CM_STRIDE), dtype=torch.float64, device="cuda")
+        _lib.check(lib.osteo_corr_moments_batched(t.data_ptr(), n, pitch, ncols, ci_t.data_ptr(), len(sets), shift.data_ptr(), rb, re, out.data_ptr(), s))
+        return out.cpu().numpy()
+
+    whole = run(0, n)
+    cut = (n // 3 // 8) * 8 + 5
+    parts = run(0, cut) + run(cut, n)
+    assert np.allclose(whole, parts, rtol=1e-6, atol=1e-4)
+    for i, cols in enumerate(sets):
+        k = len(cols)
+        blk = whole[i]
+        assert blk[0] == n
+        mom = np.concatenate([blk[:1], blk[1:1 + k], blk[33:].reshape(32, 32)[:k, :k].reshape(-1)])
+        single = val._moments(t, cols, shift[i, :k].contiguous(), (0, n)).cpu().numpy()
+        assert np.allclose(mom, single, rtol=2e-6, atol=1e-3)      # fp32 per-chunk partial sums vs fp64 products
+        if k > 1:
+            corr = val._corr_from_moments(mom, k)
+            ref = np.corrcoef(full[:, cols].astype(np.float64), rowvar=False)
+            assert np.abs(corr - ref).max() < 1e-6
