@@ -51,6 +51,15 @@ def _moments(data: torch.Tensor, cols: Sequence[int], shift: torch.Tensor, rows)
 _CM_STRIDE = 1 + 32 + 32 * 32      # osteo_corr_moments_batched: {count, s1[32], s2[32][32]} per column set
 
 
+def _moments_batched(data: torch.Tensor, ci_t: torch.Tensor, shift: torch.Tensor, rows) -> torch.Tensor:
+    """fp64 [n_sets, _CM_STRIDE]: the shifted moments of up to 32 gathered columns per set (ci_t int32 [n_sets, 32], -1 = unused
+    slot) over rows [b, e), all sets in one pass over the cohort."""
+    out = torch.empty((ci_t.shape[0], _CM_STRIDE), dtype=torch.float64, device=data.device)
+    _lib.check(_lib.load().osteo_corr_moments_batched(data.data_ptr(), data.shape[0], data.stride(0), data.shape[1], ci_t.data_ptr(), ci_t.shape[0],
+                                                      shift.data_ptr(), rows[0], rows[1], out.data_ptr(), _lib.stream_handle()))
+    return out
+
+
 def _corr_from_moments(mom: np.ndarray, k: int) -> np.ndarray:
     """Pearson correlation matrix from shifted moments (float64, host; k <= 32)."""
     n = mom[0]
@@ -120,10 +129,7 @@ class BiologicalValidator:
             ci_t = torch.from_numpy(ci).to(data.device)
             # any value near the column mean conditions the fp64 moments: the first row's
             shift = data[0, ci_t.clamp(min=0).long()].contiguous()
-            out = torch.empty((len(sets), _CM_STRIDE), dtype=torch.float64, device=data.device)
-            _lib.check(_lib.load().osteo_corr_moments_batched(data.data_ptr(), data.shape[0], data.stride(0), data.shape[1], ci_t.data_ptr(), len(sets),
-                                                              shift.data_ptr(), rows[0], rows[1], out.data_ptr(), _lib.stream_handle()))
-            parts.append(out)
+            parts.append(_moments_batched(data, ci_t, shift, rows))
         flat = D.all_reduce_sum_(torch.cat(parts)).cpu().numpy()
         scores = []
         for i, cols in enumerate(member_cols):

@@ -115,8 +115,22 @@ def _worker_mmd(rank, ws, port, q):
         k = len(cols)
         return torch.from_numpy(np.concatenate([[a.shape[0]], a.sum(0), (a.T @ a).reshape(-1)]))
 
+    def fake_moments_batched(data, ci_t, shift, rows):
+        a = data.numpy().astype(np.float64)[rows[0]:rows[1]]
+        out = np.zeros((ci_t.shape[0], val._CM_STRIDE))
+        for p, (ci, sh) in enumerate(zip(ci_t.numpy(), shift.numpy().astype(np.float64))):
+            k = int((ci >= 0).sum())
+            g = a[:, ci[:k]] - sh[:k]
+            out[p, 0] = g.shape[0]
+            out[p, 1:1 + k] = g.sum(0)
+            s2 = np.zeros((32, 32))
+            s2[:k, :k] = g.T @ g
+            out[p, 33:] = s2.reshape(-1)
+        return torch.from_numpy(out)
+
     val._gram_partial_sums = fake_partial
     val._moments = fake_moments
+    val._moments_batched = fake_moments_batched
     v = val.BiologicalValidator({"evaluation": {}}, device="cpu")
     v._require_cuda = lambda: None
     got = v.compute_mmd(X, Y)
