@@ -61,6 +61,10 @@ long long osteo_ddpm_capacity(const osteo_ddpm_ctx* ctx);
 long long osteo_ddpm_workspace_bytes(const osteo_ddpm_ctx* ctx);
 /* Rows per internal pass (activations of one pass stay L2-resident). 0 = all rows at once. */
 int osteo_ddpm_set_chunk_rows(osteo_ddpm_ctx* ctx, int chunk_rows);
+/* Sampling graphs split the batch into `branches` (1..4, default 2) contiguous row ranges captured as parallel graph branches
+ * (rows are independent: GroupNorm is per row, models/diffusion.py:202), so one branch's kernels fill the tail wave and launch gaps
+ * of the other's. Results do not depend on the setting. Batches with fewer than two waves of row tiles per branch use fewer. */
+int osteo_ddpm_set_branches(osteo_ddpm_ctx* ctx, int branches);
 int osteo_ddpm_set_precision(osteo_ddpm_ctx* ctx, int precision);
 /* bf16 mode with hidden_dims[0] <= 256 runs the FUSED reverse step by default: output_proj, the reverse update
  * (models/diffusion.py:400-423) and the NEXT step's input_proj + embedding add (models/diffusion.py:229-232) in one
@@ -143,6 +147,28 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* ctx, const float* x0_dev, const float*
                           int train, uint64_t seed, long long row_base, float* loss_dev,
                           float* const* grads_dev, int n_tensors, void* stream);
 
+/* The same step in two halves, for auxiliary losses on the PREDICTED CLEAN SAMPLE x0hat = (x_t - sqrt(1-ab_t) eps_hat) / sqrt(ab_t)
+ * (models/diffusion.py:401-403) -- the diffusion analogue of the multi-task terms of models/cvae.py:304-341:
+ *   train_forward   forward + MSE loss, keeps what the backward pass needs (arguments as osteo_ddpm_train_step);
+ *   train_x0hat     out_dev [n, n_cols] = x0hat[:, cols_dev[0..n_cols)]  (x0_dev / t_idx_dev: the tensors given to train_forward);
+ *   train_inject    d(loss)/d(eps_hat) += chain rule of g_dev [n, n_cols] = d(aux loss)/d(x0hat[:, cols]); columns must be distinct;
+ *   train_backward  the backward pass into grads_dev (same train / seed / row_base / masks as train_forward). */
+int osteo_ddpm_train_forward(osteo_ddpm_ctx* ctx, const float* x0_dev, const float* cond_dev, long long n, const int* t_idx_dev,
+                             const float* noise_dev, const uint8_t* const* drop_masks_dev, int train, uint64_t seed,
+                             long long row_base, float* loss_dev, void* stream);
+int osteo_ddpm_train_x0hat(osteo_ddpm_ctx* ctx, const float* x0_dev, const int* t_idx_dev, long long n, const int* cols_dev, int n_cols,
+                           float* out_dev, void* stream);
+int osteo_ddpm_train_inject(osteo_ddpm_ctx* ctx, const int* t_idx_dev, long long n, const int* cols_dev, int n_cols,
+                            const float* g_dev, void* stream);
+int osteo_ddpm_train_backward(osteo_ddpm_ctx* ctx, const float* cond_dev, long long n, const int* t_idx_dev,
+                              const uint8_t* const* drop_masks_dev, int train, uint64_t seed, long long row_base,
+                              float* const* grads_dev, int n_tensors, void* stream);
+
+/* With nothing injected (noise_dev == NULL, drop_masks_dev == NULL) and gradients requested, everything of the step after the two
+ * kernels that read x0_dev / cond_dev is replayed as ONE executable graph from the second call with the same n and gradient
+ * addresses on (keep the gradient tensors persistent to benefit); enable = 0 keeps every call eager. Default 1. */
+int osteo_ddpm_set_train_graph(osteo_ddpm_ctx* ctx, int enable);
+
 /* Allocate the transposed weight copies the backward pass contracts against. Must be followed by
  * osteo_ddpm_set_weights (which fills them) before osteo_ddpm_train_step is asked for gradients. */
 int osteo_ddpm_enable_training(osteo_ddpm_ctx* ctx, int enable);
@@ -203,6 +229,20 @@ int osteo_corr_moments(const float* data_dev, long long n, int ld, const int* co
  * out_dev fp64 [n_sets, 1057] = per set {count, sum (x-s) [32], sum (x-s)(x-s)^T [32][32]} over rows [row_begin,row_end), overwritten. */
 int osteo_corr_moments_batched(const float* data_dev, long long n, int ld, int ncols, const int* cols_dev, int n_sets,
                                const float* shift_dev, long long row_begin, long long row_end, double* out_dev, void* stream);
+
+/* ---- differentiable biology losses (the reference has only stubs: models/cvae.py:262-302).
+ * Per column set s of data_dev [n, ld] (cols_dev [n_sets][32] int32, -1 padded; the first `ncols` columns are staged):
+ *   modes_dev[s] == 0      loss_s = 1 - mean_{i<j} Pearson(x_i, x_j)   = 1 - the per-pathway score of validate_pathway_coherence
+ *                                                                        (utils/validation.py:150-157)
+ *   modes_dev[s] == +1/-1  loss_s = max(0, -mode * Pearson(x_0, x_1))  > 0 exactly when validate_mutation_expression_correlation
+ *                                                                        (utils/validation.py:206-214) counts a violation
+ * finish: moments_dev fp64 [n_sets * 1057] = the output of osteo_corr_moments_batched over the same sets (all-reduced over the ranks
+ * of a data-parallel job, so that the loss is the GLOBAL batch's); loss_out_dev fp32 [n_sets]; coef_out_dev fp32 [n_sets * 32 * 4]
+ * (saved for backward).  backward: grad_dev [n, ld] += upstream_dev[s] * d loss_s / d data over this rank's rows (accumulates). */
+int osteo_corr_loss_finish(const double* moments_dev, const int* cols_dev, const float* shift_dev, const int* modes_dev, int n_sets,
+                           float* loss_out_dev, float* coef_out_dev, void* stream);
+int osteo_corr_loss_backward(const float* data_dev, long long n, int ld, const int* cols_dev, int n_sets,
+                             const float* coef_dev, const float* upstream_dev, float* grad_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -38,6 +38,8 @@ SIGNATURES = {
     "osteo_ddpm_set_chunk_rows": (_i, [_vp, _i]),
     "osteo_ddpm_set_precision": (_i, [_vp, _i]),
     "osteo_ddpm_set_fused": (_i, [_vp, _i]),
+    "osteo_ddpm_set_branches": (_i, [_vp, _i]),
+    "osteo_ddpm_set_train_graph": (_i, [_vp, _i]),
     "osteo_ddpm_step_is_fused": (_i, [_vp]),
     "osteo_ddpm_set_weights": (_i, [_vp, C.POINTER(_vp), _i, _vp]),
     "osteo_ddpm_set_schedule": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
@@ -52,6 +54,10 @@ SIGNATURES = {
     "osteo_ddpm_q_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _ll, _i, _u64, _ll, _u32, _vp]),
     "osteo_ddpm_reverse_update": (_i, [_vp, _vp, _vp, _vp, _ll, _i, _u64, _ll, _vp]),
     "osteo_ddpm_train_step": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, C.POINTER(_vp), _i, _u64, _ll, _vp, C.POINTER(_vp), _i, _vp]),
+    "osteo_ddpm_train_forward": (_i, [_vp, _vp, _vp, _ll, _vp, _vp, C.POINTER(_vp), _i, _u64, _ll, _vp, _vp]),
+    "osteo_ddpm_train_x0hat": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _vp, _vp]),
+    "osteo_ddpm_train_inject": (_i, [_vp, _vp, _ll, _vp, _i, _vp, _vp]),
+    "osteo_ddpm_train_backward": (_i, [_vp, _vp, _ll, _vp, C.POINTER(_vp), _i, _u64, _ll, C.POINTER(_vp), _i, _vp]),
     "osteo_ddpm_enable_training": (_i, [_vp, _i]),
     "osteo_ddpm_profile_step": (_i, [_vp, _ll, _i, _u64, _ll, _vp, _i, _vp]),
     "osteo_ddpm_status": (_i, [_vp, _vp]),
@@ -64,6 +70,8 @@ SIGNATURES = {
     "osteo_mmd_partial": (_i, [_vp, _ll, _vp, _ll, _i, _f, _vp, _ll, _ll, _ll, _ll, _i, _vp, _vp]),
     "osteo_corr_moments": (_i, [_vp, _ll, _i, _vp, _i, _vp, _ll, _ll, _vp, _vp]),
     "osteo_corr_moments_batched": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _ll, _ll, _vp, _vp]),
+    "osteo_corr_loss_finish": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
+    "osteo_corr_loss_backward": (_i, [_vp, _ll, _i, _vp, _i, _vp, _vp, _vp, _vp]),
 }
 
 

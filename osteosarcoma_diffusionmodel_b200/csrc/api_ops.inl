@@ -248,8 +248,35 @@ int osteo_corr_moments_batched(const float* data_dev, long long n, int ld, int n
     const long long nchunks = (row_end - row_begin + chunk_rows - 1) / chunk_rows;
     const int sms = current_sms();
     const long long blocks = nchunks < 2LL * sms ? nchunks : 2LL * sms;
-    corr_moments_batched_kernel<<<static_cast<unsigned>(blocks), 32 * n_sets, smem, s>>>(data_dev, ld, ncols, cols_dev, n_sets, shift_dev, row_begin, row_end, chunk_rows,
-                                                                                          out_dev);
+    // the kernel holds a 32 x 32 fp64 moment block per warp in registers (128 per thread): at most 16 warps = 16 sets per launch
+    for (int s0 = 0; s0 < n_sets; s0 += 16) {
+        const int ns = n_sets - s0 < 16 ? n_sets - s0 : 16;
+        corr_moments_batched_kernel<<<static_cast<unsigned>(blocks), 32 * ns, smem, s>>>(data_dev, ld, ncols, cols_dev + s0 * 32, ns, shift_dev + s0 * 32, row_begin, row_end,
+                                                                                          chunk_rows, out_dev + static_cast<size_t>(s0) * CM_STRIDE);
+        OSTEO_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+int osteo_corr_loss_finish(const double* moments_dev, const int* cols_dev, const float* shift_dev, const int* modes_dev, int n_sets, float* loss_out_dev,
+                           float* coef_out_dev, void* stream) {
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (n_sets <= 0 || n_sets > 32) return fail("corr_loss_finish: %d column sets outside [1, 32]", n_sets);
+    corr_loss_finish_kernel<<<(n_sets * 32 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(moments_dev, cols_dev, shift_dev, modes_dev, n_sets, loss_out_dev,
+                                                                                                       coef_out_dev);
+    OSTEO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int osteo_corr_loss_backward(const float* data_dev, long long n, int ld, const int* cols_dev, int n_sets, const float* coef_dev, const float* upstream_dev,
+                             float* grad_dev, void* stream) {
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (n_sets <= 0 || n_sets > 32) return fail("corr_loss_backward: %d column sets outside [1, 32]", n_sets);
+    if (n <= 0) return 0;
+    const int sms = current_sms();
+    const long long blocks = n < 8LL * sms ? n : 8LL * sms;
+    corr_loss_bwd_kernel<<<static_cast<unsigned>(blocks), 32 * n_sets, 0, static_cast<cudaStream_t>(stream)>>>(data_dev, n, ld, cols_dev, n_sets, coef_dev, upstream_dev,
+                                                                                                                grad_dev);
     OSTEO_CUDA(cudaGetLastError());
     return 0;
 }

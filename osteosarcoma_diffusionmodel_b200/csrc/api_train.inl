@@ -37,19 +37,35 @@ static int ensure_train_ws(osteo_ddpm_ctx* c) {
     OSTEO_TRY(make_tmap_bf16(&w.xt_tmap, w.xt_bf.p, cap, 2 * c->DP, 2 * c->DP, BM));
     OSTEO_TRY(w.noise.alloc(static_cast<size_t>(cap) * c->DP * 4));
     for (DevBuf* b : {&w.pre0, &w.cemb, &w.h1, &w.dcemb, &w.dpre0}) OSTEO_TRY(b->alloc(static_cast<size_t>(cap) * c->E * 4));
-    int max_hidden = 0;
-    for (auto& hb : c->halves) max_hidden = hb->lin.n > max_hidden ? hb->lin.n : max_hidden;
-    const size_t part_cols = static_cast<size_t>(3 * max_hidden > c->D ? 3 * max_hidden : c->D);
-    OSTEO_TRY(w.partials.alloc(static_cast<size_t>(cap / 32) * part_cols * 4));
+    {
+        // column partials: [0] MSE epilogue (D columns), [1 + j] GroupNorm backward of half j (3 x width), [H + 1] d(h0)
+        std::vector<size_t> cols{static_cast<size_t>(c->D)};
+        for (auto& hb : c->halves) cols.push_back(static_cast<size_t>(3) * hb->lin.n);
+        cols.push_back(static_cast<size_t>(h0));
+        for (size_t pc : cols) {
+            std::unique_ptr<DevBuf> b(new DevBuf);
+            OSTEO_TRY(b->alloc(static_cast<size_t>(cap / 32) * pc * 4));
+            w.partials.push_back(std::move(b));
+        }
+    }
+    OSTEO_TRY(w.t_copy.alloc(static_cast<size_t>(cap) * sizeof(int)));
+    OSTEO_TRY(w.cond_copy.alloc(static_cast<size_t>(cap) * c->C * sizeof(float)));
+    OSTEO_TRY(w.loss_tmp.alloc(sizeof(float)));
+    c->train_graph.reset();
+    for (int i = 0; i < 2; ++i) {
+        OSTEO_CUDA(cudaStreamCreateWithFlags(&w.side[i], cudaStreamNonBlocking));
+        OSTEO_CUDA(cudaEventCreateWithFlags(&w.ev_join[i], cudaEventDisableTiming));
+    }
+    OSTEO_CUDA(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
     (void)max_w;
     w.cap = cap;
     return 0;
 }
 
-static int finish_partials(osteo_ddpm_ctx* c, long long n, int nq, int N, float* o0, float* o1, float* o2, cudaStream_t s) {
+static int finish_partials(osteo_ddpm_ctx* c, const float* partials, long long n, int nq, int N, float* o0, float* o1, float* o2, cudaStream_t s) {
     const int slabs = static_cast<int>((n + 31) / 32);
     dim3 grid((N + 31) / 32, nq), block(32, 8);
-    partials_finish_kernel<<<grid, block, 0, s>>>(c->train.partials.as<float>(), slabs, nq, N, o0, o1, o2);
+    partials_finish_kernel<<<grid, block, 0, s>>>(partials, slabs, nq, N, o0, o1, o2);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     return 0;
@@ -85,47 +101,12 @@ static int add_dgrad_segments(GemmParams& p, int sel, int k, int a_lo_off, int b
     return 0;
 }
 
-}  // namespace osteo
-
-extern "C" {
-
-int osteo_ddpm_enable_training(osteo_ddpm_ctx* c, int enable) {
-    OSTEO_TRY(check_ctx(c));
-    OSTEO_CUDA(cudaSetDevice(c->device));
-    if (!enable) return 0;
-    if (c->out_proj.wt.p) return 0;
-    OSTEO_CUDA(cudaDeviceSynchronize());
-    for (auto& hb : c->halves) OSTEO_TRY(hb->lin.init_transposed());
-    OSTEO_TRY(c->out_proj.init_transposed());
-    c->have_weights = false;   // W^T copies are filled by the next osteo_ddpm_set_weights
-    return 0;
-}
-
-int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* cond_dev, long long n, const int* t_idx_dev, const float* noise_dev,
-                          const uint8_t* const* drop_masks_dev, int train, uint64_t seed, long long row_base, float* loss_dev, float* const* grads_dev,
-                          int n_tensors, void* stream) {
-    OSTEO_TRY(check_ctx(c));
-    OSTEO_TRY(require_ready(c, n));
-    if (!t_idx_dev) return fail("train_step: t_idx_dev is required");
-    if (!loss_dev) return fail("train_step: loss_dev is required");
-    const bool want_grads = grads_dev != nullptr;
-    const int H = static_cast<int>(c->halves.size());
-    const int expect = osteo_ddpm_num_weight_tensors(static_cast<int>(c->hidden.size()));
-    if (want_grads) {
-        if (n_tensors != expect) return fail("train_step: expected %d gradient tensors, got %d", expect, n_tensors);
-        if (!c->out_proj.wt.p) return fail("train_step: call osteo_ddpm_enable_training(ctx, 1) and osteo_ddpm_set_weights before requesting gradients");
-        for (int i = 0; i < n_tensors; ++i)
-            if (!grads_dev[i]) return fail("train_step: gradient tensor %d is null", i);
-    }
-    OSTEO_CUDA(cudaSetDevice(c->device));
-    OSTEO_TRY(ensure_train_ws(c));
+// The kernels of the training step that read the caller's batch (addresses change from batch to batch: never part of a replayed
+// graph): q_sample fused with operand packing, and the condition path (cond -> cproj, saved pre-activations).
+static int train_pre(osteo_ddpm_ctx* c, const float* x0_dev, const float* cond_dev, long long n, const int* t_idx_dev, const float* noise_dev, unsigned long long seed,
+                     long long row_base, cudaStream_t s) {
     TrainWorkspace& w = c->train;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int D = c->D, DP = c->DP, h0 = c->h0(), E = c->E;
-    const bool x3 = c->x3();
-
-    // ------------------------------------------------------------------ forward
-    zero_double_kernel<<<1, 1, 0, s>>>(c->loss_acc.as<double>());
     train_prepare_kernel<<<grid_for(n * (DP / 4), 256, c->sms), 256, 0, s>>>(x0_dev, noise_dev, t_idx_dev, n, D, c->sqrt_ab.as<float>(), c->sqrt_1mab.as<float>(),
                                                                              w.noise.as<float>(), DP, w.xt_bf.as<__nv_bfloat16>(), 2 * DP, c->lo(DP), seed, row_base);
     OSTEO_CUDA(cudaGetLastError());
@@ -136,37 +117,118 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
                                                                                c->cproj.as<float>(), w.pre0.as<float>(), w.cemb.as<float>());
         OSTEO_CUDA(cudaGetLastError());
     }
-    c->launches += 3;
-    OSTEO_TRY(launch_input_proj(c, 0, n, t_idx_dev, s, &w.xt_tmap));
+    c->launches += 2;
     c->h0_primed = false;      // acts[0] now belongs to this training batch, not to a sampling state
-    for (int i = 0; i < H; ++i) {
-        HalfOpts o;
-        o.train = train != 0;
-        o.seed = seed;
-        o.row_base = row_base;
-        o.save = want_grads;
-        if (drop_masks_dev && c->halves[i]->dropout) o.drop_mask = drop_masks_dev[c->halves[i]->block];
-        OSTEO_TRY(launch_half(c, i, 0, n, o, s));
+    return 0;
+}
+
+// Shared argument checks of the training entry points.
+static int train_check(osteo_ddpm_ctx* c, long long n, const int* t_idx_dev, float* const* grads_dev, int n_tensors, bool want_grads) {
+    OSTEO_TRY(check_ctx(c));
+    OSTEO_TRY(require_ready(c, n));
+    if (!t_idx_dev) return fail("train_step: t_idx_dev is required");
+    if (want_grads) {
+        const int expect = osteo_ddpm_num_weight_tensors(static_cast<int>(c->hidden.size()));
+        if (n_tensors != expect) return fail("train_step: expected %d gradient tensors, got %d", expect, n_tensors);
+        if (!c->out_proj.wt.p) return fail("train_step: call osteo_ddpm_enable_training(ctx, 1) and osteo_ddpm_set_weights before requesting gradients");
+        for (int i = 0; i < n_tensors; ++i)
+            if (!grads_dev[i]) return fail("train_step: gradient tensor %d is null", i);
     }
-    {
-        GemmParams p;
-        out_proj_common(c, p, 0, n);
-        p.target = w.noise.as<float>();
-        p.target_ld = DP;
-        p.grad_scale = static_cast<float>(2.0 / (static_cast<double>(n) * D));
-        p.loss_acc = c->loss_acc.as<double>();
-        if (want_grads) {
-            p.out_bf = w.deps.as<__nv_bfloat16>();
-            p.out_bf_ld = 2 * DP;
-            p.out_lo_off = c->lo(DP);
-            p.col_partials = w.partials.as<float>();
+    OSTEO_CUDA(cudaSetDevice(c->device));
+    return 0;
+}
+
+// x0hat[r, g] = x0[r, col_g] - k_r (eps_hat - noise)[r, col_g],  k_r = sqrt(1 - ab[t_r]) / sqrt(ab[t_r])  -- the predicted clean sample
+// (models/diffusion.py:401-403) at the gathered columns, with (eps_hat - noise) = d(loss)/d(eps_hat) / grad_scale read back from the
+// MSE epilogue's output.
+__global__ void x0hat_gather_kernel(const float* __restrict__ x0, int D, const int* __restrict__ t_idx, const float* __restrict__ sqrt_ab, const float* __restrict__ sqrt_1mab,
+                                    const __nv_bfloat16* __restrict__ deps, int deps_ld, int lo_off, float inv_scale, const int* __restrict__ cols, int G, long long n,
+                                    float* __restrict__ out) {
+    const long long total = n * G;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / G;
+        const int col = cols[i % G];
+        const int t = t_idx[r];
+        float d = __bfloat162float(deps[r * deps_ld + col]);
+        if (lo_off) d += __bfloat162float(deps[r * deps_ld + lo_off + col]);
+        const float k = __ldg(sqrt_1mab + t) / __ldg(sqrt_ab + t);
+        out[i] = x0[r * D + col] - k * d * inv_scale;
+    }
+}
+
+// d(loss)/d(eps_hat)[r, col_g] += -k_r g[r, g] (chain rule through x0hat; g = d(aux loss)/d(x0hat)), and the same amounts into the
+// 32-row column partials the output_proj bias gradient is reduced from. The columns must be distinct.
+__global__ void x0hat_inject_kernel(const int* __restrict__ t_idx, const float* __restrict__ sqrt_ab, const float* __restrict__ sqrt_1mab, __nv_bfloat16* __restrict__ deps,
+                                    int deps_ld, int lo_off, float* __restrict__ partials, int D, const int* __restrict__ cols, int G, long long n,
+                                    const float* __restrict__ g) {
+    const long long total = n * G;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float gv = g[i];
+        if (gv == 0.0f) continue;
+        const long long r = i / G;
+        const int col = cols[i % G];
+        const int t = t_idx[r];
+        const float add = -(__ldg(sqrt_1mab + t) / __ldg(sqrt_ab + t)) * gv;
+        __nv_bfloat16* hi = deps + r * deps_ld + col;
+        float v = __bfloat162float(*hi) + add;
+        if (lo_off) v += __bfloat162float(hi[lo_off]);
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        *hi = h;
+        if (lo_off) hi[lo_off] = __float2bfloat16_rn(v - __bfloat162float(h));
+        atomicAdd(partials + (r >> 5) * D + col, add);
+    }
+}
+
+// Everything of the training step that touches only library-owned buffers plus the gradient tensors: forward from input_proj on,
+// MSE, full backward. `t_idx` / `cond` are either the caller's tensors (eager) or the library's copies of them (graph replay: the
+// captured kernels must not bake caller addresses that change from batch to batch); seed_dev, when set, overrides `seed` as the
+// Philox key of the dropout masks.
+static int train_body(osteo_ddpm_ctx* c, const float* cond_dev, long long n, const int* t_idx_dev, const uint8_t* const* drop_masks_dev, int train,
+                      unsigned long long seed, const unsigned long long* seed_dev, long long row_base, float* loss_dev, float* const* grads_dev, int n_tensors,
+                      cudaStream_t s, int phase = 0) {
+    // phase 0: forward + backward; 1: forward only, with the statistics the backward needs; 2: backward only (after a phase-1 call)
+    const bool want_grads = grads_dev != nullptr || phase == 1;
+    const int H = static_cast<int>(c->halves.size());
+    TrainWorkspace& w = c->train;
+    const int D = c->D, DP = c->DP, h0 = c->h0(), E = c->E;
+    const bool x3 = c->x3();
+
+    if (phase != 2) {
+        // ------------------------------------------------------------------ forward
+        zero_double_kernel<<<1, 1, 0, s>>>(c->loss_acc.as<double>());
+        OSTEO_CUDA(cudaGetLastError());
+        ++c->launches;
+        OSTEO_TRY(launch_input_proj(c, 0, n, t_idx_dev, s, &w.xt_tmap));
+        for (int i = 0; i < H; ++i) {
+            HalfOpts o;
+            o.train = train != 0;
+            o.seed = seed;
+            o.seed_dev = seed_dev;
+            o.row_base = row_base;
+            o.save = want_grads;
+            if (drop_masks_dev && c->halves[i]->dropout) o.drop_mask = drop_masks_dev[c->halves[i]->block];
+            OSTEO_TRY(launch_half(c, i, 0, n, o, s));
         }
-        OSTEO_TRY(after_launch(c, launch_gemm(EPI_MSE, 64, p, c->sms, s), s));
+        {
+            GemmParams p;
+            out_proj_common(c, p, 0, n);
+            p.target = w.noise.as<float>();
+            p.target_ld = DP;
+            p.grad_scale = static_cast<float>(2.0 / (static_cast<double>(n) * D));
+            p.loss_acc = c->loss_acc.as<double>();
+            if (want_grads) {
+                p.out_bf = w.deps.as<__nv_bfloat16>();
+                p.out_bf_ld = 2 * DP;
+                p.out_lo_off = c->lo(DP);
+                p.col_partials = w.partials[0]->as<float>();
+            }
+            OSTEO_TRY(after_launch(c, launch_gemm(EPI_MSE, 64, p, c->sms, s), s));
+        }
+        finish_loss_kernel<<<1, 1, 0, s>>>(c->loss_acc.as<double>(), loss_dev, 1.0 / (static_cast<double>(n) * D));
+        OSTEO_CUDA(cudaGetLastError());
+        ++c->launches;
     }
-    finish_loss_kernel<<<1, 1, 0, s>>>(c->loss_acc.as<double>(), loss_dev, 1.0 / (static_cast<double>(n) * D));
-    OSTEO_CUDA(cudaGetLastError());
-    ++c->launches;
-    if (!want_grads) return 0;
+    if (!want_grads || phase == 1) return 0;
 
     // ------------------------------------------------------------------ backward
     auto numel = [&](int i) -> size_t {
@@ -198,12 +260,26 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
     }
     const int gi_out_w = 10 + 4 * H, gi_out_b = gi_out_w + 1;
 
+    // The dgrad chain (one GEMM per activation, each needing the previous one's output) is the critical path of the backward pass;
+    // the weight / bias gradients only consume its outputs. They run on two side streams that fork from `s` after the producing
+    // kernel and join it again before this call returns, so at training batch sizes (64 row tiles per GEMM: less than one wave)
+    // they fill the SMs the chain leaves idle instead of lengthening it. OSTEO_TRAIN_OVERLAP=0 keeps everything on `s`.
+    static const bool overlap = !(getenv("OSTEO_TRAIN_OVERLAP") && atoi(getenv("OSTEO_TRAIN_OVERLAP")) == 0);
+    cudaStream_t s1 = overlap ? w.side[0] : s, s2 = overlap ? w.side[1] : s;
+    auto fork_to = [&](cudaStream_t side) -> int {      // work enqueued on `side` from here on starts after everything enqueued on `s` so far
+        if (side == s) return 0;
+        OSTEO_CUDA(cudaEventRecord(w.ev_fork, s));
+        OSTEO_CUDA(cudaStreamWaitEvent(side, w.ev_fork, 0));
+        return 0;
+    };
+
     // output_proj: bias gradient from the MSE epilogue's column partials, weight gradient = deps^T . act_last
-    OSTEO_TRY(finish_partials(c, n, 1, D, grads_dev[gi_out_b], nullptr, nullptr, s));
+    OSTEO_TRY(fork_to(s1));
+    OSTEO_TRY(finish_partials(c, w.partials[0]->as<float>(), n, 1, D, grads_dev[gi_out_b], nullptr, nullptr, s1));
     {
         const ActBuf& a = *c->acts.back();
         OSTEO_TRY(after_launch(c, launch_wgrad(w.deps.as<__nv_bfloat16>(), 2 * DP, DP, D, a.ptr(), 2 * a.width, 0, a.width, a.width, grads_dev[gi_out_w], a.width, n, x3,
-                                               c->status_dev.as<int>(), c->sms, s), s));
+                                               c->status_dev.as<int>(), c->sms, s1), s1));
     }
 
     // consumers of an activation: (half index, first input column of that activation inside the consumer's Linear)
@@ -246,7 +322,8 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
         set_rows(p, 0, n);
         p.N = width;
         p.n_tiles = width / BN;
-        p.col_partials = w.partials.as<float>();
+        p.col_partials = w.partials[j >= 0 ? 1 + j : H + 1]->as<float>();
+        cudaStream_t sj = (j & 1) ? s2 : s1;      // alternate: two consecutive halves' weight gradients can overlap each other too
         if (j >= 0) {
             HalfBlock& hb = *c->halves[j];
             p.gamma = hb.gamma.as<float>();
@@ -263,19 +340,21 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
                 p.drop_mask = drop_masks_dev ? drop_masks_dev[hb.block] : nullptr;
                 p.drop_stream = STREAM_DROPOUT + static_cast<uint32_t>(hb.block);
                 p.seed = seed;
+                p.seed_dev = seed_dev;
                 p.row_base = row_base;
             }
             OSTEO_TRY(after_launch(c, launch_gemm(EPI_GN_BWD, hb.gw, p, c->sms, s), s));
             const int gi = 10 + 4 * j;
-            OSTEO_TRY(finish_partials(c, n, 3, width, grads_dev[gi + 2], grads_dev[gi + 3], grads_dev[gi + 1], s));
+            OSTEO_TRY(fork_to(sj));
+            OSTEO_TRY(finish_partials(c, p.col_partials, n, 3, width, grads_dev[gi + 2], grads_dev[gi + 3], grads_dev[gi + 1], sj));
             // weight gradient of this half: one launch per concatenated source
             const ActBuf& a0 = *c->acts[hb.src0];
             OSTEO_TRY(after_launch(c, launch_wgrad(w.dy[j]->as<__nv_bfloat16>(), 2 * width, width, width, a0.ptr(), 2 * a0.width, 0, a0.width, a0.width, grads_dev[gi],
-                                                   hb.lin.k, n, x3, c->status_dev.as<int>(), c->sms, s), s));
+                                                   hb.lin.k, n, x3, c->status_dev.as<int>(), c->sms, sj), sj));
             if (hb.src1 >= 0) {
                 const ActBuf& a1 = *c->acts[hb.src1];
                 OSTEO_TRY(after_launch(c, launch_wgrad(w.dy[j]->as<__nv_bfloat16>(), 2 * width, width, width, a1.ptr(), 2 * a1.width, 0, a1.width, a1.width,
-                                                       grads_dev[gi] + a0.width, hb.lin.k, n, x3, c->status_dev.as<int>(), c->sms, s), s));
+                                                       grads_dev[gi] + a0.width, hb.lin.k, n, x3, c->status_dev.as<int>(), c->sms, sj), sj));
             }
         } else {
             // d(h0): plain epilogue, kept as bf16 (wgrad operand) and fp32 (embedding paths)
@@ -286,17 +365,20 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
             p.out_f32_ld = h0;
             p.step = nullptr;
             OSTEO_TRY(after_launch(c, launch_gemm(EPI_LINEAR, 64, p, c->sms, s), s));
-            OSTEO_TRY(finish_partials(c, n, 1, h0, grads_dev[5], nullptr, nullptr, s));
-            OSTEO_CUDA(cudaMemcpyAsync(grads_dev[7], grads_dev[5], sizeof(float) * h0, cudaMemcpyDeviceToDevice, s));
-            OSTEO_CUDA(cudaMemcpyAsync(grads_dev[9], grads_dev[5], sizeof(float) * h0, cudaMemcpyDeviceToDevice, s));
         }
     }
-    // input_proj weight gradient: dh0^T . x_t
+    // Everything below needs only d(h0). Side stream 1: input_proj weight gradient (dh0^T . x_t, the largest wgrad); side stream 2: the
+    // three bias gradients that equal colsum(d(h0)) and the time_proj / cond_proj weight gradients; `s`: the ConditionalEmbedding chain.
+    OSTEO_TRY(fork_to(s1));
+    OSTEO_TRY(fork_to(s2));
     OSTEO_TRY(after_launch(c, launch_wgrad(w.dh0_bf.as<__nv_bfloat16>(), 2 * h0, h0, h0, w.xt_bf.as<__nv_bfloat16>(), 2 * DP, 0, DP, D, grads_dev[4], D, n, x3, c->status_dev.as<int>(),
-                                           c->sms, s), s));
+                                           c->sms, s1), s1));
+    OSTEO_TRY(finish_partials(c, w.partials[H + 1]->as<float>(), n, 1, h0, grads_dev[5], nullptr, nullptr, s2));
+    OSTEO_CUDA(cudaMemcpyAsync(grads_dev[7], grads_dev[5], sizeof(float) * h0, cudaMemcpyDeviceToDevice, s2));
+    OSTEO_CUDA(cudaMemcpyAsync(grads_dev[9], grads_dev[5], sizeof(float) * h0, cudaMemcpyDeviceToDevice, s2));
     // time_proj / cond_proj / ConditionalEmbedding (fp32 CUDA-core kernels; tiny matrices)
-    OSTEO_TRY(outer_accum(c, w.dh0_f32.as<float>(), h0, c->emb_table.as<float>(), c->TD, t_idx_dev, n, grads_dev[8], s));
-    OSTEO_TRY(outer_accum(c, w.dh0_f32.as<float>(), h0, w.cemb.as<float>(), E, nullptr, n, grads_dev[6], s));
+    OSTEO_TRY(outer_accum(c, w.dh0_f32.as<float>(), h0, c->emb_table.as<float>(), c->TD, t_idx_dev, n, grads_dev[8], s2));
+    OSTEO_TRY(outer_accum(c, w.dh0_f32.as<float>(), h0, w.cemb.as<float>(), E, nullptr, n, grads_dev[6], s2));
     {
         const size_t smem = sizeof(float) * 8 * (h0 + E);
         // Wc^T view: cond_bwd needs Wc as [h0, E] row-major, which is exactly cond_proj.weight's layout.
@@ -314,6 +396,121 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
     }
     OSTEO_TRY(outer_accum(c, w.dcemb.as<float>(), E, w.h1.as<float>(), E, nullptr, n, grads_dev[2], s));
     OSTEO_TRY(outer_accum(c, w.dpre0.as<float>(), E, cond_dev, c->C, nullptr, n, grads_dev[0], s));
+    for (int i = 0; i < 2 && overlap; ++i) {
+        OSTEO_CUDA(cudaEventRecord(w.ev_join[i], w.side[i]));
+        OSTEO_CUDA(cudaStreamWaitEvent(s, w.ev_join[i], 0));
+    }
+    return 0;
+}
+
+
+}  // namespace osteo
+
+extern "C" {
+
+int osteo_ddpm_enable_training(osteo_ddpm_ctx* c, int enable) {
+    OSTEO_TRY(check_ctx(c));
+    OSTEO_CUDA(cudaSetDevice(c->device));
+    if (!enable) return 0;
+    if (c->out_proj.wt.p) return 0;
+    OSTEO_CUDA(cudaDeviceSynchronize());
+    for (auto& hb : c->halves) OSTEO_TRY(hb->lin.init_transposed());
+    OSTEO_TRY(c->out_proj.init_transposed());
+    c->have_weights = false;   // W^T copies are filled by the next osteo_ddpm_set_weights
+    return 0;
+}
+
+int osteo_ddpm_set_train_graph(osteo_ddpm_ctx* c, int enable) {
+    OSTEO_TRY(check_ctx(c));
+    c->train_graph_enable = enable ? 1 : 0;
+    if (!enable) c->train_graph.reset();
+    return 0;
+}
+
+int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* cond_dev, long long n, const int* t_idx_dev, const float* noise_dev,
+                          const uint8_t* const* drop_masks_dev, int train, uint64_t seed, long long row_base, float* loss_dev, float* const* grads_dev,
+                          int n_tensors, void* stream) {
+    if (!loss_dev) return fail("train_step: loss_dev is required");
+    const bool want_grads = grads_dev != nullptr;
+    OSTEO_TRY(train_check(c, n, t_idx_dev, grads_dev, n_tensors, want_grads));
+    OSTEO_TRY(ensure_train_ws(c));
+    TrainWorkspace& w = c->train;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    w.fwd_n = want_grads ? n : -1;
+
+    OSTEO_TRY(train_pre(c, x0_dev, cond_dev, n, t_idx_dev, noise_dev, seed, row_base, s));
+
+    // ---- everything else: forward from input_proj on, MSE, backward. Replayed as ONE graph launch when nothing is injected: at
+    // batch 8192 the ~120 launches of a step cost more host time than device time (scripts/train_probe.py).
+    const bool graphable = want_grads && c->train_graph_enable && !noise_dev && !drop_masks_dev && !c->prof;
+    if (!graphable) return train_body(c, cond_dev, n, t_idx_dev, drop_masks_dev, train, seed, nullptr, row_base, loss_dev, grads_dev, n_tensors, s);
+    OSTEO_CUDA(cudaMemcpyAsync(w.t_copy.p, t_idx_dev, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
+    OSTEO_CUDA(cudaMemcpyAsync(w.cond_copy.p, cond_dev, sizeof(float) * n * c->C, cudaMemcpyDeviceToDevice, s));
+    set_u64_kernel<<<1, 1, 0, s>>>(c->seed_dev.as<unsigned long long>(), seed);
+    OSTEO_CUDA(cudaGetLastError());
+    c->launches += 3;
+    std::vector<unsigned long long> key{static_cast<unsigned long long>(n), static_cast<unsigned long long>(train != 0), static_cast<unsigned long long>(row_base),
+                                        static_cast<unsigned long long>(c->precision), static_cast<unsigned long long>(c->ws_enable),
+                                        reinterpret_cast<unsigned long long>(c->acts[0]->ptr()), reinterpret_cast<unsigned long long>(w.deps.p),
+                                        reinterpret_cast<unsigned long long>(c->out_proj.wt.p)};
+    for (int i = 0; i < n_tensors; ++i) key.push_back(reinterpret_cast<unsigned long long>(grads_dev[i]));
+    OSTEO_TRY(run_cached(c, c->train_graph, key, s, [&](cudaStream_t q) {
+        return train_body(c, w.cond_copy.as<float>(), n, w.t_copy.as<int>(), nullptr, train, seed, c->seed_dev.as<unsigned long long>(), row_base, w.loss_tmp.as<float>(),
+                          grads_dev, n_tensors, q);
+    }));
+    OSTEO_CUDA(cudaMemcpyAsync(loss_dev, w.loss_tmp.p, sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return 0;
+}
+
+// ---- the training step in two halves, for auxiliary losses on the predicted clean sample: forward, then the
+// caller reads x0hat at the columns its losses need, injects d(aux)/d(x0hat), and runs the backward pass.
+int osteo_ddpm_train_forward(osteo_ddpm_ctx* c, const float* x0_dev, const float* cond_dev, long long n, const int* t_idx_dev, const float* noise_dev,
+                             const uint8_t* const* drop_masks_dev, int train, uint64_t seed, long long row_base, float* loss_dev, void* stream) {
+    if (!loss_dev) return fail("train_forward: loss_dev is required");
+    OSTEO_TRY(train_check(c, n, t_idx_dev, nullptr, 0, false));
+    if (!c->out_proj.wt.p) return fail("train_forward: call osteo_ddpm_enable_training(ctx, 1) and osteo_ddpm_set_weights first");
+    OSTEO_TRY(ensure_train_ws(c));
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OSTEO_TRY(train_pre(c, x0_dev, cond_dev, n, t_idx_dev, noise_dev, seed, row_base, s));
+    OSTEO_TRY(train_body(c, cond_dev, n, t_idx_dev, drop_masks_dev, train, seed, nullptr, row_base, loss_dev, nullptr, 0, s, /*phase=*/1));
+    c->train.fwd_n = n;
+    return 0;
+}
+
+int osteo_ddpm_train_x0hat(osteo_ddpm_ctx* c, const float* x0_dev, const int* t_idx_dev, long long n, const int* cols_dev, int n_cols, float* out_dev, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    TrainWorkspace& w = c->train;
+    if (w.fwd_n != n || n <= 0) return fail("train_x0hat: no forward pass of %lld rows is pending (osteo_ddpm_train_forward)", n);
+    if (n_cols <= 0) return fail("train_x0hat: n_cols must be positive");
+    const float inv_scale = static_cast<float>(static_cast<double>(n) * c->D / 2.0);
+    x0hat_gather_kernel<<<grid_for(n * n_cols, 256, c->sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(x0_dev, c->D, t_idx_dev, c->sqrt_ab.as<float>(), c->sqrt_1mab.as<float>(),
+                                                                                                        w.deps.as<__nv_bfloat16>(), 2 * c->DP, c->lo(c->DP), inv_scale, cols_dev,
+                                                                                                        n_cols, n, out_dev);
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+int osteo_ddpm_train_inject(osteo_ddpm_ctx* c, const int* t_idx_dev, long long n, const int* cols_dev, int n_cols, const float* g_dev, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    TrainWorkspace& w = c->train;
+    if (w.fwd_n != n || n <= 0) return fail("train_inject: no forward pass of %lld rows is pending (osteo_ddpm_train_forward)", n);
+    if (n_cols <= 0) return fail("train_inject: n_cols must be positive");
+    x0hat_inject_kernel<<<grid_for(n * n_cols, 256, c->sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(t_idx_dev, c->sqrt_ab.as<float>(), c->sqrt_1mab.as<float>(),
+                                                                                                        w.deps.as<__nv_bfloat16>(), 2 * c->DP, c->lo(c->DP),
+                                                                                                        w.partials[0]->as<float>(), c->D, cols_dev, n_cols, n, g_dev);
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
+int osteo_ddpm_train_backward(osteo_ddpm_ctx* c, const float* cond_dev, long long n, const int* t_idx_dev, const uint8_t* const* drop_masks_dev, int train, uint64_t seed,
+                              long long row_base, float* const* grads_dev, int n_tensors, void* stream) {
+    if (!grads_dev) return fail("train_backward: grads_dev is required");
+    OSTEO_TRY(train_check(c, n, t_idx_dev, grads_dev, n_tensors, true));
+    if (c->train.fwd_n != n) return fail("train_backward: no forward pass of %lld rows is pending (osteo_ddpm_train_forward)", n);
+    OSTEO_TRY(train_body(c, cond_dev, n, t_idx_dev, drop_masks_dev, train, seed, nullptr, row_base, nullptr, grads_dev, n_tensors, static_cast<cudaStream_t>(stream), /*phase=*/2));
+    c->train.fwd_n = -1;
     return 0;
 }
 

@@ -307,8 +307,10 @@ __global__ void unpack_hilo_kernel(const __nv_bfloat16* __restrict__ src, long l
     }
 }
 
-__global__ void set_int_kernel(int* p, int v) { *p = v; }
-__global__ void add_int_kernel(int* p, int v) { *p += v; }
+// one thread per word (the per-branch step words of the sampling graphs)
+__global__ void set_int_kernel(int* p, int v) { p[threadIdx.x] = v; }
+__global__ void add_int_kernel(int* p, int v) { p[threadIdx.x] += v; }
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 __global__ void finish_loss_kernel(const double* acc, float* out, double scale) { *out = static_cast<float>(*acc * scale); }
 
 }  // namespace osteo

@@ -128,6 +128,7 @@ struct GemmParams {
     float* eps_out;           // optional fp32 eps [M, eps_ld]
     int eps_ld;
     unsigned long long seed;
+    const unsigned long long* seed_dev;   // when set, the Philox key of the dropout masks is read from this device word (graph-replayed training step)
     // EPI_MSE
     const float* target;      // noise [M, target_ld]
     int target_ld;
@@ -862,7 +863,7 @@ struct Epilogue<EPI_GN_SILU> {
             } else {
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                    const uint4 w = philox_words(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>((col >> 2) + j4), p.drop_stream, p.step ? static_cast<uint32_t>(*p.step) : 0u);
+                    const uint4 w = philox_words(p.seed_dev ? *p.seed_dev : p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>((col >> 2) + j4), p.drop_stream, p.step ? static_cast<uint32_t>(*p.step) : 0u);
                     v[4 * j4 + 0] = (u01(w.x) >= p.drop_p) ? v[4 * j4 + 0] * keep_scale : 0.0f;
                     v[4 * j4 + 1] = (u01(w.y) >= p.drop_p) ? v[4 * j4 + 1] * keep_scale : 0.0f;
                     v[4 * j4 + 2] = (u01(w.z) >= p.drop_p) ? v[4 * j4 + 2] * keep_scale : 0.0f;
@@ -1153,7 +1154,7 @@ struct Epilogue<EPI_GN_BWD> {
                 } else {
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
-                        const uint4 w = philox_words(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>((c0 >> 2) + j4), p.drop_stream, 0u);
+                        const uint4 w = philox_words(p.seed_dev ? *p.seed_dev : p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>((c0 >> 2) + j4), p.drop_stream, 0u);
                         v[4 * j4 + 0] = (u01(w.x) >= p.drop_p) ? v[4 * j4 + 0] * keep_scale : 0.0f;
                         v[4 * j4 + 1] = (u01(w.y) >= p.drop_p) ? v[4 * j4 + 1] * keep_scale : 0.0f;
                         v[4 * j4 + 2] = (u01(w.z) >= p.drop_p) ? v[4 * j4 + 2] * keep_scale : 0.0f;

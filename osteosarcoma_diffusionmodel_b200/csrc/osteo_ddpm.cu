@@ -157,6 +157,21 @@ struct HalfBlock {
 
 using namespace osteo;
 
+// A cached executable graph of one host-side enqueue sequence (weight repack, training step). The FIRST call with a given key runs
+// eagerly (it may allocate, set function attributes ...), the second one captures the same sequence on an internal stream, and
+// every later call with that key is a single cudaGraphLaunch. A different key drops the graph and starts over.
+struct GraphSlot {
+    std::vector<unsigned long long> key;
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;
+    void reset() {
+        if (exec) cudaGraphExecDestroy(exec);
+        exec = nullptr;
+        key.clear();
+    }
+    ~GraphSlot() { reset(); }
+};
+
 struct osteo_ddpm_ctx {
     int device = 0, sms = 0;
     int D = 0, C = 0, TD = 0, E = 0, T = 0;
@@ -197,7 +212,8 @@ struct osteo_ddpm_ctx {
     long long h0_n = 0;
     std::vector<std::unique_ptr<ActBuf>> acts;   // [0] = h0, then one per half block
     DevBuf cproj;                        // fp32 [cap, h0]
-    DevBuf step_dev, status_dev;
+    DevBuf step_dev, status_dev;      // step_dev: MAX_BRANCHES step words (equal outside a graph replay), one per row branch
+    int branches = 2, cur_branch = 0;
     DevBuf loss_acc;                     // fp64 scalar
     TrainWorkspace train;
 
@@ -206,9 +222,13 @@ struct osteo_ddpm_ctx {
     long long graph_n = -1;
     unsigned long long graph_seed = 0;
     long long graph_row_base = 0;
-    int graph_precision = -1, graph_chunk = -1, graph_fused = -1;
+    int graph_precision = -1, graph_chunk = -1, graph_fused = -1, graph_branches = -1;
     long long graph_launches_per_step = 0;
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every GEMM launch
+    // graph caches of the training path (api_train.inl): weight repack after an optimizer step, forward + backward
+    GraphSlot weights_graph, train_graph;
+    int train_graph_enable = 1;
+    DevBuf seed_dev;                     // u64: Philox key of the graph-replayed training step
 
     bool x3() const { return precision == OSTEO_PREC_FP32X3; }
     bool fused_ok() const { return fused_enable && precision == OSTEO_PREC_BF16 && hidden[0] <= 256; }
@@ -234,7 +254,7 @@ static int check_ctx(const osteo_ddpm_ctx* c) {
 static void base_params(const osteo_ddpm_ctx* c, GemmParams& p) {
     std::memset(&p, 0, sizeof p);
     p.status = c->status_dev.as<int>();
-    p.step = c->step_dev.as<int>();
+    p.step = c->step_dev.as<int>() + c->cur_branch;
     p.gn_eps = 1e-5f;
 }
 
@@ -286,6 +306,7 @@ struct HalfOpts {
     bool train = false;
     const uint8_t* drop_mask = nullptr;
     unsigned long long seed = 0;
+    const unsigned long long* seed_dev = nullptr;
     long long row_base = 0;
     bool save = false;
 };
@@ -330,6 +351,7 @@ static int launch_half(osteo_ddpm_ctx* c, int hi, long long row0, long long row1
         p.drop_mask = o.drop_mask;
         p.drop_stream = STREAM_DROPOUT + static_cast<uint32_t>(hb.block);
         p.seed = o.seed;
+        p.seed_dev = o.seed_dev;
         p.row_base = o.row_base;
         p.step = nullptr;
     }
@@ -419,7 +441,7 @@ static int launch_fused(osteo_ddpm_ctx* c, long long row0, long long row1, const
     p.nkb = c->h0() / BK;
     p.h0 = c->h0();
     p.status = c->status_dev.as<int>();
-    p.step = c->step_dev.as<int>();
+    p.step = c->step_dev.as<int>() + c->cur_branch;
     p.coef_x = c->coef_x.as<float>();
     p.coef_eps = c->coef_eps.as<float>();
     p.coef_sigma = c->coef_sigma.as<float>();
@@ -474,13 +496,15 @@ static long long chunk_of(const osteo_ddpm_ctx* c, long long n) {
 
 // Enqueue one full reverse step over rows [0, n); the timestep is read from the device word.
 // Fused path: acts[0] must already hold this step's h0 (ensure_primed); the step leaves the NEXT step's h0 there.
-static int enqueue_reverse_step(osteo_ddpm_ctx* c, long long n, const float* noise, float* eps_out, unsigned long long seed, long long row_base, cudaStream_t s) {
+static int enqueue_reverse_step(osteo_ddpm_ctx* c, long long n, const float* noise, float* eps_out, unsigned long long seed, long long row_base, cudaStream_t s,
+                                long long rb = 0, long long re = -1) {
     if (c->x_c8 != c->fused_ok())
         return fail("the state was loaded under a different precision / fused setting: call load_state or init_noise again");
+    if (re < 0) re = n;
     const long long ch = chunk_of(c, n);
     HalfOpts o;
-    for (long long r0 = 0; r0 < n; r0 += ch) {
-        const long long r1 = r0 + ch < n ? r0 + ch : n;
+    for (long long r0 = rb; r0 < re; r0 += ch) {
+        const long long r1 = r0 + ch < re ? r0 + ch : re;
         if (!c->x_c8) OSTEO_TRY(launch_input_proj(c, r0, r1, nullptr, s));
         for (size_t i = 0; i < c->halves.size(); ++i) OSTEO_TRY(launch_half(c, static_cast<int>(i), r0, r1, o, s));
         if (c->x_c8) OSTEO_TRY(launch_fused(c, r0, r1, noise, eps_out, seed, row_base, s));
@@ -517,32 +541,107 @@ static void after_steps(osteo_ddpm_ctx* c, int t, int steps) {
 }
 
 constexpr int GRAPH_UNROLL = 10;
+constexpr int MAX_BRANCHES = 4;
 
-// Capture `count` consecutive reverse steps (each followed by the decrement of the device step word) into an executable graph.
+// Capture `count` consecutive reverse steps into an executable graph. Rows are independent, so the batch is split into
+// `branches` contiguous row ranges (128-row aligned) captured as parallel graph branches: each branch is its own chain of
+// count x (10 block GEMMs + fused tail) with its OWN device step word, decremented after each of its steps, and the branches only
+// join at the end of the graph. A persistent kernel's tail wave (782 row tiles on 148 SMs = 5.28 waves), its prologue and the
+// launch gap of one branch are then filled by the other branch's kernels instead of idling the SMs.
 static int capture_steps(osteo_ddpm_ctx* c, long long n, unsigned long long seed, long long row_base, int count, cudaGraphExec_t* out) {
-    cudaStream_t cs;
-    OSTEO_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    const long long tiles = (n + BM - 1) / BM;
+    int nb = c->branches < 1 ? 1 : (c->branches > MAX_BRANCHES ? MAX_BRANCHES : c->branches);
+    if (const char* e = getenv("OSTEO_DDPM_BRANCHES")) nb = atoi(e) < 1 ? 1 : (atoi(e) > MAX_BRANCHES ? MAX_BRANCHES : atoi(e));
+    while (nb > 1 && tiles < 2LL * c->sms * nb) --nb;  // small batches: less than two waves per branch would only add launches
+    cudaStream_t cs[MAX_BRANCHES] = {};
+    cudaEvent_t fork = nullptr, join[MAX_BRANCHES] = {};
     cudaGraph_t graph = nullptr;
-    OSTEO_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
-    for (int i = 0; i < count && rc == 0; ++i) {
-        rc = enqueue_reverse_step(c, n, nullptr, nullptr, seed, row_base, cs);
-        if (rc == 0) {
-            add_int_kernel<<<1, 1, 0, cs>>>(c->step_dev.as<int>(), -1);
+    cudaError_t ce = cudaSuccess;
+    for (int b = 0; b < nb && ce == cudaSuccess; ++b) ce = cudaStreamCreateWithFlags(&cs[b], cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&fork, cudaEventDisableTiming);
+    for (int b = 1; b < nb && ce == cudaSuccess; ++b) ce = cudaEventCreateWithFlags(&join[b], cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaStreamBeginCapture(cs[0], cudaStreamCaptureModeThreadLocal);
+    if (ce == cudaSuccess) {
+        if (nb > 1) ce = cudaEventRecord(fork, cs[0]);
+        for (int b = 1; b < nb && ce == cudaSuccess; ++b) ce = cudaStreamWaitEvent(cs[b], fork, 0);
+        for (int b = 0; b < nb && rc == 0 && ce == cudaSuccess; ++b) {
+            const long long rb = (tiles * b / nb) * BM, re_ = (tiles * (b + 1) / nb) * BM;
+            const long long re = re_ < n ? re_ : n;
+            c->cur_branch = b;
+            for (int i = 0; i < count && rc == 0; ++i) {
+                rc = enqueue_reverse_step(c, n, nullptr, nullptr, seed, row_base, cs[b], rb, re);
+                if (rc == 0) {
+                    add_int_kernel<<<1, 1, 0, cs[b]>>>(c->step_dev.as<int>() + b, -1);
+                    ++c->launches;
+                }
+            }
+            if (b > 0 && rc == 0) {
+                ce = cudaEventRecord(join[b], cs[b]);
+                if (ce == cudaSuccess) ce = cudaStreamWaitEvent(cs[0], join[b], 0);
+            }
+        }
+        c->cur_branch = 0;
+        if (rc == 0 && ce == cudaSuccess && nb < MAX_BRANCHES) {      // unused step words follow along so that all words stay equal
+            add_int_kernel<<<1, MAX_BRANCHES - nb, 0, cs[0]>>>(c->step_dev.as<int>() + nb, -count);
             ++c->launches;
         }
+        const cudaError_t ce2 = cudaStreamEndCapture(cs[0], &graph);
+        if (ce == cudaSuccess) ce = ce2;
     }
-    cudaError_t ce = cudaStreamEndCapture(cs, &graph);
-    cudaStreamDestroy(cs);
+    for (int b = 0; b < nb; ++b) if (cs[b]) cudaStreamDestroy(cs[b]);
+    if (fork) cudaEventDestroy(fork);
+    for (int b = 1; b < nb; ++b) if (join[b]) cudaEventDestroy(join[b]);
     if (rc != 0) {
         if (graph) cudaGraphDestroy(graph);
         return rc;
     }
-    if (ce != cudaSuccess) return fail("graph capture failed: %s", cudaGetErrorString(ce));
+    if (ce != cudaSuccess) {
+        if (graph) cudaGraphDestroy(graph);
+        return fail("graph capture failed: %s", cudaGetErrorString(ce));
+    }
     ce = cudaGraphInstantiate(out, graph, 0);
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) return fail("graph instantiate failed: %s", cudaGetErrorString(ce));
     return 0;
+}
+
+// See GraphSlot. `enqueue(stream)` must be a pure function of `key` and of device memory contents.
+template <class F>
+static int run_cached(osteo_ddpm_ctx* c, GraphSlot& slot, const std::vector<unsigned long long>& key, cudaStream_t s, F&& enqueue) {
+    if (slot.exec && slot.key == key) {
+        OSTEO_CUDA(cudaGraphLaunch(slot.exec, s));
+        c->launches += slot.launches;
+        return 0;
+    }
+    if (!slot.exec && !slot.key.empty() && slot.key == key && !c->prof) {
+        cudaStream_t cs = nullptr;
+        OSTEO_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+        int rc = 0;
+        const long long before = c->launches;
+        if (ce == cudaSuccess) {
+            rc = enqueue(cs);
+            ce = cudaStreamEndCapture(cs, &graph);
+        }
+        slot.launches = c->launches - before;
+        c->launches = before;
+        cudaStreamDestroy(cs);
+        if (rc == 0 && ce == cudaSuccess) ce = cudaGraphInstantiate(&slot.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != 0 || ce != cudaSuccess) {
+            slot.reset();
+            cudaGetLastError();
+            return rc != 0 ? rc : fail("graph capture failed: %s", cudaGetErrorString(ce));
+        }
+        OSTEO_CUDA(cudaGraphLaunch(slot.exec, s));
+        c->launches += slot.launches;
+        return 0;
+    }
+    slot.reset();
+    slot.key = key;
+    return enqueue(s);
 }
 
 static int require_ready(const osteo_ddpm_ctx* c, long long n) {
@@ -622,10 +721,11 @@ int osteo_ddpm_create(osteo_ddpm_ctx** out, int device, int data_dim, int cond_d
     OSTEO_TRY(c->emb_table.alloc(sizeof(float) * c->T * c->TD));
     OSTEO_TRY(c->time_table.alloc(sizeof(float) * c->T * h0));
     for (DevBuf* b : {&c->sqrt_ab, &c->sqrt_1mab, &c->coef_x, &c->coef_eps, &c->coef_sigma}) OSTEO_TRY(b->alloc(sizeof(float) * c->T));
-    OSTEO_TRY(c->step_dev.alloc(sizeof(int)));
+    OSTEO_TRY(c->step_dev.alloc(MAX_BRANCHES * sizeof(int)));
+    OSTEO_TRY(c->seed_dev.alloc(sizeof(unsigned long long)));
     OSTEO_TRY(c->status_dev.alloc(sizeof(int)));
     OSTEO_TRY(c->loss_acc.alloc(sizeof(double)));
-    OSTEO_CUDA(cudaMemset(c->step_dev.p, 0, sizeof(int)));
+    OSTEO_CUDA(cudaMemset(c->step_dev.p, 0, MAX_BRANCHES * sizeof(int)));
     OSTEO_CUDA(cudaMemset(c->status_dev.p, 0, sizeof(int)));
 
     OSTEO_TRY(c->in_proj.init(h0, data_dim));
@@ -705,6 +805,12 @@ int osteo_ddpm_set_chunk_rows(osteo_ddpm_ctx* c, int chunk_rows) {
     c->chunk_rows = chunk_rows;
     return 0;
 }
+int osteo_ddpm_set_branches(osteo_ddpm_ctx* c, int branches) {
+    OSTEO_TRY(check_ctx(c));
+    if (branches < 1 || branches > MAX_BRANCHES) return fail("branches must be in [1, %d]", MAX_BRANCHES);
+    c->branches = branches;
+    return 0;
+}
 int osteo_ddpm_set_precision(osteo_ddpm_ctx* c, int precision) {
     OSTEO_TRY(check_ctx(c));
     if (precision != OSTEO_PREC_BF16 && precision != OSTEO_PREC_FP32X3) return fail("unknown precision %d", precision);
@@ -770,37 +876,48 @@ int osteo_ddpm_set_weights(osteo_ddpm_ctx* c, const float* const* w, int n_tenso
     for (int i = 0; i < n_tensors; ++i)
         if (!w[i]) return fail("weight tensor %d is null", i);
     OSTEO_CUDA(cudaSetDevice(c->device));
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    auto copy = [&](DevBuf& dst, const float* src) -> int {
-        OSTEO_CUDA(cudaMemcpyAsync(dst.p, src, dst.bytes, cudaMemcpyDeviceToDevice, s));
-        return 0;
+    cudaStream_t s0 = static_cast<cudaStream_t>(stream);
+    // After every optimizer step the same 52 tensors are repacked (bf16 [hi|lo] operands, transposes for the backward pass, the
+    // time table): ~30 small launches, replayed as one graph from the third call with the same addresses on (see GraphSlot).
+    auto enqueue = [&](cudaStream_t s) -> int {
+        auto copy = [&](DevBuf& dst, const float* src) -> int {
+            OSTEO_CUDA(cudaMemcpyAsync(dst.p, src, dst.bytes, cudaMemcpyDeviceToDevice, s));
+            return 0;
+        };
+        OSTEO_TRY(copy(c->ce_w0, w[0]));
+        OSTEO_TRY(copy(c->ce_b0, w[1]));
+        OSTEO_TRY(copy(c->ce_w2, w[2]));
+        OSTEO_TRY(copy(c->ce_b2, w[3]));
+        OSTEO_TRY(c->in_proj.upload(w[4], w[5], c->sms, s));
+        OSTEO_TRY(copy(c->cp_w, w[6]));
+        OSTEO_TRY(copy(c->cp_b, w[7]));
+        OSTEO_TRY(copy(c->tp_w, w[8]));
+        OSTEO_TRY(copy(c->tp_b, w[9]));
+        transpose_f32_kernel<<<(c->E * c->C + 255) / 256, 256, 0, s>>>(c->ce_w0.as<float>(), c->E, c->C, c->ce_w0t.as<float>());
+        transpose_f32_kernel<<<(c->E * c->E + 255) / 256, 256, 0, s>>>(c->ce_w2.as<float>(), c->E, c->E, c->ce_w2t.as<float>());
+        transpose_f32_kernel<<<(c->h0() * c->E + 255) / 256, 256, 0, s>>>(c->cp_w.as<float>(), c->h0(), c->E, c->cp_wt.as<float>());
+        transpose_f32_kernel<<<(c->h0() * c->TD + 255) / 256, 256, 0, s>>>(c->tp_w.as<float>(), c->h0(), c->TD, c->tp_wt.as<float>());
+        OSTEO_CUDA(cudaGetLastError());
+        int idx = 10;
+        for (auto& hb : c->halves) {
+            OSTEO_TRY(hb->lin.upload(w[idx], w[idx + 1], c->sms, s));
+            OSTEO_TRY(copy(hb->gamma, w[idx + 2]));
+            OSTEO_TRY(copy(hb->beta, w[idx + 3]));
+            idx += 4;
+        }
+        OSTEO_TRY(c->out_proj.upload(w[idx], w[idx + 1], c->sms, s));
+        c->launches += 2 + static_cast<long long>(c->halves.size());
+        return rebuild_time_table(c, s);
     };
-    OSTEO_TRY(copy(c->ce_w0, w[0]));
-    OSTEO_TRY(copy(c->ce_b0, w[1]));
-    OSTEO_TRY(copy(c->ce_w2, w[2]));
-    OSTEO_TRY(copy(c->ce_b2, w[3]));
-    OSTEO_TRY(c->in_proj.upload(w[4], w[5], c->sms, s));
-    OSTEO_TRY(copy(c->cp_w, w[6]));
-    OSTEO_TRY(copy(c->cp_b, w[7]));
-    OSTEO_TRY(copy(c->tp_w, w[8]));
-    OSTEO_TRY(copy(c->tp_b, w[9]));
-    transpose_f32_kernel<<<(c->E * c->C + 255) / 256, 256, 0, s>>>(c->ce_w0.as<float>(), c->E, c->C, c->ce_w0t.as<float>());
-    transpose_f32_kernel<<<(c->E * c->E + 255) / 256, 256, 0, s>>>(c->ce_w2.as<float>(), c->E, c->E, c->ce_w2t.as<float>());
-    transpose_f32_kernel<<<(c->h0() * c->E + 255) / 256, 256, 0, s>>>(c->cp_w.as<float>(), c->h0(), c->E, c->cp_wt.as<float>());
-    transpose_f32_kernel<<<(c->h0() * c->TD + 255) / 256, 256, 0, s>>>(c->tp_w.as<float>(), c->h0(), c->TD, c->tp_wt.as<float>());
-    OSTEO_CUDA(cudaGetLastError());
-    int idx = 10;
-    for (auto& hb : c->halves) {
-        OSTEO_TRY(hb->lin.upload(w[idx], w[idx + 1], c->sms, s));
-        OSTEO_TRY(copy(hb->gamma, w[idx + 2]));
-        OSTEO_TRY(copy(hb->beta, w[idx + 3]));
-        idx += 4;
-    }
-    OSTEO_TRY(c->out_proj.upload(w[idx], w[idx + 1], c->sms, s));
-    c->launches += 2 + static_cast<long long>(c->halves.size());
-    c->have_weights = true;
+    std::vector<unsigned long long> key{static_cast<unsigned long long>(c->precision), reinterpret_cast<unsigned long long>(c->out_proj.wt.p),
+                                        static_cast<unsigned long long>(c->have_emb)};
+    for (int i = 0; i < n_tensors; ++i) key.push_back(reinterpret_cast<unsigned long long>(w[i]));
+    const bool had = c->have_weights;
+    c->have_weights = true;       // rebuild_time_table (last step of `enqueue`) needs it
+    const int rc = run_cached(c, c->weights_graph, key, s0, enqueue);
+    if (rc != 0) c->have_weights = had;
     c->h0_primed = false;
-    return rebuild_time_table(c, s);
+    return rc;
 }
 
 int osteo_ddpm_set_schedule(osteo_ddpm_ctx* c, const float* sqrt_ab, const float* sqrt_1mab, const float* coef_x, const float* coef_eps, const float* sigma) {
@@ -889,7 +1006,7 @@ int osteo_ddpm_reverse_step(osteo_ddpm_ctx* c, long long n, int t, const float* 
     OSTEO_TRY(require_ready(c, n));
     if (t < 0 || t >= c->T) return fail("timestep %d outside [0, %d)", t, c->T);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    set_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), t);
+    set_int_kernel<<<1, MAX_BRANCHES, 0, s>>>(c->step_dev.as<int>(), t);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     OSTEO_TRY(ensure_primed(c, n, t, s));
@@ -905,7 +1022,7 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
     if (t_start >= c->T || t_end < 0 || t_end > t_start) return fail("bad step range [%d, %d]", t_start, t_end);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int steps = t_start - t_end + 1;
-    set_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), t_start);
+    set_int_kernel<<<1, MAX_BRANCHES, 0, s>>>(c->step_dev.as<int>(), t_start);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     if (c->x_c8 != c->fused_ok()) return fail("the state was loaded under a different precision / fused setting: call load_state or init_noise again");
@@ -914,7 +1031,7 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
         for (int i = 0; i < steps; ++i) {
             const float* nz = noise_dev ? noise_dev + static_cast<size_t>(i) * n * c->D : nullptr;
             OSTEO_TRY(enqueue_reverse_step(c, n, nz, nullptr, seed, row_base, s));
-            add_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), -1);
+            add_int_kernel<<<1, MAX_BRANCHES, 0, s>>>(c->step_dev.as<int>(), -1);
             OSTEO_CUDA(cudaGetLastError());
             ++c->launches;
         }
@@ -924,7 +1041,8 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
     // One step (and a block of GRAPH_UNROLL steps) captured once and replayed; the device-resident step word is the only thing that
     // changes between replays. The unrolled graph amortises the per-graph-launch gap over GRAPH_UNROLL steps.
     const bool reuse = c->graph_exec && c->graph_n == n && c->graph_seed == seed && c->graph_row_base == row_base &&
-                       c->graph_precision == c->precision && c->graph_chunk == c->chunk_rows && c->graph_fused == (c->x_c8 ? 1 : 0);
+                       c->graph_precision == c->precision && c->graph_chunk == c->chunk_rows && c->graph_fused == (c->x_c8 ? 1 : 0) &&
+                       c->graph_branches == c->branches;
     if (!reuse) {
         for (cudaGraphExec_t* g : {&c->graph_exec, &c->graph_exec_multi}) {
             if (*g) cudaGraphExecDestroy(*g);
@@ -940,6 +1058,7 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
         c->graph_row_base = row_base;
         c->graph_precision = c->precision;
         c->graph_chunk = c->chunk_rows;
+        c->graph_branches = c->branches;
         c->graph_fused = c->x_c8 ? 1 : 0;
     }
     int left = steps;
@@ -1008,7 +1127,7 @@ int osteo_ddpm_profile_step(osteo_ddpm_ctx* c, long long n, int t, uint64_t seed
     OSTEO_TRY(require_ready(c, n));
     if (t < 0 || t >= c->T) return fail("timestep %d outside [0, %d)", t, c->T);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    set_int_kernel<<<1, 1, 0, s>>>(c->step_dev.as<int>(), t);
+    set_int_kernel<<<1, MAX_BRANCHES, 0, s>>>(c->step_dev.as<int>(), t);
     OSTEO_CUDA(cudaGetLastError());
     OSTEO_TRY(ensure_primed(c, n, t, s));
     std::vector<cudaEvent_t> ev;

@@ -13,6 +13,7 @@ namespace osteo {
 // Tensors saved by the training forward for the backward pass.
 struct TrainWorkspace {
     long long cap = 0;
+    long long fwd_n = -1;                        // rows of the pending forward pass (two-phase API), -1 = none
     // per half block
     std::vector<std::unique_ptr<DevBuf>> xhat;   // bf16 [cap, 2*n]  normalised pre-affine activations [hi|lo]
     std::vector<std::unique_ptr<DevBuf>> rstd;   // fp32 [cap, 8]
@@ -25,10 +26,16 @@ struct TrainWorkspace {
     CUtensorMap xt_tmap;
     DevBuf noise;                                // fp32 [cap, DP]    target of the MSE epilogue
     DevBuf pre0, cemb, h1, dcemb, dpre0;         // fp32 [cap, E] each: condition-embedding forward saves / backward temporaries
-    DevBuf partials;                             // fp32 [cap/32, 3, max_width]
+    std::vector<std::unique_ptr<DevBuf>> partials;   // fp32 [cap/32, nq, width] column partials, one buffer per producer (MSE epilogue, each
+                                                     // GroupNorm-backward dgrad, d(h0)) so that their reductions can run beside the next dgrad
+    // side streams of the backward pass: weight / bias gradients run beside the dgrad chain (api_train.inl)
+    cudaStream_t side[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     DevBuf colsum_tmp;                           // fp32 [E] scratch
+    DevBuf t_copy, cond_copy, loss_tmp;          // graph-replayed step: library-owned copies of t [cap] / cond [cap, C], and the loss scalar
     size_t bytes() const {
-        size_t b = dh0_bf.bytes + dh0_f32.bytes + deps.bytes + xt_bf.bytes + noise.bytes + pre0.bytes + cemb.bytes + h1.bytes + dcemb.bytes + dpre0.bytes + partials.bytes;
+        size_t b = dh0_bf.bytes + dh0_f32.bytes + deps.bytes + xt_bf.bytes + noise.bytes + pre0.bytes + cemb.bytes + h1.bytes + dcemb.bytes + dpre0.bytes;
+        for (auto& p : partials) b += p->bytes;
         for (auto& p : xhat) b += p->bytes;
         for (auto& p : rstd) b += p->bytes;
         for (auto& p : dy) b += p->bytes;
@@ -39,7 +46,16 @@ struct TrainWorkspace {
         rstd.clear();
         dy.clear();
         dy_tmap.clear();
-        for (DevBuf* b : {&dh0_bf, &dh0_f32, &deps, &xt_bf, &noise, &pre0, &cemb, &h1, &dcemb, &dpre0, &partials, &colsum_tmp}) b->release();
+        partials.clear();
+        for (DevBuf* b : {&dh0_bf, &dh0_f32, &deps, &xt_bf, &noise, &pre0, &cemb, &h1, &dcemb, &dpre0, &colsum_tmp, &t_copy, &cond_copy, &loss_tmp}) b->release();
+        for (int i = 0; i < 2; ++i) {
+            if (side[i]) cudaStreamDestroy(side[i]);
+            if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+            side[i] = nullptr;
+            ev_join[i] = nullptr;
+        }
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        ev_fork = nullptr;
         cap = 0;
     }
 };

@@ -167,4 +167,74 @@ __global__ void corr_moments_batched_kernel(const float* __restrict__ data, int 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Differentiable forms of the two correlation validators (the reference only has stubs, models/cvae.py:262-302;
+// the forward values are tied to validate_pathway_coherence / validate_mutation_expression_correlation, utils/validation.py:125-223).
+//   mode 0  (pathway coherence):   loss_s = 1 - mean_{i<j} R_ij                      over the set's k >= 2 columns
+//   mode +1 / -1 (required sign):  loss_s = max(0, -mode * R_01)                     (k == 2: mutation column, pathway-score column)
+// with R the Pearson correlation matrix over the rows. Written S_s = sum_{i<j} R_ij, the gradient is
+//   dS/dx[r, i] = (1 / (n sd_i)) * (sum_j z_j - z_i - rho_i z_i),   z = (x - mean) / sd,   rho_i = sum_{j != i} R_ij
+// so the backward pass needs only {mean_i, 1/sd_i, rho_i} per column and dloss/dS per set.
+constexpr int CL_COEF = 4;      // per column: mean, 1/sd, (dloss/dS) / (n sd), rho
+
+// One warp per column set, from the shifted fp64 moments of corr_moments_batched_kernel.
+__global__ void corr_loss_finish_kernel(const double* __restrict__ mom, const int* __restrict__ cols, const float* __restrict__ shift,
+                                        const int* __restrict__ modes, int n_sets, float* __restrict__ loss_out, float* __restrict__ coef) {
+    const int lane = threadIdx.x & 31;
+    const int set = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (set >= n_sets) return;
+    const double* m = mom + static_cast<size_t>(set) * CM_STRIDE;
+    const bool has = cols[set * 32 + lane] >= 0;
+    const int k = __popc(__ballot_sync(0xffffffffu, has));
+    const double n = m[0];
+    const double mean = (has && n > 0) ? m[1 + lane] / n : 0.0;
+    const double var = (has && n > 0) ? m[33 + lane * 32 + lane] / n - mean * mean : 0.0;
+    const double isd = var > 0.0 ? rsqrt(var) : 0.0;      // a constant column has no correlation: it contributes R = 0
+    double rho = 0.0;
+    for (int j = 0; j < k; ++j) {
+        const double mean_j = __shfl_sync(0xffffffffu, mean, j), isd_j = __shfl_sync(0xffffffffu, isd, j);
+        if (has && j != lane) rho += (m[33 + lane * 32 + j] / n - mean * mean_j) * isd * isd_j;
+    }
+    double S = rho;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) S += __shfl_xor_sync(0xffffffffu, S, o);
+    S *= 0.5;
+    const int mode = modes[set];
+    const double npairs = 0.5 * k * (k - 1);
+    double loss, dS;
+    if (mode == 0) {
+        loss = npairs > 0 ? 1.0 - S / npairs : 0.0;
+        dS = npairs > 0 ? -1.0 / npairs : 0.0;
+    } else {
+        const double v = -static_cast<double>(mode) * S;
+        loss = v > 0.0 ? v : 0.0;
+        dS = v > 0.0 ? -static_cast<double>(mode) : 0.0;
+    }
+    if (lane == 0) loss_out[set] = static_cast<float>(loss);
+    float* c = coef + (static_cast<size_t>(set) * 32 + lane) * CL_COEF;
+    c[0] = static_cast<float>(mean + (has ? static_cast<double>(shift[set * 32 + lane]) : 0.0));
+    c[1] = static_cast<float>(isd);
+    c[2] = (has && n > 0) ? static_cast<float>(dS * isd / n) : 0.0f;
+    c[3] = static_cast<float>(rho);
+}
+
+// grad[r, col] += upstream[set] * dloss_set/dx[r, col]. Block = n_sets warps (warp <-> set), grid-stride over rows; columns shared by
+// several sets collide only within a row, hence the atomics.
+__global__ void corr_loss_bwd_kernel(const float* __restrict__ data, long long n, int ld, const int* __restrict__ cols, int n_sets,
+                                     const float* __restrict__ coef, const float* __restrict__ upstream, float* __restrict__ grad) {
+    const int lane = threadIdx.x & 31, set = threadIdx.x >> 5;
+    const int col = cols[set * 32 + lane];
+    const bool has = col >= 0;
+    const float* c = coef + (static_cast<size_t>(set) * 32 + lane) * CL_COEF;
+    const float mean = c[0], isd = c[1], a = c[2] * upstream[set], rho = c[3];
+    if (__all_sync(0xffffffffu, a == 0.0f)) return;       // inactive rule / zero upstream
+    for (long long r = blockIdx.x; r < n; r += gridDim.x) {
+        const float z = has ? (data[r * ld + col] - mean) * isd : 0.0f;
+        float sz = z;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sz += __shfl_xor_sync(0xffffffffu, sz, o);
+        if (has) atomicAdd(grad + r * ld + col, a * (sz - z - rho * z));
+    }
+}
+
 }  // namespace osteo

@@ -95,14 +95,18 @@ class _TrainStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, x0, cond, inject, *params):
         loss, grads = model._run_train_step(x0, cond, inject, want_grads=True)
-        ctx.save_for_backward(*grads)
+        ctx.model, ctx.grads, ctx.epoch = model, grads, model._grad_epoch
         return loss
 
     @staticmethod
     def backward(ctx, grad_out):
-        grads = ctx.saved_tensors
-        # one fused multi-tensor kernel instead of 52 tiny launches
-        return (None, None, None, None) + tuple(torch._foreach_mul(list(grads), grad_out))
+        # The gradients live in the model's persistent flat buffer (stable addresses: the library replays the step as one graph);
+        # a second forward before this backward would have overwritten them.
+        if ctx.model._grad_epoch != ctx.epoch:
+            raise RuntimeError("backward() of a loss whose gradients were overwritten by a later forward(): call backward() before the next "
+                               "training forward of this model")
+        # one fused multi-tensor kernel instead of 52 tiny launches; the products are fresh tensors
+        return (None, None, None, None) + tuple(torch._foreach_mul(ctx.grads, grad_out))
 
 
 class BiologyAwareDiffusionModel(nn.Module):
@@ -142,8 +146,12 @@ class BiologyAwareDiffusionModel(nn.Module):
         self._chunk_rows = int(os.environ.get("OSTEO_DDPM_CHUNK_ROWS", b200.get("chunk_rows", 131072)))
         self._use_graph = bool(int(os.environ.get("OSTEO_DDPM_GRAPH", b200.get("use_graph", 1))))
         self._fused = bool(int(os.environ.get("OSTEO_DDPM_FUSED", b200.get("fused", 1))))
+        self._branches = b200.get("branches")          # None = library default
+        self._train_graph = bool(int(os.environ.get("OSTEO_TRAIN_GRAPH", b200.get("train_graph", 1))))
         self._seed = int(b200.get("seed", 0))
         self._draws = 0                 # counter mixed into the seed of un-seeded calls
+        self._grad_buf = None           # (flat fp32 gradient buffer, per-parameter views, ctypes pointer array)
+        self._grad_epoch = 0            # bumped by every gradient-producing forward
         self._ctx = None                # C context handle
         self._ctx_device = None
         self._weights_sig = None
@@ -208,6 +216,19 @@ class BiologyAwareDiffusionModel(nn.Module):
         if self._ctx is not None:
             _lib.check(_lib.load().osteo_ddpm_set_chunk_rows(self._ctx, self._chunk_rows))
 
+    def set_train_graph(self, enable: bool) -> None:
+        """Training steps with nothing injected are replayed as one executable graph per (batch size, gradient buffer) by default;
+        set_train_graph(False) keeps every launch eager (same results)."""
+        self._train_graph = bool(enable)
+        if self._ctx is not None:
+            _lib.check(_lib.load().osteo_ddpm_set_train_graph(self._ctx, int(self._train_graph)))
+
+    def set_branches(self, branches: int) -> None:
+        """Number of parallel row branches of the sampling graphs (1..4, default 2); results do not depend on it."""
+        self._branches = int(branches)
+        if self._ctx is not None:
+            _lib.check(_lib.load().osteo_ddpm_set_branches(self._ctx, self._branches))
+
     def manual_seed(self, seed: int) -> None:
         """Seed of the in-kernel Philox streams (x_T, reverse noise, q_sample noise, dropout, timesteps)."""
         self._seed = int(seed)
@@ -249,6 +270,9 @@ class BiologyAwareDiffusionModel(nn.Module):
             self._train_enabled = False
             _lib.check(lib.osteo_ddpm_set_chunk_rows(self._ctx, self._chunk_rows))
             _lib.check(lib.osteo_ddpm_set_fused(self._ctx, int(self._fused)))
+            if self._branches is not None:
+                _lib.check(lib.osteo_ddpm_set_branches(self._ctx, self._branches))
+            _lib.check(lib.osteo_ddpm_set_train_graph(self._ctx, int(self._train_graph)))
             emb = self.unet.time_embed.table(self.num_steps).numpy()
             _lib.check(lib.osteo_ddpm_set_time_embedding(self._ctx, emb.ctypes.data))
         if rows > lib.osteo_ddpm_capacity(self._ctx):
@@ -303,7 +327,7 @@ class BiologyAwareDiffusionModel(nn.Module):
     def __getstate__(self):
         # the C context is per-object device state: copies / pickles start without one
         state = self.__dict__.copy()
-        state.update(_ctx=None, _ctx_device=None, _weights_sig=None, _schedule_sig=None, _inject=None, _train_enabled=False)
+        state.update(_ctx=None, _ctx_device=None, _weights_sig=None, _schedule_sig=None, _inject=None, _train_enabled=False, _grad_buf=None)
         return state
 
     def check_status(self) -> None:
@@ -361,7 +385,9 @@ class BiologyAwareDiffusionModel(nn.Module):
             return inject["t"].to(self._device())
         return torch.randint(0, self.num_steps, (n,), device=self._device())   # models/diffusion.py:361
 
-    def _run_train_step(self, x_0, conditions, inject, want_grads: bool):
+    def _run_train_step(self, x_0, conditions, inject, want_grads: bool, aux=None):
+        """One C-ABI training step. `aux` (multitask.py) adds auxiliary losses on the predicted clean sample: the step then runs in
+        two halves (osteo_ddpm_train_forward / _backward) with d(aux)/d(x0hat) injected between them."""
         n = x_0.shape[0]
         lib = self._ensure_ctx(n, train=want_grads)
         dev = self._device()
@@ -375,19 +401,37 @@ class BiologyAwareDiffusionModel(nn.Module):
                 masks = [m.to(device=dev, dtype=torch.uint8).contiguous() for m in inject["masks"]]
         loss = torch.zeros((), device=dev, dtype=torch.float32)
         ps = self._param_list()
-        grads = []
+        grads, garr = [], None
         if want_grads:
-            # one flat buffer, per-parameter views: the library zeroes it with a single memset
-            flat = torch.empty(sum(p.numel() for p in ps), device=dev, dtype=torch.float32)
-            o = 0
-            for p in ps:
-                grads.append(flat[o:o + p.numel()].view_as(p))
-                o += p.numel()
-        garr = (C.c_void_p * len(ps))(*[g.data_ptr() for g in grads]) if want_grads else None
+            # one persistent flat buffer, per-parameter views: the library zeroes it with a single memset, and the stable addresses
+            # let it replay the whole step as one executable graph (osteo_ddpm_set_train_graph)
+            total = sum(p.numel() for p in ps)
+            gb = self._grad_buf
+            if gb is None or gb[0].device != dev or gb[0].numel() != total:
+                flat = torch.empty(total, device=dev, dtype=torch.float32)
+                views, o = [], 0
+                for p in ps:
+                    views.append(flat[o:o + p.numel()].view_as(p))
+                    o += p.numel()
+                gb = self._grad_buf = (flat, views, (C.c_void_p * len(ps))(*[g.data_ptr() for g in views]))
+            _, grads, garr = gb
+            self._grad_epoch += 1
         marr = (C.c_void_p * len(masks))(*[m.data_ptr() for m in masks]) if masks is not None else None
-        _lib.check(lib.osteo_ddpm_train_step(self._ctx, x_0.data_ptr(), conditions.data_ptr(), n, t.data_ptr(),
-                                             _lib.ptr(noise), marr, int(self.training), self._next_seed(), 0,
-                                             loss.data_ptr(), garr, len(ps) if want_grads else 0, _lib.stream_handle()))
+        seed, s = self._next_seed(), _lib.stream_handle()
+        if aux is None or not want_grads:
+            _lib.check(lib.osteo_ddpm_train_step(self._ctx, x_0.data_ptr(), conditions.data_ptr(), n, t.data_ptr(), _lib.ptr(noise), marr, int(self.training),
+                                                 seed, 0, loss.data_ptr(), garr, len(ps) if want_grads else 0, s))
+            return loss, grads
+        _lib.check(lib.osteo_ddpm_train_forward(self._ctx, x_0.data_ptr(), conditions.data_ptr(), n, t.data_ptr(), _lib.ptr(noise), marr, int(self.training),
+                                                seed, 0, loss.data_ptr(), s))
+        cols = aux.columns.to(device=dev, dtype=torch.int32).contiguous()
+        x0hat = torch.empty((n, cols.numel()), device=dev, dtype=torch.float32)
+        _lib.check(lib.osteo_ddpm_train_x0hat(self._ctx, x_0.data_ptr(), t.data_ptr(), n, cols.data_ptr(), cols.numel(), x0hat.data_ptr(), s))
+        g = aux.gradient(x0hat, t)                # d(aux loss)/d(x0hat[:, cols]) or None
+        if g is not None:
+            g = g.to(torch.float32).contiguous()
+            _lib.check(lib.osteo_ddpm_train_inject(self._ctx, t.data_ptr(), n, cols.data_ptr(), cols.numel(), g.data_ptr(), s))
+        _lib.check(lib.osteo_ddpm_train_backward(self._ctx, conditions.data_ptr(), n, t.data_ptr(), marr, int(self.training), seed, 0, garr, len(ps), s))
         return loss, grads
 
     # ------------------------------------------------------------------ reverse process (models/diffusion.py:382-449)

@@ -164,3 +164,53 @@ def test_in_kernel_draws_train_and_reduce_the_loss():
     with torch.no_grad():
         assert torch.isfinite(model(x0, cond))
     model.check_status()
+
+
+def _train_run(case, graph: bool, steps: int = 5):
+    """`steps` optimiser steps (utils/train.py:230-244) with in-kernel noise / dropout; returns losses, final parameters, last gradients."""
+    model = build_model(case, "fp32x3")
+    model.set_train_graph(graph)
+    model.train()
+    model.manual_seed(11)
+    torch.manual_seed(11)            # the timestep draws (torch.randint, models/diffusion.py:361)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-5)
+    x0, cond = case["x0"].cuda(), case["cond"].cuda()
+    losses = []
+    for _ in range(steps):
+        opt.zero_grad()
+        loss = model(x0.clone(), cond.clone())      # fresh input addresses every step, like a DataLoader
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        losses.append(loss.item())
+    model.check_status()
+    return losses, [p.detach().clone() for p in model.parameters()], [p.grad.detach().clone() for p in model.parameters()]
+
+
+@pytest.mark.parametrize("name", ["smoke", "linear3"])
+def test_graph_replayed_training_matches_eager(name):
+    """The step is replayed as one graph from its second call on (weights repack: from the third): same losses, gradients and
+    parameters as the eager launches, and the in-kernel noise / dropout streams still advance from step to step."""
+    case = load_case(name)
+    l_g, p_g, g_g = _train_run(case, True)
+    l_e, p_e, g_e = _train_run(case, False)
+    assert len(set(l_g)) == len(l_g)                       # a frozen seed or timestep tensor would repeat a loss
+    for a, b in zip(l_g, l_e):
+        assert abs(a - b) < 2e-5 * abs(b)
+    for a, b in zip(g_g, g_e):
+        assert rel(a, b) < 1e-4 or (a - b).abs().max().item() < 1e-7      # split-batch wgrad accumulates atomically: not bit-stable
+    for a, b in zip(p_g, p_e):
+        assert rel(a, b) < 1e-3         # AdamW's g / sqrt(v) amplifies the atomics' rounding noise on near-zero gradients
+
+
+def test_backward_after_a_second_forward_is_refused():
+    case = load_case("smoke")
+    model = build_model(case, "bf16")
+    model.train()
+    x0, cond = case["x0"].cuda(), case["cond"].cuda()
+    first = model(x0, cond)
+    second = model(x0, cond)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        first.backward()
+    second.backward()
+    assert all(p.grad is not None for p in model.parameters())

@@ -114,6 +114,8 @@ def test_batched_moments_match_numpy_and_the_single_set_kernel(n, ncols, pitch):
     full[:, 7] = 0.5 * full[:, 2] + 0.5 * full[:, 7]
     t = torch.from_numpy(full).cuda()
     sets = [sorted(rs.choice(ncols, k, replace=False).tolist()) for k in (1, 15, 17, 32)]
+    if n < 2000:
+        sets = sets + [sorted(rs.choice(ncols, 3 + i % 5, replace=False).tolist()) for i in range(28)]      # 32 sets: two launches of 16 warps
     ci = np.full((len(sets), 32), -1, dtype=np.int32)
     for i, c in enumerate(sets):
         ci[i, :len(c)] = c
