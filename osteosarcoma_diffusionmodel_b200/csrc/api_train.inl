@@ -48,6 +48,8 @@ static int ensure_train_ws(osteo_ddpm_ctx* c) {
             w.partials.push_back(std::move(b));
         }
     }
+    OSTEO_TRY(w.temb_bf.alloc(static_cast<size_t>(cap) * 2 * c->TD * 2));
+    OSTEO_TRY(w.cemb_bf.alloc(static_cast<size_t>(cap) * 2 * c->E * 2));
     OSTEO_TRY(w.t_copy.alloc(static_cast<size_t>(cap) * sizeof(int)));
     OSTEO_TRY(w.cond_copy.alloc(static_cast<size_t>(cap) * c->C * sizeof(float)));
     OSTEO_TRY(w.loss_tmp.alloc(sizeof(float)));
@@ -107,15 +109,25 @@ static int train_pre(osteo_ddpm_ctx* c, const float* x0_dev, const float* cond_d
                      long long row_base, cudaStream_t s) {
     TrainWorkspace& w = c->train;
     const int D = c->D, DP = c->DP, h0 = c->h0(), E = c->E;
-    train_prepare_kernel<<<grid_for(n * (DP / 4), 256, c->sms), 256, 0, s>>>(x0_dev, noise_dev, t_idx_dev, n, D, c->sqrt_ab.as<float>(), c->sqrt_1mab.as<float>(),
-                                                                             w.noise.as<float>(), DP, w.xt_bf.as<__nv_bfloat16>(), 2 * DP, c->lo(DP), seed, row_base);
-    OSTEO_CUDA(cudaGetLastError());
     {
+        // the condition path is independent of q_sample: it runs beside it on a side stream (HBM-bound 98 us next to a 33 us CUDA-core kernel)
+        cudaStream_t sc = w.side[1] ? w.side[1] : s;
+        if (sc != s) {
+            OSTEO_CUDA(cudaEventRecord(w.ev_fork, s));
+            OSTEO_CUDA(cudaStreamWaitEvent(sc, w.ev_fork, 0));
+        }
         const size_t smem = sizeof(float) * 16 * (c->C + 2 * E);
-        cond_path_kernel<<<static_cast<unsigned>((n + 15) / 16), 256, smem, s>>>(cond_dev, n, c->C, E, h0, c->ce_w0t.as<float>(), c->ce_b0.as<float>(),
-                                                                               c->ce_w2t.as<float>(), c->ce_b2.as<float>(), c->cp_wt.as<float>(), c->cp_b.as<float>(),
-                                                                               c->cproj.as<float>(), w.pre0.as<float>(), w.cemb.as<float>());
+        cond_path_kernel<<<static_cast<unsigned>((n + 15) / 16), 256, smem, sc>>>(cond_dev, n, c->C, E, h0, c->ce_w0t.as<float>(), c->ce_b0.as<float>(),
+                                                                                c->ce_w2t.as<float>(), c->ce_b2.as<float>(), c->cp_wt.as<float>(), c->cp_b.as<float>(),
+                                                                                c->cproj.as<float>(), w.pre0.as<float>(), w.cemb.as<float>());
         OSTEO_CUDA(cudaGetLastError());
+        train_prepare_kernel<<<grid_for(n * (DP / 4), 256, c->sms), 256, 0, s>>>(x0_dev, noise_dev, t_idx_dev, n, D, c->sqrt_ab.as<float>(), c->sqrt_1mab.as<float>(),
+                                                                                 w.noise.as<float>(), DP, w.xt_bf.as<__nv_bfloat16>(), 2 * DP, c->lo(DP), seed, row_base);
+        OSTEO_CUDA(cudaGetLastError());
+        if (sc != s) {
+            OSTEO_CUDA(cudaEventRecord(w.ev_join[1], sc));
+            OSTEO_CUDA(cudaStreamWaitEvent(s, w.ev_join[1], 0));
+        }
     }
     c->launches += 2;
     c->h0_primed = false;      // acts[0] now belongs to this training batch, not to a sampling state
@@ -376,9 +388,22 @@ static int train_body(osteo_ddpm_ctx* c, const float* cond_dev, long long n, con
     OSTEO_TRY(finish_partials(c, w.partials[H + 1]->as<float>(), n, 1, h0, grads_dev[5], nullptr, nullptr, s2));
     OSTEO_CUDA(cudaMemcpyAsync(grads_dev[7], grads_dev[5], sizeof(float) * h0, cudaMemcpyDeviceToDevice, s2));
     OSTEO_CUDA(cudaMemcpyAsync(grads_dev[9], grads_dev[5], sizeof(float) * h0, cudaMemcpyDeviceToDevice, s2));
-    // time_proj / cond_proj / ConditionalEmbedding (fp32 CUDA-core kernels; tiny matrices)
-    OSTEO_TRY(outer_accum(c, w.dh0_f32.as<float>(), h0, c->emb_table.as<float>(), c->TD, t_idx_dev, n, grads_dev[8], s2));
-    OSTEO_TRY(outer_accum(c, w.dh0_f32.as<float>(), h0, w.cemb.as<float>(), E, nullptr, n, grads_dev[6], s2));
+    // time_proj / cond_proj weight gradients = dh0^T . emb[t] and dh0^T . cemb: [h0 x 128] and [h0 x 64] contractions over the batch on the
+    // tensor cores (as CUDA-core outer products they were the longest kernels of the tail: 108 + 52 us at batch 8192)
+    if ((c->TD & 63) == 0 && (E & 63) == 0) {
+        const int TD = c->TD;
+        pack_rows_hilo_kernel<<<grid_for(n * (TD / 4), 256, c->sms), 256, 0, s2>>>(c->emb_table.as<float>(), TD, t_idx_dev, n, TD, w.temb_bf.as<__nv_bfloat16>(), 2 * TD, c->lo(TD));
+        pack_rows_hilo_kernel<<<grid_for(n * (E / 4), 256, c->sms), 256, 0, s2>>>(w.cemb.as<float>(), E, nullptr, n, E, w.cemb_bf.as<__nv_bfloat16>(), 2 * E, c->lo(E));
+        OSTEO_CUDA(cudaGetLastError());
+        c->launches += 2;
+        OSTEO_TRY(after_launch(c, launch_wgrad(w.dh0_bf.as<__nv_bfloat16>(), 2 * h0, h0, h0, w.temb_bf.as<__nv_bfloat16>(), 2 * TD, 0, TD, TD, grads_dev[8], TD, n, x3,
+                                               c->status_dev.as<int>(), c->sms, s2), s2));
+        OSTEO_TRY(after_launch(c, launch_wgrad(w.dh0_bf.as<__nv_bfloat16>(), 2 * h0, h0, h0, w.cemb_bf.as<__nv_bfloat16>(), 2 * E, 0, E, E, grads_dev[6], E, n, x3,
+                                               c->status_dev.as<int>(), c->sms, s2), s2));
+    } else {
+        OSTEO_TRY(outer_accum(c, w.dh0_f32.as<float>(), h0, c->emb_table.as<float>(), c->TD, t_idx_dev, n, grads_dev[8], s2));
+        OSTEO_TRY(outer_accum(c, w.dh0_f32.as<float>(), h0, w.cemb.as<float>(), E, nullptr, n, grads_dev[6], s2));
+    }
     {
         const size_t smem = sizeof(float) * 8 * (h0 + E);
         // Wc^T view: cond_bwd needs Wc as [h0, E] row-major, which is exactly cond_proj.weight's layout.
@@ -388,7 +413,10 @@ static int train_body(osteo_ddpm_ctx* c, const float* cond_dev, long long n, con
         ++c->launches;
     }
     {
-        dim3 grid((E + 63) / 64, 64);
+        // 16 rows per block: a block's loop is a serial chain of dependent loads (64 blocks of 128 rows took 54 us for 2 MB)
+        long long gy = (n + 15) / 16;
+        gy = gy < 1 ? 1 : (gy > 4096 ? 4096 : gy);
+        dim3 grid((E + 63) / 64, static_cast<unsigned>(gy));
         colsum_f32_kernel<<<grid, 64, 0, s>>>(w.dcemb.as<float>(), n, E, grads_dev[3]);
         colsum_f32_kernel<<<grid, 64, 0, s>>>(w.dpre0.as<float>(), n, E, grads_dev[1]);
         OSTEO_CUDA(cudaGetLastError());

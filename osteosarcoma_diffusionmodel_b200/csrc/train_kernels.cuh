@@ -32,6 +32,7 @@ struct TrainWorkspace {
     cudaStream_t side[2] = {nullptr, nullptr};
     cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     DevBuf colsum_tmp;                           // fp32 [E] scratch
+    DevBuf temb_bf, cemb_bf;                     // bf16 [cap, 2*TD], [cap, 2*E]: gathered time embedding / condition embedding as wgrad operands
     DevBuf t_copy, cond_copy, loss_tmp;          // graph-replayed step: library-owned copies of t [cap] / cond [cap, C], and the loss scalar
     size_t bytes() const {
         size_t b = dh0_bf.bytes + dh0_f32.bytes + deps.bytes + xt_bf.bytes + noise.bytes + pre0.bytes + cemb.bytes + h1.bytes + dcemb.bytes + dpre0.bytes;
@@ -47,7 +48,7 @@ struct TrainWorkspace {
         dy.clear();
         dy_tmap.clear();
         partials.clear();
-        for (DevBuf* b : {&dh0_bf, &dh0_f32, &deps, &xt_bf, &noise, &pre0, &cemb, &h1, &dcemb, &dpre0, &colsum_tmp, &t_copy, &cond_copy, &loss_tmp}) b->release();
+        for (DevBuf* b : {&dh0_bf, &dh0_f32, &deps, &xt_bf, &noise, &pre0, &cemb, &h1, &dcemb, &dpre0, &colsum_tmp, &t_copy, &cond_copy, &loss_tmp, &temb_bf, &cemb_bf}) b->release();
         for (int i = 0; i < 2; ++i) {
             if (side[i]) cudaStreamDestroy(side[i]);
             if (ev_join[i]) cudaEventDestroy(ev_join[i]);
@@ -114,6 +115,24 @@ __global__ void partials_finish_kernel(const float* __restrict__ part, int slabs
         for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
         float* out = q == 0 ? out0 : (q == 1 ? out1 : out2);
         if (out) out[c] = t;
+    }
+}
+
+// fp32 rows (optionally gathered through `idx`: the sinusoidal time-embedding table, models/diffusion.py:124-139) -> bf16 [n, dst_ld] with the
+// hi part at column c and the residual at c + lo_off (lo_off = 0: none): the MN-major X operand of a tensor-core weight gradient.
+__global__ void pack_rows_hilo_kernel(const float* __restrict__ src, int src_ld, const int* __restrict__ idx, long long n, int k, __nv_bfloat16* __restrict__ dst,
+                                      int dst_ld, int lo_off) {
+    const int q = k / 4;
+    const long long total = n * q;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / q;
+        const int c = static_cast<int>(i % q) * 4;
+        const long long sr = idx ? __ldg(idx + r) : r;
+        const float4 v = *reinterpret_cast<const float4*>(src + sr * src_ld + c);
+        *reinterpret_cast<uint2*>(dst + r * dst_ld + c) = make_uint2(pack2(v.x, v.y), pack2(v.z, v.w));
+        if (lo_off > 0)
+            *reinterpret_cast<uint2*>(dst + r * dst_ld + lo_off + c) =
+                make_uint2(pack2(v.x - bf16r(v.x), v.y - bf16r(v.y)), pack2(v.z - bf16r(v.z), v.w - bf16r(v.w)));
     }
 }
 

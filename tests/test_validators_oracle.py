@@ -81,3 +81,35 @@ def test_mutation_expression_matches_reference(golden_dir):
     res = V.mutation_expression_violation_rate([(mut[:, 0], path[:, 0], "negative"), (mut[:, 1], path[:, 1], "positive")])
     assert res["mutation_expression_violation_rate"] == float(g["mutexpr_violation_rate"]) == 0.5
     assert np.allclose(res["_correlations"], g["mutexpr_corr"], rtol=0, atol=1e-12)
+
+
+def test_bio_loss_oracle_is_tied_to_the_validator_oracle():
+    """oracle/bio_losses_oracle.py (the checker of the A12 kernels): coherence loss = 1 - per-pathway validator score, rule loss > 0
+    exactly on a sign violation; its autograd gradient matches central differences."""
+    import torch
+    from oracle import bio_losses_oracle as B
+
+    rs = np.random.RandomState(2)
+    base = rs.standard_normal((200, 3))
+    data = base @ rs.standard_normal((3, 12)) + 0.5 * rs.standard_normal((200, 12))
+    sets = [[0, 1, 2, 3], [4, 5, 6, 7, 8], [9, 10], [9, 11]]
+    modes = [0, 0, 1, -1]
+    x = torch.from_numpy(data).requires_grad_(True)
+    losses = B.correlation_losses(x, sets, modes)
+    for s, m, l in zip(sets, modes, losses.tolist()):
+        sub = data[:, s]
+        if m == 0:
+            assert abs(l - (1.0 - V.mean_upper(V.pearson_matrix(sub)))) < 1e-12
+        else:
+            c = V.pearson(sub[:, 0], sub[:, 1])
+            assert abs(l - max(0.0, -m * c)) < 1e-12
+            assert (l > 0) == ((m > 0 and c < 0) or (m < 0 and c > 0))
+    w = torch.tensor([1.0, 0.5, 2.0, 3.0], dtype=torch.float64)
+    (losses * w).sum().backward()
+    for (r, c) in [(0, 0), (17, 5), (199, 9), (3, 11)]:
+        h = 1e-6
+        xp, xm = data.copy(), data.copy()
+        xp[r, c] += h
+        xm[r, c] -= h
+        fd = ((B.correlation_losses(torch.from_numpy(xp), sets, modes) - B.correlation_losses(torch.from_numpy(xm), sets, modes)) * w).sum().item() / (2 * h)
+        assert abs(fd - x.grad[r, c].item()) < 1e-6 * max(1.0, abs(fd))
