@@ -162,7 +162,7 @@ def workload_config(args, rows_per_gpu):
             "patients_per_gpu": rows_per_gpu, "num_steps": T_STEPS, "precision": args.precision,
             "rng": "in-kernel Philox4x32-10 keyed by (seed, global row, t, column)", "weights": "random init (synthetic.make_params seed 0)",
             "l2_policy": "fp32 state (2.1 GB per 100k patients) is larger than L2; no flush needed",
-            "sharding": "contiguous global-row ranges per rank, no data-path collective"}
+            "sharding": "contiguous global-row ranges per rank, no data-path collective", "graph": "10-step executable graphs, 2 parallel row branches per rank (osteo_ddpm_set_branches)"}
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -402,6 +402,35 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
     flops = 22.6e6 * B          # fwd + wgrad + dgrad per sample
     out["train_step"] = {"batch": B, "precision": model._precision, "ms_per_step": ms, "samples_per_s": B / (ms / 1e3), "fwd_bwd_ms": ms_fb,
                          "tensor_frac_fwd_bwd": flops / (ms_fb / 1e3) / 1e12 / tf_peak, "optimizer": "torch AdamW + clip_grad_norm_(1.0), unmodified"}
+    out["train_step"]["note"] = ("forward + backward replayed as one executable graph per batch shape; weight / bias gradients on side streams beside the dgrad chain; "
+                                 "the host enqueue of torch's clip + AdamW bounds the full step")
+    # multi-task step (BASELINE.json configs[3]): + pathway coherence (10 pathways x 15 genes), 2 sign rules, survival head
+    try:
+        from osteosarcoma_diffusionmodel_b200.multitask import BiologyConstrainedDiffusion
+        rs = np.random.RandomState(0)
+        members = [sorted(rs.choice(D_EXPR, 15, replace=False).tolist()) for _ in range(10)]
+        mt = BiologyConstrainedDiffusion(D_MUT, D_EXPR, D_PATH, N_COND, synth.model_config(hidden_dims=HIDDEN), pathway_members=members,
+                                         correlation_rules=[(0, 0, -1), (1, 1, 1)])
+        mt.diffusion.load_state_dict(synth.make_params(D, N_COND, HIDDEN, seed=0), strict=False)
+        mt = mt.to(dev).train()
+        mt.diffusion.set_precision(model._precision)
+        mopt = torch.optim.AdamW(mt.parameters(), lr=1e-4, weight_decay=1e-5)
+        surv = cond[:, 0].contiguous()
+
+        def mt_step():
+            mopt.zero_grad()
+            loss = mt(x0, cond, survival_time=surv)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(mt.parameters(), 1.0)
+            mopt.step()
+
+        ms_mt = timed(mt_step, 3, 10)
+        out["train_step"]["multitask_ms_per_step"] = ms_mt
+        out["train_step"]["multitask_parts"] = {k: float(v) for k, v in mt.last_losses.items()}
+        mt.diffusion.check_status()
+        del mt, mopt
+    except Exception as e:      # keep the bench line if the optional workload fails
+        out["train_step"]["multitask_error"] = repr(e)
     model.eval()
     # CPU port: autograd over the oracle, batch 1024
     torch.set_num_threads(os.cpu_count() or 1)

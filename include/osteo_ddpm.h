@@ -98,6 +98,12 @@ int osteo_ddpm_set_time_embedding(osteo_ddpm_ctx* ctx, const float* emb_host);
 int osteo_ddpm_load_state(osteo_ddpm_ctx* ctx, const float* x_dev, long long n, void* stream);
 /* internal state -> out_dev [n, data_dim] fp32. */
 int osteo_ddpm_store_state(osteo_ddpm_ctx* ctx, float* out_dev, long long n, void* stream);
+/* internal state -> the pieces SyntheticPatientGenerator.generate makes on the host (utils/generate.py:130-135), any of them NULL to
+ * skip: calls_dev uint8 [n, mutation_dim] = (x[:, :mutation_dim] > threshold); call_bits_dev uint8 [n, ceil(mutation_dim / 8)] the
+ * same calls one bit per gene (LSB first); rest_dev fp32 [n, data_dim - mutation_dim] = expression | pathway scores. The comparison
+ * is made on the fp32 state, i.e. on exactly the values osteo_ddpm_store_state returns. */
+int osteo_ddpm_store_split(osteo_ddpm_ctx* ctx, long long n, int mutation_dim, float threshold, uint8_t* calls_dev,
+                           uint8_t* call_bits_dev, float* rest_dev, void* stream);
 /* x_T ~ N(0, I) from Philox4x32-10(seed; row_base + row, column): models/diffusion.py:443. */
 int osteo_ddpm_init_noise(osteo_ddpm_ctx* ctx, long long n, uint64_t seed, long long row_base, void* stream);
 /* ConditionalEmbedding + cond_proj hoisted out of the step loop (models/diffusion.py:107-114,

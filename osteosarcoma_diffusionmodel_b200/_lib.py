@@ -46,6 +46,7 @@ SIGNATURES = {
     "osteo_ddpm_set_time_embedding": (_i, [_vp, _vp]),
     "osteo_ddpm_load_state": (_i, [_vp, _vp, _ll, _vp]),
     "osteo_ddpm_store_state": (_i, [_vp, _vp, _ll, _vp]),
+    "osteo_ddpm_store_split": (_i, [_vp, _ll, _i, _f, _vp, _vp, _vp, _vp]),
     "osteo_ddpm_init_noise": (_i, [_vp, _ll, _u64, _ll, _vp]),
     "osteo_ddpm_set_conditions": (_i, [_vp, _vp, _ll, _vp]),
     "osteo_ddpm_reverse_step": (_i, [_vp, _ll, _i, _vp, _vp, _u64, _ll, _vp]),

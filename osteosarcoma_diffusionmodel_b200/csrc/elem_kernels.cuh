@@ -108,6 +108,35 @@ __global__ void store_state_kernel(const float* __restrict__ x, int x_nbox, int 
     }
 }
 
+// Egress of a finished cohort in the form SyntheticPatientGenerator.generate consumes it (utils/generate.py:130-135): the mutation block
+// thresholded (x > thr) into 0/1 bytes and/or one bit per gene (LSB first, ceil(mut / 8) bytes per patient), and the remaining
+// expression + pathway-score columns as a dense fp32 matrix [n, d - mut].
+__global__ void store_split_kernel(const float* __restrict__ x, int x_nbox, int x_shift, long long n, int d, int mut, float thr, uint8_t* __restrict__ calls,
+                                   uint8_t* __restrict__ bits, float* __restrict__ rest) {
+    const int bpr = (mut + 7) / 8;
+    const int rest_w = d - mut;
+    const int per_row = bpr + rest_w;            // work items per patient: one per packed byte of calls, one per remaining column
+    const long long total = n * per_row;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / per_row;
+        const int j = static_cast<int>(i % per_row);
+        if (j < bpr) {
+            uint32_t b = 0;
+            for (int k = 0; k < 8; ++k) {
+                const int c = j * 8 + k;
+                if (c >= mut) break;
+                const bool on = x[x_blocked_off(r, c, x_nbox, x_shift)] > thr;
+                if (calls) calls[r * mut + c] = on ? 1 : 0;
+                b |= (on ? 1u : 0u) << k;
+            }
+            if (bits) bits[r * bpr + j] = static_cast<uint8_t>(b);
+        } else if (rest) {
+            const int c = mut + (j - bpr);
+            rest[r * rest_w + (j - bpr)] = x[x_blocked_off(r, c, x_nbox, x_shift)];
+        }
+    }
+}
+
 // x_T ~ N(0, I): models/diffusion.py:443. One Philox call per 4 columns.
 __global__ void init_noise_kernel(float* __restrict__ x, int x_nbox, int x_shift, int dp, __nv_bfloat16* __restrict__ xb, int xb_nbox, int lo_boxes, long long n, int d,
                                   unsigned long long seed, long long row_base, uint32_t stream_id, uint32_t step) {

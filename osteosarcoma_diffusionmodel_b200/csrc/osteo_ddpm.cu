@@ -971,6 +971,19 @@ int osteo_ddpm_store_state(osteo_ddpm_ctx* c, float* out_dev, long long n, void*
     return 0;
 }
 
+int osteo_ddpm_store_split(osteo_ddpm_ctx* c, long long n, int mutation_dim, float threshold, uint8_t* calls_dev, uint8_t* call_bits_dev, float* rest_dev, void* stream) {
+    OSTEO_TRY(check_ctx(c));
+    if (n <= 0 || n > c->cap) return fail("store_split: %lld rows outside (0, capacity %lld]", n, c->cap);
+    if (mutation_dim < 0 || mutation_dim > c->D) return fail("store_split: mutation_dim %d outside [0, %d]", mutation_dim, c->D);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const long long items = n * ((mutation_dim + 7) / 8 + (c->D - mutation_dim));
+    store_split_kernel<<<grid_for(items, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->xs_nbox(), c->xs_shift(), n, c->D, mutation_dim, threshold, calls_dev, call_bits_dev,
+                                                                   rest_dev);
+    OSTEO_CUDA(cudaGetLastError());
+    ++c->launches;
+    return 0;
+}
+
 int osteo_ddpm_init_noise(osteo_ddpm_ctx* c, long long n, uint64_t seed, long long row_base, void* stream) {
     OSTEO_TRY(check_ctx(c));
     if (n <= 0 || n > c->cap) return fail("init_noise: %lld rows outside (0, capacity %lld]", n, c->cap);

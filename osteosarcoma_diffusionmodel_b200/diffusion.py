@@ -462,7 +462,7 @@ class BiologyAwareDiffusionModel(nn.Module):
 
     @torch.no_grad()
     def sample(self, conditions, num_samples: int = 1, *, seed: Optional[int] = None, row_base: int = 0, x_T=None, noise=None,
-               t_stop: int = 0):
+               t_stop: int = 0, _components: Optional[str] = None):
         """Generate samples via reverse diffusion (models/diffusion.py:427-449).
 
         Extra keyword-only arguments (all optional, defaults reproduce the reference call):
@@ -488,9 +488,30 @@ class BiologyAwareDiffusionModel(nn.Module):
         z = self._as_f32(noise, dev) if noise is not None else None
         _lib.check(lib.osteo_ddpm_sample_loop(self._ctx, n, self.num_steps - 1, int(t_stop), _lib.ptr(z), seed, int(row_base),
                                               int(self._use_graph), s))
+        if _components:
+            return self._store_components(n, dev, lib, s, conditions, pack_bits=_components == "bits")
         out = torch.empty((n, self.data_dim), device=dev, dtype=torch.float32)
         _lib.check(lib.osteo_ddpm_store_state(self._ctx, out.data_ptr(), n, s))
         return out
+
+    def _store_components(self, n, dev, lib, s, conditions, pack_bits: bool):
+        md = self.mutation_dim
+        calls = torch.empty((n, md), device=dev, dtype=torch.uint8)
+        bits = torch.empty((n, (md + 7) // 8), device=dev, dtype=torch.uint8) if pack_bits else None
+        rest = torch.empty((n, self.data_dim - md), device=dev, dtype=torch.float32)
+        _lib.check(lib.osteo_ddpm_store_split(self._ctx, n, md, 0.5, calls.data_ptr(), _lib.ptr(bits), rest.data_ptr(), s))
+        out = {"mutations": calls, "expression": rest[:, :self.expression_dim], "pathways": rest[:, self.expression_dim:], "conditions": conditions}
+        if pack_bits:
+            out["mutation_bits"] = bits
+        return out
+
+    @torch.no_grad()
+    def sample_components(self, conditions, num_samples: int = 1, *, pack_bits: bool = False, **kw):
+        """sample() with the egress of SyntheticPatientGenerator.generate fused on the device (utils/generate.py:127-144): returns
+        {'mutations': uint8 [n, mutation_dim] = samples[:, :mutation_dim] > 0.5, 'expression': fp32 [n, expression_dim],
+        'pathways': fp32 [n, pathway_dim], 'conditions'} as device tensors (plus 'mutation_bits', one bit per gene, LSB first, when
+        pack_bits=True) instead of the dense [n, D] matrix. The calls are bit-identical to thresholding sample()'s output."""
+        return self.sample(conditions, num_samples, _components="bits" if pack_bits else "bytes", **kw)
 
     @torch.no_grad()
     def predict_noise(self, x_t, t, conditions):

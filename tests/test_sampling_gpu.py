@@ -219,3 +219,23 @@ def test_more_rows_than_one_chunk_and_single_row():
     with pytest.raises(ValueError):
         model.sample(cond[:3], 5)
     model.check_status()
+
+
+def test_sample_components_is_the_split_and_thresholded_sample():
+    """utils/generate.py:130-135 on the device: mutation calls bit-identical to (sample()[:, :mutation_dim] > 0.5), bit packing LSB
+    first, expression / pathway blocks equal to the column split."""
+    case = load_case("smoke")
+    model = build_model(case, "bf16")
+    n = 300
+    cond = case["cond"][:1].repeat(n, 1).cuda()
+    full = model.sample(cond, n, seed=5, t_stop=900)
+    comp = model.sample_components(cond, n, seed=5, t_stop=900, pack_bits=True)
+    md, ed = model.mutation_dim, model.expression_dim
+    calls = (full[:, :md] > 0.5)
+    assert comp["mutations"].dtype == torch.uint8 and torch.equal(comp["mutations"].bool(), calls)
+    assert torch.equal(comp["expression"], full[:, md:md + ed]) and torch.equal(comp["pathways"], full[:, md + ed:])
+    bits = comp["mutation_bits"].cpu().numpy()
+    unpacked = np.unpackbits(bits, axis=1, bitorder="little")[:, :md]
+    assert np.array_equal(unpacked.astype(bool), calls.cpu().numpy())
+    assert 0 < calls.float().mean().item() < 1       # both outcomes occur
+    model.check_status()
