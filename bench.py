@@ -334,6 +334,9 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_secondary:
         secondary = run_secondary(model, dev, hbm_peak, tf_peak)
 
+    if world > 1 and not args.no_secondary:
+        secondary = run_secondary_dp(model, dev, dist, rank, world, tf_peak)      # every rank takes part; rank 0 keeps the numbers
+
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -487,6 +490,52 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
                         "streamed_gb_per_s": rows * 371 * 4 / (ms / 1e3) / 1e9, "hbm_frac": rows * 371 * 4 / (ms / 1e3) / 1e9 / hbm_peak,
                         "note": "one pass over whole rows for all pathways (osteo_corr_moments_batched); includes the host-side finish of both cohorts"}
     return out
+
+
+def run_secondary_dp(model, dev, dist, rank, world, tf_peak):
+    """N > 1: the data-parallel training step of BASELINE.json configs[3] (8192 rows per GPU, one all-reduce of the 17 MB flat gradient
+    buffer, clip after the reduce, unmodified torch AdamW) and the row-sharded RBF-MMD of configs[4] (Gram rows split over the ranks,
+    three fp64 sums all-reduced). Device-timed between barriers, max over ranks."""
+    import torch
+    from osteosarcoma_diffusionmodel_b200 import distributed as Dm
+    from osteosarcoma_diffusionmodel_b200 import synthetic as synth
+    from osteosarcoma_diffusionmodel_b200.validation import BiologicalValidator
+
+    def timed(fn, warm, reps):
+        for _ in range(warm):
+            fn()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / reps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    out = {}
+    B = 8192
+    x0, cond = synth.make_cohort(B, D_MUT, D_EXPR, D_PATH, N_COND, seed=3 + rank)
+    x0, cond = x0.to(dev), cond.to(dev)
+    model.train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
+    ms = timed(lambda: Dm.dp_train_step(model, opt, x0, cond), 4, 10)
+    out["dp_train_step"] = {"batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms, "samples_per_s": B * world / (ms / 1e3),
+                            "allreduce": "one NCCL all-reduce of the flat fp32 gradient buffer per step, after the graph-replayed backward"}
+    model.eval()
+    n = 32768
+    g = torch.Generator(device=dev).manual_seed(1)
+    X = torch.randn(n, D, device=dev, generator=g) + 4.0
+    Y = torch.randn(n, D, device=dev, generator=g) * 1.1 + 4.1
+    val = BiologicalValidator({"evaluation": {}}, precision="bf16")
+    ms = timed(lambda: val.compute_mmd(X, Y), 1, 3)
+    out["mmd_bf16_row_sharded"] = {"rows": n, "ms": ms, "kernel_pairs_per_s": 3.0 * n * n / (ms / 1e3), "value": val.compute_mmd(X, Y),
+                                   "note": "every rank holds X and Y and reduces its share of the Gram rows; full (not symmetric-half) Grams when sharded"}
+    model.check_status()
+    return out if rank == 0 else None
 
 
 def main():

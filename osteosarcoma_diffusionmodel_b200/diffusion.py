@@ -96,6 +96,15 @@ class _TrainStep(torch.autograd.Function):
     def forward(ctx, model, x0, cond, inject, *params):
         loss, grads = model._run_train_step(x0, cond, inject, want_grads=True)
         ctx.model, ctx.grads, ctx.epoch = model, grads, model._grad_epoch
+        ctx.scale = 1.0
+        if model._flat_allreduce:
+            # data parallel: ONE all-reduce of the flat gradient buffer (17 MB for config.yaml) instead of per-bucket cat / copy-back;
+            # the 1 / world_size of the mean rides on the scaling backward() does anyway
+            from . import distributed as D
+            rank, ws = D.world()
+            if ws > 1:
+                D.all_reduce_sum_(model._grad_buf[0])
+                ctx.scale = 1.0 / ws
         return loss
 
     @staticmethod
@@ -106,7 +115,7 @@ class _TrainStep(torch.autograd.Function):
             raise RuntimeError("backward() of a loss whose gradients were overwritten by a later forward(): call backward() before the next "
                                "training forward of this model")
         # one fused multi-tensor kernel instead of 52 tiny launches; the products are fresh tensors
-        return (None, None, None, None) + tuple(torch._foreach_mul(ctx.grads, grad_out))
+        return (None, None, None, None) + tuple(torch._foreach_mul(ctx.grads, grad_out * ctx.scale if ctx.scale != 1.0 else grad_out))
 
 
 class BiologyAwareDiffusionModel(nn.Module):
@@ -152,6 +161,7 @@ class BiologyAwareDiffusionModel(nn.Module):
         self._draws = 0                 # counter mixed into the seed of un-seeded calls
         self._grad_buf = None           # (flat fp32 gradient buffer, per-parameter views, ctypes pointer array)
         self._grad_epoch = 0            # bumped by every gradient-producing forward
+        self._flat_allreduce = False    # distributed.dp_train_step: average the flat gradient buffer over the ranks inside forward()
         self._ctx = None                # C context handle
         self._ctx_device = None
         self._weights_sig = None

@@ -2,7 +2,8 @@
 NVLink on GPUs, gloo in the CPU tests). The data path itself never communicates:
 
   sampling   rows are independent -> contiguous global-row shards, no collective (Philox is keyed by global row);
-  training   data parallel -> bucketed all-reduce (mean) of the 52 gradient tensors, largest / last-layer bucket first;
+  training   data parallel -> ONE all-reduce (mean) of the model's flat gradient buffer (generic modules: bucketed all-reduce of the
+             .grad tensors, largest / last-layer bucket first);
   MMD        Gram ROWS sharded, one all-reduce of the three fp64 partial sums;
   coherence  cohort rows sharded, one all-reduce of the per-pathway fp64 moment blocks.
 """
@@ -90,9 +91,17 @@ def dp_train_step(model, optimizer, x0: torch.Tensor, conditions: torch.Tensor, 
     """One data-parallel optimiser step with the reference's recipe (utils/train.py:230-246): the global gradient norm is
     taken AFTER the all-reduce, so every rank clips identically and parameters stay bit-identical across ranks."""
     optimizer.zero_grad()
-    loss = model(x0, conditions, return_loss=True)
-    loss.backward()
-    allreduce_gradients(model.parameters(), bucket_bytes)
+    flat = hasattr(model, "_flat_allreduce") and hasattr(model, "_grad_buf")      # BiologyAwareDiffusionModel: one all-reduce of its flat buffer
+    if flat:
+        model._flat_allreduce = True
+    try:
+        loss = model(x0, conditions, return_loss=True)
+        loss.backward()
+    finally:
+        if flat:
+            model._flat_allreduce = False
+    if not flat:
+        allreduce_gradients(model.parameters(), bucket_bytes)
     torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
     optimizer.step()
     return loss.detach()
