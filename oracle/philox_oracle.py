@@ -1,7 +1,7 @@
 """ORACLE — numpy restatement of the in-kernel counter RNG (csrc/philox.cuh); test infrastructure.
 
 Philox4x32-10 (Salmon et al., SC'11; same constants as Random123 / cuRAND) with
-counter = (col4, row_lo, row_hi, stream << 16 | step), key = (seed_lo, seed_hi).  The reference has
+counter = (col4 -- col8 for the packed reverse-noise stream --, row_lo, row_hi, stream << 16 | step), key = (seed_lo, seed_hi).  The reference has
 no counterpart (it calls torch.randn, models/diffusion.py:335,409,443); this is pinned by the
 Random123 known-answer vectors in tests/test_philox.py.
 """
@@ -54,8 +54,13 @@ def u01(w: np.ndarray) -> np.ndarray:
     return (unit_1_2(w) - np.float32(1.0)).astype(np.float32)
 
 
+STREAM_REVERSE = 0      # csrc/philox.cuh: the reverse-step noise uses the PACKED mapping (one word per Box-Muller pair)
+
+
 def normals(seed: int, rows: np.ndarray, d: int, stream: int, step: int) -> np.ndarray:
-    """fp64-evaluated Box-Muller on the same words: float64 [len(rows), d]."""
+    """fp64-evaluated Box-Muller on the same words, in the stream's mapping (csrc/philox.cuh): float64 [len(rows), d]."""
+    if stream == STREAM_REVERSE:
+        return normals_packed(seed, rows, d, stream, step)
     ncol4 = (d + 3) // 4
     w = words(seed, rows, ncol4, stream, step)
     f = unit_1_2(w)
@@ -67,3 +72,17 @@ def normals(seed: int, rows: np.ndarray, d: int, stream: int, step: int) -> np.n
     t1 = 2.0 * np.pi * u_a[..., 3]
     z = np.stack([r0 * np.cos(t0), r0 * np.sin(t0), r1 * np.cos(t1), r1 * np.sin(t1)], axis=-1)
     return z.reshape(len(rows), ncol4 * 4)[:, :d]
+
+
+def normals_packed(seed: int, rows: np.ndarray, d: int, stream: int, step: int) -> np.ndarray:
+    """PACKED mapping: counter word 0 = column / 8, every 32-bit word gives one pair -- radius uniform u1 = 1 - (w >> 12) / 2^20 in
+    (0, 1], angle 2 pi (w & 0xFFF) / 2^12 -- so a Philox block yields the 8 normals of columns 8b .. 8b + 7 (word j -> 2j, 2j + 1)."""
+    ncol8 = (d + 7) // 8
+    w = words(seed, rows, ncol8, stream, step)                                   # [n, ncol8, 4]
+    f_r = (np.uint32(0x3F800000) | ((w >> np.uint32(12)) << np.uint32(3))).astype(np.uint32).view(np.float32)
+    f_a = (np.uint32(0x3F800000) | ((w & np.uint32(0xFFF)) << np.uint32(11))).astype(np.uint32).view(np.float32)
+    u_r = (np.float32(2.0) - f_r).astype(np.float64)
+    ang = 2.0 * np.pi * (f_a - np.float32(1.0)).astype(np.float64)
+    r = np.sqrt(-2.0 * np.log(u_r))
+    z = np.stack([r * np.cos(ang), r * np.sin(ang)], axis=-1)                    # [n, ncol8, 4, 2]
+    return z.reshape(len(rows), ncol8 * 8)[:, :d]

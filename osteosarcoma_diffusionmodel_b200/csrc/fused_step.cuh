@@ -107,33 +107,33 @@ __device__ __forceinline__ void tmem_st_16(uint32_t taddr, const float (&v)[16])
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// out[i] = base[i] + kr * z_i for the 16 columns [4*col4_0, 4*col4_0 + 16) of one row, z_i the Philox4x32-10 + Box-Muller normals of
-// philox_normal_row (philox.cuh: same counters, same uniforms). |kr| is folded into the Box-Muller radius,
-// |kr| sqrt(-2 ln u1) = sqrt(k2 lg2 u1) with k2 = -2 ln2 kr^2; `neg` carries the sign of kr.
-__device__ __forceinline__ void philox_axpy_normal16(uint64_t seed, uint64_t row, uint32_t col4_0, uint32_t stream, uint32_t step, float k2, bool neg,
+// out[i] = base[i] + kr * z_i for the 16 columns [8*col8_0, 8*col8_0 + 16) of one row, z_i the PACKED Philox4x32-10 + Box-Muller normals of
+// philox_normal_row_packed (philox.cuh: same counters, same uniforms; two Philox blocks, one word per pair). |kr| is folded into the
+// Box-Muller radius, |kr| sqrt(-2 ln u1) = sqrt(k2 lg2 u1) with k2 = -2 ln2 kr^2; `neg` carries the sign of kr.
+__device__ __forceinline__ void philox_axpy_normal16(uint64_t seed, uint64_t row, uint32_t col8_0, uint32_t stream, uint32_t step, float k2, bool neg,
                                                      const float (&base)[16], float (&out)[16]) {
-    uint4 c[4];
+    uint4 c[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-        c[i] = make_uint4(col4_0 + i, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), (stream << 16) | (step & 0xFFFFu));
-    philox4x32_10_batch<4>(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    for (int i = 0; i < 2; ++i)
+        c[i] = make_uint4(col8_0 + i, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), (stream << 16) | (step & 0xFFFFu));
+    philox4x32_10_batch<2>(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
         const uint32_t w[4] = {c[i].x, c[i].y, c[i].z, c[i].w};
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            // u1 = 2 - f in (0, 1] is never subnormal (>= 2^-23): the .ftz forms drop the denormal pre-scaling __log2f emits.
+        for (int h = 0; h < 4; ++h) {
+            // u1 in (0, 1] is never subnormal (>= 2^-20): the .ftz forms drop the denormal pre-scaling __log2f emits.
             // The angle is 2 pi f with f in [1, 2): one full turn more than 2 pi (f - 1), same sine and cosine, one FMUL instead of an FFMA.
-            const float u1 = 2.0f - unit_1_2(w[2 * h]);
-            const float th = unit_1_2(w[2 * h + 1]) * 6.283185307179586f;
+            const float u1 = packed_radius_uniform(w[h]);
+            const float th = packed_angle_1_2(w[h]) * 6.283185307179586f;
             float l2, r, s, co;
             asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
             asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(k2 * l2));
             asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(th));
             asm("cos.approx.ftz.f32 %0, %1;" : "=f"(co) : "f"(th));
             r = neg ? -r : r;
-            out[4 * i + 2 * h] = fmaf(r, co, base[4 * i + 2 * h]);
-            out[4 * i + 2 * h + 1] = fmaf(r, s, base[4 * i + 2 * h + 1]);
+            out[8 * i + 2 * h] = fmaf(r, co, base[8 * i + 2 * h]);
+            out[8 * i + 2 * h + 1] = fmaf(r, s, base[8 * i + 2 * h + 1]);
         }
     }
 }
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                         for (int i = 0; i < 16; ++i)
                             if (i < nvalid) v[i] = fmaf(kr, nz[i], v[i]);
                     } else {
-                        philox_axpy_normal16(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 2), STREAM_REVERSE, static_cast<uint32_t>(t), k2,
+                        philox_axpy_normal16(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 3), STREAM_REVERSE, static_cast<uint32_t>(t), k2,
                                              /*neg=*/true, v, v);
                     }
                 }
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                                 for (int i = 0; i < 16; ++i)
                                     if (i < nvalid) z[i] = sg * nz[i];
                             } else {
-                                philox_axpy_normal16(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 2), STREAM_REVERSE, static_cast<uint32_t>(t),
+                                philox_axpy_normal16(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 3), STREAM_REVERSE, static_cast<uint32_t>(t),
                                                      -1.3862943611198906f * sg * sg, /*neg=*/false, z, z);
                             }
                         }

@@ -896,7 +896,7 @@ struct Epilogue<EPI_DDPM> {
                 if (c0 + j < p.N) z[j] = nz[j];
             return;
         }
-        philox_normal_row<8>(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 2), STREAM_REVERSE, static_cast<uint32_t>(t), z);
+        philox_normal_row_packed<4>(p.seed, static_cast<uint64_t>(p.row_base + row), static_cast<uint32_t>(c0 >> 3), STREAM_REVERSE, static_cast<uint32_t>(t), z);
     }
 
     // One pass = 16 columns [c0, c0 + 16) of row `row`: chunks j4_0 .. j4_0 + 3 of the 128-byte swizzled row in the staged box.

@@ -3,6 +3,14 @@
 // row's noise is independent of how rows are sharded over GPUs.
 // The numpy restatement lives in oracle/philox_oracle.py and is compared bit-exactly
 // (uint32 words) and within 2e-6 (Box-Muller normals) in tests/test_philox.py.
+//
+// Two word -> normal mappings:
+//   * two words per Box-Muller pair (23-bit radius uniform, 23-bit angle), 4 normals per Philox block, counter word 0 = column / 4:
+//     x_T, q_sample noise (drawn once per patient / training row);
+//   * PACKED, for the reverse-step noise z (5142 x 1000 normals per patient: Philox was ~60 % of every instruction the sampling loop
+//     executed): ONE word per pair -- radius uniform from the top 20 bits (u1 = 1 - k / 2^20 in (0, 1], |z| <= 5.27), angle from the
+//     low 12 bits (4096 directions: every trigonometric moment below order 4096 is exact) -- so a block yields 8 normals and
+//     counter word 0 = column / 8. Half the Philox blocks: +9 % patients/s at the board's power cap.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -53,6 +61,19 @@ __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, 
     z1 = r * s;
 }
 
+// PACKED mapping: one word -> two normals (see the header of this file).
+__device__ __forceinline__ float packed_radius_uniform(uint32_t w) { return 2.0f - __uint_as_float(0x3f800000u | ((w >> 12) << 3)); }   // (0, 1], 2^20 levels
+__device__ __forceinline__ float packed_angle_1_2(uint32_t w) { return __uint_as_float(0x3f800000u | ((w & 0xFFFu) << 11)); }           // [1, 2), 2^12 levels
+__device__ __forceinline__ void box_muller_packed(uint32_t w, float& z0, float& z1) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(packed_radius_uniform(w))));   // sqrt(-2 ln u1)
+    float s, c;
+    __sincosf(6.283185307179586f * (packed_angle_1_2(w) - 1.0f), &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+__device__ __forceinline__ bool stream_is_packed(uint32_t stream) { return stream == STREAM_REVERSE; }
+
 // N independent Philox4x32-10 blocks advanced round by round (round loop outermost): N independent dependency
 // chains in flight instead of one, which is what keeps the integer pipes busy with few warps per scheduler.
 template <int N>
@@ -86,9 +107,33 @@ __device__ __forceinline__ void philox_normal_row(uint64_t seed, uint64_t row, u
     }
 }
 
+// PACKED: 8*N normals for columns [8*col8_0, 8*(col8_0 + N)) of one row.
+template <int N>
+__device__ __forceinline__ void philox_normal_row_packed(uint64_t seed, uint64_t row, uint32_t col8_0, uint32_t stream, uint32_t step, float (&z)[8 * N]) {
+    uint4 c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+        c[i] = make_uint4(col8_0 + i, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), (stream << 16) | (step & 0xFFFFu));
+    philox4x32_10_batch<N>(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        box_muller_packed(c[i].x, z[8 * i + 0], z[8 * i + 1]);
+        box_muller_packed(c[i].y, z[8 * i + 2], z[8 * i + 3]);
+        box_muller_packed(c[i].z, z[8 * i + 4], z[8 * i + 5]);
+        box_muller_packed(c[i].w, z[8 * i + 6], z[8 * i + 7]);
+    }
+}
+
+// The 4 normals of columns [4*col4, 4*col4 + 4) of one row, in the stream's mapping (elementwise kernels: 4 columns per thread).
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t row, uint32_t col4, uint32_t stream, uint32_t step) {
-    const uint4 w = philox_words(seed, row, col4, stream, step);
     float4 z;
+    if (stream_is_packed(stream)) {
+        const uint4 w = philox_words(seed, row, col4 >> 1, stream, step);
+        box_muller_packed((col4 & 1u) ? w.z : w.x, z.x, z.y);
+        box_muller_packed((col4 & 1u) ? w.w : w.y, z.z, z.w);
+        return z;
+    }
+    const uint4 w = philox_words(seed, row, col4, stream, step);
     box_muller(w.x, w.y, z.x, z.y);
     box_muller(w.z, w.w, z.z, z.w);
     return z;

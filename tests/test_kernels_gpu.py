@@ -85,6 +85,17 @@ def test_philox_normals_match_oracle_and_moments(lib):
     assert abs(big.mean().item()) < 2e-3 and abs(big.var().item() - 1.0) < 3e-3
     kurt = (big ** 4).mean().item()
     assert abs(kurt - 3.0) < 0.02
+    # the PACKED mapping of the reverse-noise stream (stream 0: one word per Box-Muller pair, 20-bit radius / 12-bit angle)
+    packed = torch.zeros(4096, 2048, device="cuda")
+    _lib.check(lib.osteo_philox_normal(packed.data_ptr(), 4096, 2048, 1, 0, 0, 17, None))
+    assert abs(packed.mean().item()) < 2e-3 and abs(packed.var().item() - 1.0) < 3e-3
+    assert abs((packed ** 4).mean().item() - 3.0) < 0.02 and abs((packed ** 6).mean().item() - 15.0) < 0.3
+    assert 4.5 < packed.abs().max().item() <= 5.2655        # sqrt(2 * 20 * ln 2)
+    pairs = packed.view(4096, 1024, 2)
+    assert abs((pairs[..., 0] * pairs[..., 1]).mean().item()) < 2e-3                      # the two normals of a pair are uncorrelated
+    assert abs((packed[:, :-2] * packed[:, 2:]).mean().item()) < 2e-3                     # and so are neighbouring pairs
+    ref8 = P.normals(1, np.arange(4, dtype=np.uint64), 2048, 0, 17)
+    assert np.abs(packed[:4].cpu().numpy() - ref8).max() < 2e-4
     # distinct (stream, step, row_base) give distinct streams
     other = torch.zeros(4096, 2048, device="cuda")
     _lib.check(lib.osteo_philox_normal(other.data_ptr(), 4096, 2048, 1, 0, 1, 1, None))

@@ -28,3 +28,24 @@ def test_counter_layout_and_uniforms():
 def test_normals_have_unit_moments():
     z = P.normals(1, np.arange(512, dtype=np.uint64), 1024, 0, 10)
     assert abs(z.mean()) < 5e-3 and abs(z.var() - 1.0) < 1e-2
+
+
+def test_packed_mapping_of_the_reverse_noise_stream():
+    """oracle.normals: stream 0 (reverse-step noise) maps ONE word to a Box-Muller pair (20-bit radius uniform, 12-bit angle), so a block
+    covers 8 columns; the other streams keep two words per pair. Checks the bit layout on hand-computed values and the moments."""
+    seed, rows, d, step = 9, np.arange(3, dtype=np.uint64), 20, 5
+    z = P.normals(seed, rows, d, 0, step)
+    w = P.words(seed, rows, 3, 0, step)                   # ceil(20 / 8) blocks
+    for (r, b, j) in [(0, 0, 0), (1, 1, 3), (2, 2, 1)]:
+        word = int(w[r, b, j])
+        u1 = 1.0 - (word >> 12) / 2.0 ** 20
+        ang = 2.0 * np.pi * (word & 0xFFF) / 4096.0
+        rad = np.sqrt(-2.0 * np.log(u1))
+        col = 8 * b + 2 * j
+        assert abs(z[r, col] - rad * np.cos(ang)) < 1e-12 and abs(z[r, col + 1] - rad * np.sin(ang)) < 1e-12
+    assert z.shape == (3, 20)
+    other = P.normals(seed, rows, d, 1, step)             # two-word mapping: different values, same shape
+    assert other.shape == z.shape and not np.allclose(other, z)
+    big = P.normals(3, np.arange(256, dtype=np.uint64), 4096, 0, 1)
+    assert abs(big.mean()) < 4e-3 and abs(big.var() - 1.0) < 6e-3 and abs((big ** 4).mean() - 3.0) < 0.05
+    assert np.abs(big).max() <= np.sqrt(2 * 20 * np.log(2)) + 1e-12
