@@ -405,6 +405,20 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
     flops = 22.6e6 * B          # fwd + wgrad + dgrad per sample
     out["train_step"] = {"batch": B, "precision": model._precision, "ms_per_step": ms, "samples_per_s": B / (ms / 1e3), "fwd_bwd_ms": ms_fb,
                          "tensor_frac_fwd_bwd": flops / (ms_fb / 1e3) / 1e12 / tf_peak, "optimizer": "torch AdamW + clip_grad_norm_(1.0), unmodified"}
+    # the same step with the library's fused clip + AdamW (optim.FusedAdamW: two launches instead of torch's ~25 foreach launches)
+    try:
+        from osteosarcoma_diffusionmodel_b200.optim import FusedAdamW
+        fopt = FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, max_grad_norm=1.0)
+
+        def fstep():
+            fopt.zero_grad()
+            model(x0, cond, return_loss=True).backward()
+            fopt.step()
+
+        out["train_step"]["fused_optimizer_ms_per_step"] = timed(fstep, 3, 10)
+        del fopt
+    except Exception as e:
+        out["train_step"]["fused_optimizer_error"] = repr(e)
     out["train_step"]["note"] = ("forward + backward replayed as one executable graph per batch shape; weight / bias gradients on side streams beside the dgrad chain; "
                                  "the host enqueue of torch's clip + AdamW bounds the full step")
     # multi-task step (BASELINE.json configs[3]): + pathway coherence (10 pathways x 15 genes), 2 sign rules, survival head

@@ -175,6 +175,18 @@ int osteo_ddpm_train_backward(osteo_ddpm_ctx* ctx, const float* cond_dev, long l
  * addresses on (keep the gradient tensors persistent to benefit); enable = 0 keeps every call eager. Default 1. */
 int osteo_ddpm_set_train_graph(osteo_ddpm_ctx* ctx, int enable);
 
+/* ---- optimiser step: replaces torch.nn.utils.clip_grad_norm_(params, max_norm) + torch.optim.AdamW.step() (utils/train.py:169-173,
+ * :242-244) for a list of fp32 tensors with two launches. create takes the element counts (host array); step takes HOST arrays of
+ * DEVICE pointers (params, grads, exp_avg, exp_avg_sq; re-uploaded only when an address changed), torch's hyper-parameters (doubles, like torch's Python scalars: the derived constants are rounded to fp32 once), the
+ * 1-based step count, and max_norm (<= 0: no clipping). The gradients are scaled in place by min(1, max_norm / (||g||_2 + 1e-6))
+ * exactly as clip_grad_norm_ does; norm_out_dev (optional, fp32 scalar on the device) receives the total norm before clipping. */
+typedef struct osteo_adamw osteo_adamw;
+int osteo_adamw_create(osteo_adamw** out, int n_tensors, const long long* numel_host);
+int osteo_adamw_destroy(osteo_adamw* h);
+int osteo_adamw_step(osteo_adamw* h, float* const* params_dev, float* const* grads_dev, float* const* exp_avg_dev,
+                     float* const* exp_avg_sq_dev, double lr, double beta1, double beta2, double eps, double weight_decay,
+                     long long step, double max_norm, float* norm_out_dev, void* stream);
+
 /* Allocate the transposed weight copies the backward pass contracts against. Must be followed by
  * osteo_ddpm_set_weights (which fills them) before osteo_ddpm_train_step is asked for gradients. */
 int osteo_ddpm_enable_training(osteo_ddpm_ctx* ctx, int enable);

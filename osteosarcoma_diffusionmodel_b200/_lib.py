@@ -22,6 +22,7 @@ _u64 = C.c_uint64
 _u32 = C.c_uint32
 _i = C.c_int
 _f = C.c_float
+_d = C.c_double
 
 # name -> (restype, argtypes). Mirrors include/osteo_ddpm.h one to one; tests/test_abi.py checks the
 # header and this table declare the same symbols.
@@ -60,6 +61,9 @@ SIGNATURES = {
     "osteo_ddpm_train_inject": (_i, [_vp, _vp, _ll, _vp, _i, _vp, _vp]),
     "osteo_ddpm_train_backward": (_i, [_vp, _vp, _ll, _vp, C.POINTER(_vp), _i, _u64, _ll, C.POINTER(_vp), _i, _vp]),
     "osteo_ddpm_enable_training": (_i, [_vp, _i]),
+    "osteo_adamw_create": (_i, [C.POINTER(_vp), _i, C.POINTER(_ll)]),
+    "osteo_adamw_destroy": (_i, [_vp]),
+    "osteo_adamw_step": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), _d, _d, _d, _d, _d, _ll, _d, _vp, _vp]),
     "osteo_ddpm_profile_step": (_i, [_vp, _ll, _i, _u64, _ll, _vp, _i, _vp]),
     "osteo_ddpm_status": (_i, [_vp, _vp]),
     "osteo_ddpm_launch_count": (_ll, [_vp]),

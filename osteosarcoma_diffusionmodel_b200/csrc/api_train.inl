@@ -542,4 +542,98 @@ int osteo_ddpm_train_backward(osteo_ddpm_ctx* c, const float* cond_dev, long lon
     return 0;
 }
 
+
+// ---- fused clip_grad_norm_ + AdamW (utils/train.py:242-244)
+struct osteo_adamw {
+    int n = 0;
+    std::vector<long long> numel;
+    std::vector<const void*> host_ptrs;      // [4 * n]: last uploaded params | grads | exp_avg | exp_avg_sq
+    void* pinned = nullptr;                  // staging for the pointer tables
+    osteo::DevBuf ptrs, numel_dev, chunk_tensor, chunk_start, acc;
+    int chunks = 0;
+    ~osteo_adamw() {
+        if (pinned) cudaFreeHost(pinned);
+    }
+};
+
+int osteo_adamw_create(osteo_adamw** out, int n_tensors, const long long* numel_host) {
+    if (!out || n_tensors <= 0 || !numel_host) return fail("adamw_create: bad arguments");
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    std::unique_ptr<osteo_adamw> h(new osteo_adamw);
+    h->n = n_tensors;
+    h->numel.assign(numel_host, numel_host + n_tensors);
+    std::vector<int> ct;
+    std::vector<long long> cs;
+    for (int i = 0; i < n_tensors; ++i) {
+        if (numel_host[i] < 0) return fail("adamw_create: negative element count");
+        for (long long s0 = 0; s0 < numel_host[i]; s0 += OPT_CHUNK) {
+            ct.push_back(i);
+            cs.push_back(s0);
+        }
+    }
+    h->chunks = static_cast<int>(ct.size());
+    if (h->chunks == 0) return fail("adamw_create: nothing to optimise");
+    OSTEO_TRY(h->ptrs.alloc(sizeof(void*) * 4 * n_tensors));
+    OSTEO_TRY(h->numel_dev.alloc(sizeof(long long) * n_tensors));
+    OSTEO_TRY(h->chunk_tensor.alloc(sizeof(int) * ct.size()));
+    OSTEO_TRY(h->chunk_start.alloc(sizeof(long long) * cs.size()));
+    OSTEO_TRY(h->acc.alloc(sizeof(double)));
+    OSTEO_CUDA(cudaMallocHost(&h->pinned, sizeof(void*) * 4 * n_tensors));
+    OSTEO_CUDA(cudaMemcpy(h->numel_dev.p, numel_host, sizeof(long long) * n_tensors, cudaMemcpyHostToDevice));
+    OSTEO_CUDA(cudaMemcpy(h->chunk_tensor.p, ct.data(), sizeof(int) * ct.size(), cudaMemcpyHostToDevice));
+    OSTEO_CUDA(cudaMemcpy(h->chunk_start.p, cs.data(), sizeof(long long) * cs.size(), cudaMemcpyHostToDevice));
+    *out = h.release();
+    return 0;
+}
+
+int osteo_adamw_destroy(osteo_adamw* h) {
+    delete h;
+    return 0;
+}
+
+int osteo_adamw_step(osteo_adamw* h, float* const* params_dev, float* const* grads_dev, float* const* exp_avg_dev, float* const* exp_avg_sq_dev, double lr, double beta1,
+                     double beta2, double eps, double weight_decay, long long step, double max_norm, float* norm_out_dev, void* stream) {
+    if (!h) return fail("adamw_step: null handle");
+    if (!params_dev || !grads_dev || !exp_avg_dev || !exp_avg_sq_dev) return fail("adamw_step: null pointer table");
+    if (step < 1) return fail("adamw_step: step counts from 1");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int n = h->n;
+    std::vector<const void*> now(4 * n);
+    for (int i = 0; i < n; ++i) {
+        now[i] = params_dev[i];
+        now[n + i] = grads_dev[i];
+        now[2 * n + i] = exp_avg_dev[i];
+        now[3 * n + i] = exp_avg_sq_dev[i];
+        if (h->numel[i] > 0 && (!params_dev[i] || !grads_dev[i] || !exp_avg_dev[i] || !exp_avg_sq_dev[i])) return fail("adamw_step: tensor %d has a null pointer", i);
+    }
+    if (now != h->host_ptrs) {
+        // the staging buffer may still be in flight from the previous upload: wait for it (rare: addresses are stable in steady state)
+        if (!h->host_ptrs.empty()) OSTEO_CUDA(cudaStreamSynchronize(s));
+        std::memcpy(h->pinned, now.data(), sizeof(void*) * 4 * n);
+        OSTEO_CUDA(cudaMemcpyAsync(h->ptrs.p, h->pinned, sizeof(void*) * 4 * n, cudaMemcpyHostToDevice, s));
+        h->host_ptrs = now;
+    }
+    OptTables t;
+    float** base = h->ptrs.as<float*>();
+    t.params = base;
+    t.grads = base + n;
+    t.exp_avg = base + 2 * n;
+    t.exp_avg_sq = base + 3 * n;
+    t.numel = h->numel_dev.as<long long>();
+    t.chunk_tensor = h->chunk_tensor.as<int>();
+    t.chunk_start = h->chunk_start.as<long long>();
+    if (max_norm > 0.0) {
+        OSTEO_CUDA(cudaMemsetAsync(h->acc.p, 0, sizeof(double), s));
+        opt_sumsq_kernel<<<h->chunks, 256, 0, s>>>(t, h->acc.as<double>());
+        OSTEO_CUDA(cudaGetLastError());
+    }
+    const double bc1 = 1.0 - std::pow(beta1, static_cast<double>(step));
+    const double bc2 = 1.0 - std::pow(beta2, static_cast<double>(step));
+    opt_adamw_kernel<<<h->chunks, 256, 0, s>>>(t, h->acc.as<double>(), static_cast<float>(max_norm), static_cast<float>(1.0 - lr * weight_decay),
+                                               static_cast<float>(1.0 - beta1), static_cast<float>(beta2), static_cast<float>(1.0 - beta2), static_cast<float>(eps),
+                                               static_cast<float>(lr / bc1), static_cast<float>(std::sqrt(bc2)), norm_out_dev);
+    OSTEO_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // extern "C"

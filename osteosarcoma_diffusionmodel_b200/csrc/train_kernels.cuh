@@ -268,4 +268,71 @@ __global__ void cond_bwd_rows_kernel(const float* __restrict__ dh0, long long n,
 
 __global__ void zero_double_kernel(double* p) { *p = 0.0; }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// clip_grad_norm_(max_norm) + AdamW.step() over a list of tensors in two launches (utils/train.py:242-244 run the torch foreach
+// versions: ~25 launches and 0.9 ms of host time per step for 52 tensors). Work is cut into chunks of OPT_CHUNK elements of one
+// tensor each (multi-tensor apply): chunk c = (tensor id, first element).
+constexpr int OPT_CHUNK = 4096;
+struct OptTables {
+    float* const* params;
+    float* const* grads;
+    float* const* exp_avg;
+    float* const* exp_avg_sq;
+    const long long* numel;
+    const int* chunk_tensor;
+    const long long* chunk_start;
+};
+
+__global__ void opt_sumsq_kernel(OptTables t, double* __restrict__ acc) {
+    const int ti = t.chunk_tensor[blockIdx.x];
+    const long long s0 = t.chunk_start[blockIdx.x];
+    const long long n = t.numel[ti] - s0 < OPT_CHUNK ? t.numel[ti] - s0 : OPT_CHUNK;
+    const float* g = t.grads[ti] + s0;
+    float a = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a = fmaf(g[i], g[i], a);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    __shared__ float red[8];
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = a;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < static_cast<int>(blockDim.x >> 5); ++w) s += static_cast<double>(red[w]);
+        atomicAdd(acc, s);
+    }
+}
+
+// torch.optim.AdamW (decoupled weight decay, no amsgrad) in torch's operation order, after the gradient has been scaled by
+// clip = min(1, max_norm / (||g|| + 1e-6)) as clip_grad_norm_ does (the scaled gradient is written back, as torch does in place).
+// decay = 1 - lr * weight_decay, w1 = 1 - beta1, w2 = 1 - beta2 are formed on the host in double and rounded once, as torch's Python scalars are
+// (1.0f - 0.999f differs from float(1 - 0.999) by 1.3e-5 relative).
+__global__ void opt_adamw_kernel(OptTables t, const double* __restrict__ sumsq, float max_norm, float decay, float w1, float beta2, float w2, float eps,
+                                 float step_size, float bc2_sqrt, float* __restrict__ norm_out) {
+    float clip = 1.0f;
+    if (max_norm > 0.0f) {
+        const float total = static_cast<float>(sqrt(*sumsq));
+        clip = fminf(max_norm / (total + 1e-6f), 1.0f);
+        if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = total;
+    }
+    const int ti = t.chunk_tensor[blockIdx.x];
+    const long long s0 = t.chunk_start[blockIdx.x];
+    const long long n = t.numel[ti] - s0 < OPT_CHUNK ? t.numel[ti] - s0 : OPT_CHUNK;
+    float* p = t.params[ti] + s0;
+    float* g = t.grads[ti] + s0;
+    float* m = t.exp_avg[ti] + s0;
+    float* v = t.exp_avg_sq[ti] + s0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float gi = max_norm > 0.0f ? __fmul_rn(g[i], clip) : g[i];
+        if (max_norm > 0.0f) g[i] = gi;
+        float pi = __fmul_rn(p[i], decay);
+        const float mi = fmaf(gi - m[i], w1, m[i]);                       // exp_avg.lerp_(grad, 1 - beta1)
+        const float vi = fmaf(__fmul_rn(gi, gi), w2, __fmul_rn(v[i], beta2));   // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+        const float denom = __fdiv_rn(__fsqrt_rn(vi), bc2_sqrt) + eps;
+        pi = fmaf(-step_size, __fdiv_rn(mi, denom), pi);                  // param.addcdiv_(exp_avg, denom, value=-step_size)
+        m[i] = mi;
+        v[i] = vi;
+        p[i] = pi;
+    }
+}
+
 }  // namespace osteo

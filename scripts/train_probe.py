@@ -27,7 +27,17 @@ def step():
     opt.step()
 
 
-for name, fn in (("fwd_bwd", fwd_bwd), ("full step", step)):
+from osteosarcoma_diffusionmodel_b200.optim import FusedAdamW
+fopt = FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, max_grad_norm=1.0)
+
+
+def fused_step():
+    fopt.zero_grad()
+    model(x0, cond, return_loss=True).backward()
+    fopt.step()
+
+
+for name, fn in (("fwd_bwd", fwd_bwd), ("full step", step), ("full step, FusedAdamW", fused_step)):
     for _ in range(3):
         fn()
     torch.cuda.synchronize()

@@ -214,3 +214,62 @@ def test_backward_after_a_second_forward_is_refused():
         first.backward()
     second.backward()
     assert all(p.grad is not None for p in model.parameters())
+
+
+@pytest.mark.parametrize("max_norm", [1.0, None])
+def test_fused_adamw_tracks_torch_clip_and_adamw(max_norm):
+    """osteo_adamw_step (two launches) against torch.nn.utils.clip_grad_norm_ + torch.optim.AdamW.step (utils/train.py:242-244) on
+    the same gradients for 6 steps: parameters, moments, clipped gradients and the reported norm; optimizer state_dicts are
+    interchangeable."""
+    from osteosarcoma_diffusionmodel_b200.optim import FusedAdamW
+
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(5142, 256), (256,), (512, 512), (3, 64), (1,), (4097,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device="cuda", generator=g)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = FusedAdamW(pa, lr=1e-2, weight_decay=1e-2, max_grad_norm=max_norm)
+    ob = torch.optim.AdamW(pb, lr=1e-2, weight_decay=1e-2)
+    for step in range(6):
+        scale = 10.0 if step % 2 == 0 else 1e-3          # clipping active / inactive
+        for a, b in zip(pa, pb):
+            gr = torch.randn(a.shape, device="cuda", generator=g) * scale
+            a.grad, b.grad = gr.clone(), gr.clone()
+        v0 = [p._version for p in pa]
+        oa.step()
+        assert all(p._version > v for p, v in zip(pa, v0))       # weight caches keyed on the version see the update
+        if max_norm is not None:
+            ref_norm = torch.nn.utils.clip_grad_norm_(pb, max_norm)
+            assert abs(oa.last_grad_norm.item() - ref_norm.item()) < 1e-5 * ref_norm.item()
+            for a, b in zip(pa, pb):
+                assert rel(a.grad, b.grad) < 1e-6
+        ob.step()
+        for a, b in zip(pa, pb):
+            assert rel(a, b) < 2e-6
+            assert rel(oa.state[a]["exp_avg"], ob.state[b]["exp_avg"]) < 2e-6
+            assert rel(oa.state[a]["exp_avg_sq"], ob.state[b]["exp_avg_sq"]) < 2e-6
+    # a torch AdamW checkpoint loads into the fused optimizer and vice versa
+    oa.load_state_dict(ob.state_dict())
+    ob.load_state_dict(oa.state_dict())
+    assert int(oa.state[pa[0]]["step"]) == 6
+
+
+def test_fused_adamw_drives_the_model():
+    """The drop-in loop with the fused optimiser: the model repacks its weights after every step (version counters bumped) and the loss falls."""
+    from osteosarcoma_diffusionmodel_b200.optim import FusedAdamW
+
+    case = load_case("smoke")
+    model = build_model(case, "bf16")
+    model.train()
+    opt = FusedAdamW(model.parameters(), lr=2e-3, weight_decay=1e-5, max_grad_norm=1.0)
+    x0, cond = case["x0"].cuda(), case["cond"].cuda()
+    torch.manual_seed(0)
+    model.manual_seed(0)
+    losses = []
+    for _ in range(30):
+        opt.zero_grad()
+        loss = model(x0, cond)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5])
+    model.check_status()
