@@ -227,6 +227,8 @@ struct osteo_ddpm_ctx {
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every GEMM launch
     // graph caches of the training path (api_train.inl): weight repack after an optimizer step, forward + backward
     GraphSlot weights_graph, train_graph;
+    cudaStream_t aux[3] = {nullptr, nullptr, nullptr};      // lanes of the weight repack
+    cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};
     int train_graph_enable = 1;
     DevBuf seed_dev;                     // u64: Philox key of the graph-replayed training step
 
@@ -239,6 +241,11 @@ struct osteo_ddpm_ctx {
     int lo_boxes() const { return x3() ? DP / BK : 0; }
     __nv_bfloat16* xb_ptr() const { return xb.as<__nv_bfloat16>(); }
     ~osteo_ddpm_ctx() {
+        for (int i = 0; i < 3; ++i) {
+            if (aux[i]) cudaStreamDestroy(aux[i]);
+            if (aux_join[i]) cudaEventDestroy(aux_join[i]);
+        }
+        if (aux_fork) cudaEventDestroy(aux_fork);
         if (graph_exec) cudaGraphExecDestroy(graph_exec);
         if (graph_exec_multi) cudaGraphExecDestroy(graph_exec_multi);
     }
@@ -879,35 +886,55 @@ int osteo_ddpm_set_weights(osteo_ddpm_ctx* c, const float* const* w, int n_tenso
     cudaStream_t s0 = static_cast<cudaStream_t>(stream);
     // After every optimizer step the same 52 tensors are repacked (bf16 [hi|lo] operands, transposes for the backward pass, the
     // time table): ~30 small launches, replayed as one graph from the third call with the same addresses on (see GraphSlot).
+    if (!c->aux_fork) {
+        for (int i = 0; i < 3; ++i) {
+            OSTEO_CUDA(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+            OSTEO_CUDA(cudaEventCreateWithFlags(&c->aux_join[i], cudaEventDisableTiming));
+        }
+        OSTEO_CUDA(cudaEventCreateWithFlags(&c->aux_fork, cudaEventDisableTiming));
+    }
+    // The repacks of different layers are independent: they are spread over four lanes (`s` + three library streams forked from it and
+    // joined back), which become parallel branches of the captured graph -- ~30 dependent 3 us launches were 0.1 ms of every training step.
     auto enqueue = [&](cudaStream_t s) -> int {
-        auto copy = [&](DevBuf& dst, const float* src) -> int {
-            OSTEO_CUDA(cudaMemcpyAsync(dst.p, src, dst.bytes, cudaMemcpyDeviceToDevice, s));
+        cudaStream_t lane[4] = {s, c->aux[0], c->aux[1], c->aux[2]};
+        OSTEO_CUDA(cudaEventRecord(c->aux_fork, s));
+        for (int i = 1; i < 4; ++i) OSTEO_CUDA(cudaStreamWaitEvent(lane[i], c->aux_fork, 0));
+        auto copy = [&](DevBuf& dst, const float* src, cudaStream_t q) -> int {
+            OSTEO_CUDA(cudaMemcpyAsync(dst.p, src, dst.bytes, cudaMemcpyDeviceToDevice, q));
             return 0;
         };
-        OSTEO_TRY(copy(c->ce_w0, w[0]));
-        OSTEO_TRY(copy(c->ce_b0, w[1]));
-        OSTEO_TRY(copy(c->ce_w2, w[2]));
-        OSTEO_TRY(copy(c->ce_b2, w[3]));
-        OSTEO_TRY(c->in_proj.upload(w[4], w[5], c->sms, s));
-        OSTEO_TRY(copy(c->cp_w, w[6]));
-        OSTEO_TRY(copy(c->cp_b, w[7]));
-        OSTEO_TRY(copy(c->tp_w, w[8]));
-        OSTEO_TRY(copy(c->tp_b, w[9]));
+        // lane 0: the small fp32 layers, their transposes and the time table that depends on them
+        OSTEO_TRY(copy(c->ce_w0, w[0], s));
+        OSTEO_TRY(copy(c->ce_b0, w[1], s));
+        OSTEO_TRY(copy(c->ce_w2, w[2], s));
+        OSTEO_TRY(copy(c->ce_b2, w[3], s));
+        OSTEO_TRY(copy(c->cp_w, w[6], s));
+        OSTEO_TRY(copy(c->cp_b, w[7], s));
+        OSTEO_TRY(copy(c->tp_w, w[8], s));
+        OSTEO_TRY(copy(c->tp_b, w[9], s));
         transpose_f32_kernel<<<(c->E * c->C + 255) / 256, 256, 0, s>>>(c->ce_w0.as<float>(), c->E, c->C, c->ce_w0t.as<float>());
         transpose_f32_kernel<<<(c->E * c->E + 255) / 256, 256, 0, s>>>(c->ce_w2.as<float>(), c->E, c->E, c->ce_w2t.as<float>());
         transpose_f32_kernel<<<(c->h0() * c->E + 255) / 256, 256, 0, s>>>(c->cp_w.as<float>(), c->h0(), c->E, c->cp_wt.as<float>());
         transpose_f32_kernel<<<(c->h0() * c->TD + 255) / 256, 256, 0, s>>>(c->tp_w.as<float>(), c->h0(), c->TD, c->tp_wt.as<float>());
         OSTEO_CUDA(cudaGetLastError());
-        int idx = 10;
+        OSTEO_TRY(rebuild_time_table(c, s));
+        // lanes 1..3: the packed GEMM operands, the two 5142-wide projections on lanes of their own
+        OSTEO_TRY(c->in_proj.upload(w[4], w[5], c->sms, lane[1]));
+        int idx = 10, k = 0;
         for (auto& hb : c->halves) {
-            OSTEO_TRY(hb->lin.upload(w[idx], w[idx + 1], c->sms, s));
-            OSTEO_TRY(copy(hb->gamma, w[idx + 2]));
-            OSTEO_TRY(copy(hb->beta, w[idx + 3]));
+            cudaStream_t q = lane[3 - (k++ & 1) * 3];      // alternate lane 3 / lane 0
+            OSTEO_TRY(hb->lin.upload(w[idx], w[idx + 1], c->sms, q));
+            OSTEO_TRY(copy(hb->gamma, w[idx + 2], q));
+            OSTEO_TRY(copy(hb->beta, w[idx + 3], q));
             idx += 4;
         }
-        OSTEO_TRY(c->out_proj.upload(w[idx], w[idx + 1], c->sms, s));
+        OSTEO_TRY(c->out_proj.upload(w[idx], w[idx + 1], c->sms, lane[2]));
         c->launches += 2 + static_cast<long long>(c->halves.size());
-        return rebuild_time_table(c, s);
+        for (int i = 1; i < 4; ++i) {
+            OSTEO_CUDA(cudaEventRecord(c->aux_join[i - 1], lane[i]));
+            OSTEO_CUDA(cudaStreamWaitEvent(s, c->aux_join[i - 1], 0));
+        }
+        return 0;
     };
     std::vector<unsigned long long> key{static_cast<unsigned long long>(c->precision), reinterpret_cast<unsigned long long>(c->out_proj.wt.p),
                                         static_cast<unsigned long long>(c->have_emb)};
