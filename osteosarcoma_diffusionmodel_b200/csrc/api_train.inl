@@ -54,6 +54,8 @@ static int ensure_train_ws(osteo_ddpm_ctx* c) {
     OSTEO_TRY(w.cond_copy.alloc(static_cast<size_t>(cap) * c->C * sizeof(float)));
     OSTEO_TRY(w.loss_tmp.alloc(sizeof(float)));
     c->train_graph.reset();
+    c->train_fwd_graph.reset();
+    c->train_bwd_graph.reset();
     for (int i = 0; i < 2; ++i) {
         OSTEO_CUDA(cudaStreamCreateWithFlags(&w.side[i], cudaStreamNonBlocking));
         OSTEO_CUDA(cudaEventCreateWithFlags(&w.ev_join[i], cudaEventDisableTiming));
@@ -451,7 +453,11 @@ int osteo_ddpm_enable_training(osteo_ddpm_ctx* c, int enable) {
 int osteo_ddpm_set_train_graph(osteo_ddpm_ctx* c, int enable) {
     OSTEO_TRY(check_ctx(c));
     c->train_graph_enable = enable ? 1 : 0;
-    if (!enable) c->train_graph.reset();
+    if (!enable) {
+        c->train_graph.reset();
+        c->train_fwd_graph.reset();
+        c->train_bwd_graph.reset();
+    }
     return 0;
 }
 
@@ -499,9 +505,29 @@ int osteo_ddpm_train_forward(osteo_ddpm_ctx* c, const float* x0_dev, const float
     if (!c->out_proj.wt.p) return fail("train_forward: call osteo_ddpm_enable_training(ctx, 1) and osteo_ddpm_set_weights first");
     OSTEO_TRY(ensure_train_ws(c));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    TrainWorkspace& w = c->train;
     OSTEO_TRY(train_pre(c, x0_dev, cond_dev, n, t_idx_dev, noise_dev, seed, row_base, s));
-    OSTEO_TRY(train_body(c, cond_dev, n, t_idx_dev, drop_masks_dev, train, seed, nullptr, row_base, loss_dev, nullptr, 0, s, /*phase=*/1));
-    c->train.fwd_n = n;
+    // graph replay as in osteo_ddpm_train_step, one cached graph per half
+    w.fwd_graphed = c->train_graph_enable && !noise_dev && !drop_masks_dev && !c->prof;
+    if (!w.fwd_graphed) {
+        OSTEO_TRY(train_body(c, cond_dev, n, t_idx_dev, drop_masks_dev, train, seed, nullptr, row_base, loss_dev, nullptr, 0, s, /*phase=*/1));
+    } else {
+        OSTEO_CUDA(cudaMemcpyAsync(w.t_copy.p, t_idx_dev, sizeof(int) * n, cudaMemcpyDeviceToDevice, s));
+        OSTEO_CUDA(cudaMemcpyAsync(w.cond_copy.p, cond_dev, sizeof(float) * n * c->C, cudaMemcpyDeviceToDevice, s));
+        set_u64_kernel<<<1, 1, 0, s>>>(c->seed_dev.as<unsigned long long>(), seed);
+        OSTEO_CUDA(cudaGetLastError());
+        c->launches += 3;
+        std::vector<unsigned long long> key{static_cast<unsigned long long>(n), static_cast<unsigned long long>(train != 0), static_cast<unsigned long long>(row_base),
+                                            static_cast<unsigned long long>(c->precision), static_cast<unsigned long long>(c->ws_enable),
+                                            reinterpret_cast<unsigned long long>(c->acts[0]->ptr()), reinterpret_cast<unsigned long long>(w.deps.p),
+                                            reinterpret_cast<unsigned long long>(c->out_proj.wt.p)};
+        OSTEO_TRY(run_cached(c, c->train_fwd_graph, key, s, [&](cudaStream_t q) {
+            return train_body(c, w.cond_copy.as<float>(), n, w.t_copy.as<int>(), nullptr, train, seed, c->seed_dev.as<unsigned long long>(), row_base,
+                              w.loss_tmp.as<float>(), nullptr, 0, q, /*phase=*/1);
+        }));
+        OSTEO_CUDA(cudaMemcpyAsync(loss_dev, w.loss_tmp.p, sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
+    w.fwd_n = n;
     return 0;
 }
 
@@ -537,8 +563,23 @@ int osteo_ddpm_train_backward(osteo_ddpm_ctx* c, const float* cond_dev, long lon
     if (!grads_dev) return fail("train_backward: grads_dev is required");
     OSTEO_TRY(train_check(c, n, t_idx_dev, grads_dev, n_tensors, true));
     if (c->train.fwd_n != n) return fail("train_backward: no forward pass of %lld rows is pending (osteo_ddpm_train_forward)", n);
-    OSTEO_TRY(train_body(c, cond_dev, n, t_idx_dev, drop_masks_dev, train, seed, nullptr, row_base, nullptr, grads_dev, n_tensors, static_cast<cudaStream_t>(stream), /*phase=*/2));
-    c->train.fwd_n = -1;
+    TrainWorkspace& w = c->train;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!w.fwd_graphed || drop_masks_dev) {
+        OSTEO_TRY(train_body(c, cond_dev, n, t_idx_dev, drop_masks_dev, train, seed, nullptr, row_base, nullptr, grads_dev, n_tensors, s, /*phase=*/2));
+    } else {
+        // t / cond copies and the seed word were written by the matching train_forward
+        std::vector<unsigned long long> key{static_cast<unsigned long long>(n), static_cast<unsigned long long>(train != 0), static_cast<unsigned long long>(row_base),
+                                            static_cast<unsigned long long>(c->precision), static_cast<unsigned long long>(c->ws_enable),
+                                            reinterpret_cast<unsigned long long>(c->acts[0]->ptr()), reinterpret_cast<unsigned long long>(w.deps.p),
+                                            reinterpret_cast<unsigned long long>(c->out_proj.wt.p)};
+        for (int i = 0; i < n_tensors; ++i) key.push_back(reinterpret_cast<unsigned long long>(grads_dev[i]));
+        OSTEO_TRY(run_cached(c, c->train_bwd_graph, key, s, [&](cudaStream_t q) {
+            return train_body(c, w.cond_copy.as<float>(), n, w.t_copy.as<int>(), nullptr, train, seed, c->seed_dev.as<unsigned long long>(), row_base, nullptr,
+                              grads_dev, n_tensors, q, /*phase=*/2);
+        }));
+    }
+    w.fwd_n = -1;
     return 0;
 }
 

@@ -226,7 +226,7 @@ struct osteo_ddpm_ctx {
     long long graph_launches_per_step = 0;
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every GEMM launch
     // graph caches of the training path (api_train.inl): weight repack after an optimizer step, forward + backward
-    GraphSlot weights_graph, train_graph;
+    GraphSlot weights_graph, train_graph, train_fwd_graph, train_bwd_graph;      // the last two: the halves of the two-phase step
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};      // lanes of the weight repack
     cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};
     int train_graph_enable = 1;

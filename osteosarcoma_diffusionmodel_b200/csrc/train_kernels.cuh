@@ -14,6 +14,7 @@ namespace osteo {
 struct TrainWorkspace {
     long long cap = 0;
     long long fwd_n = -1;                        // rows of the pending forward pass (two-phase API), -1 = none
+    bool fwd_graphed = false;                    // that forward was graph-replayed: the backward half may use the library's t / cond copies
     // per half block
     std::vector<std::unique_ptr<DevBuf>> xhat;   // bf16 [cap, 2*n]  normalised pre-affine activations [hi|lo]
     std::vector<std::unique_ptr<DevBuf>> rstd;   // fp32 [cap, 8]

@@ -39,15 +39,24 @@ class _CorrLoss(torch.autograd.Function):
     """losses[s] of the column sets `ci` [S, 32] (int32, -1 padded) of data [n, G]; modes[s] = 0 (coherence) or +-1 (required sign)."""
 
     @staticmethod
-    def forward(ctx, data, ci, modes):
+    def forward(ctx, data, ci, modes, n_eff=None):
+        """n_eff (optional device scalar): the number of rows that count. The other rows must be EXACTLY ZERO in `data`; the moments are then
+        taken with a zero shift, to which such rows contribute nothing, and only the row count is replaced -- a row filter without
+        compaction, i.e. without a device-to-host synchronisation for the size of the compacted matrix."""
         data = data.contiguous()
         lib = _lib.load()
         n, G = data.shape
         S = ci.shape[0]
         rank, ws = D.world()
         # a shift near the column means conditions the fp64 moments; ranks must agree on it before their moments are summed
-        shift = data[0, ci.clamp(min=0).long()].contiguous() if ws == 1 else torch.zeros((S, 32), device=data.device, dtype=torch.float32)
-        mom = D.all_reduce_sum_(_moments_batched(data, ci, shift, (0, n)))
+        if ws == 1 and n_eff is None:
+            shift = data[0, ci.clamp(min=0).long()].contiguous()
+        else:
+            shift = torch.zeros((S, 32), device=data.device, dtype=torch.float32)
+        mom = _moments_batched(data, ci, shift, (0, n))
+        if n_eff is not None:
+            mom[:, 0] = n_eff.to(torch.float64)
+        mom = D.all_reduce_sum_(mom)
         losses = torch.empty(S, device=data.device, dtype=torch.float32)
         coef = torch.empty(S * 32 * 4, device=data.device, dtype=torch.float32)
         _lib.check(lib.osteo_corr_loss_finish(mom.data_ptr(), ci.data_ptr(), shift.data_ptr(), modes.data_ptr(), S, losses.data_ptr(), coef.data_ptr(),
@@ -63,19 +72,15 @@ class _CorrLoss(torch.autograd.Function):
         grad = torch.zeros_like(data)
         _lib.check(_lib.load().osteo_corr_loss_backward(data.data_ptr(), data.shape[0], data.shape[1], ci.data_ptr(), ci.shape[0], coef.data_ptr(), up.data_ptr(),
                                                         grad.data_ptr(), _lib.stream_handle()))
-        return grad, None, None
+        return grad, None, None, None
 
 
-def correlation_losses(data: torch.Tensor, column_sets: Sequence[Sequence[int]], modes: Sequence[int]) -> torch.Tensor:
-    """Differentiable per-set losses (fp32 [len(column_sets)]) of data [n, G] (fp32, CUDA): mode 0 = 1 - mean pairwise Pearson
-    correlation of the set's columns; mode +1 / -1 = max(0, -mode * Pearson(col 0, col 1))."""
-    if data.device.type != "cuda":
-        raise RuntimeError("correlation_losses computes only on a CUDA device; there is no CPU fallback")
+def pack_column_sets(column_sets: Sequence[Sequence[int]], modes: Sequence[int], device) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+    """Device-side index tensors of correlation_losses, in groups of at most 32 sets: [(ci int32 [S, 32] (-1 padded), modes int32 [S])].
+    Build them once for a fixed set list (BiologyConstrainedDiffusion does): every rebuild is a host-to-device copy per step."""
     if len(column_sets) != len(modes):
         raise ValueError("one mode per column set")
-    if data.shape[1] * 4 > 96 * 1024:
-        raise ValueError("gather the columns first: a row must fit the kernel's 96 KB staging buffer")
-    outs = []
+    packs = []
     for b0 in range(0, len(column_sets), 32):
         sets = column_sets[b0:b0 + 32]
         ci = torch.full((len(sets), 32), -1, dtype=torch.int32)
@@ -85,8 +90,23 @@ def correlation_losses(data: torch.Tensor, column_sets: Sequence[Sequence[int]],
             if modes[b0 + i] != 0 and len(cols) != 2:
                 raise ValueError("a required-sign rule is a pair of columns")
             ci[i, :len(cols)] = torch.tensor(list(cols), dtype=torch.int32)
-        outs.append(_CorrLoss.apply(data.to(torch.float32), ci.to(data.device), torch.tensor(list(modes[b0:b0 + 32]), dtype=torch.int32, device=data.device)))
-    return torch.cat(outs)
+        packs.append((ci.to(device), torch.tensor(list(modes[b0:b0 + 32]), dtype=torch.int32, device=device)))
+    return packs
+
+
+def correlation_losses(data: torch.Tensor, column_sets: Sequence[Sequence[int]] = (), modes: Sequence[int] = (), packed=None,
+                       n_eff: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Differentiable per-set losses (fp32 [n_sets]) of data [n, G] (fp32, CUDA): mode 0 = 1 - mean pairwise Pearson correlation of the
+    set's columns; mode +1 / -1 = max(0, -mode * Pearson(col 0, col 1)). `packed` = a cached pack_column_sets(...) result; `n_eff` = device
+    scalar, the number of rows that count when the others have been zeroed (see _CorrLoss.forward)."""
+    if data.device.type != "cuda":
+        raise RuntimeError("correlation_losses computes only on a CUDA device; there is no CPU fallback")
+    if data.shape[1] * 4 > 96 * 1024:
+        raise ValueError("gather the columns first: a row must fit the kernel's 96 KB staging buffer")
+    if packed is None:
+        packed = pack_column_sets(column_sets, modes, data.device)
+    data = data.to(torch.float32)
+    return torch.cat([_CorrLoss.apply(data, ci, md, n_eff) for ci, md in packed])
 
 
 class _AuxEvaluator:
@@ -106,16 +126,16 @@ class _AuxEvaluator:
         zero = torch.zeros((), device=dev)
         self.parts = {"pathway_coherence": zero, "mutation_expression": zero, "survival": zero}
         self.total = zero
-        keep = (o.diffusion.alphas_cumprod[t.long()] >= o.min_alpha_bar).nonzero().squeeze(1)
-        if keep.numel() < 3:
-            return None
+        # rows whose timestep still carries signal; filtered by zeroing (no compaction: nothing here waits for the device)
+        kf = (o.diffusion.alphas_cumprod[t.long()] >= o.min_alpha_bar).to(torch.float32)
+        n_eff = kf.sum()
         head = list(o.survival_predictor.parameters())
         with torch.enable_grad():
             xh = x0hat.detach().requires_grad_(True)
-            sub = xh.index_select(0, keep)
+            sub = xh * kf[:, None]
             total = zero
             if o._sets:
-                losses = correlation_losses(sub, o._sets, o._modes)
+                losses = correlation_losses(sub, packed=o._packed_sets(dev), n_eff=n_eff)
                 P = o._n_pathways
                 if P and o.pathway_coherence_weight:
                     self.parts["pathway_coherence"] = losses[:P].mean()
@@ -128,7 +148,8 @@ class _AuxEvaluator:
                 if u.shape[1] < o.latent_dim:
                     u = F.pad(u, (0, o.latent_dim - u.shape[1]))
                 pred = o.survival_predictor(u).squeeze(-1)
-                self.parts["survival"] = F.mse_loss(pred, self.survival_time.to(dev, torch.float32).index_select(0, keep))
+                err = (pred - self.survival_time.to(dev, torch.float32)) ** 2
+                self.parts["survival"] = (err * kf).sum() / n_eff.clamp(min=1.0)          # F.mse_loss over the kept rows
                 total = total + o.survival_weight * self.parts["survival"]
             if not total.requires_grad:
                 return None
@@ -205,8 +226,14 @@ class BiologyConstrainedDiffusion(nn.Module):
         self._sets: List[List[int]] = [[pos[c] for c in s] for s in abs_sets]         # positions inside the gathered x0hat matrix
         self._modes: List[int] = [0] * len(members) + [int(sign) for _, _, sign in rules]
         self._n_pathways = len(members)
+        self._packs = None          # (device, pack_column_sets(...)): index tensors uploaded once
         self.register_buffer("_aux_columns", torch.tensor(cols, dtype=torch.int32), persistent=False)
         self.register_buffer("_head_pos", torch.tensor([pos[c] for c in head_cols], dtype=torch.long), persistent=False)
+
+    def _packed_sets(self, device):
+        if self._packs is None or self._packs[0] != device:
+            self._packs = (device, pack_column_sets(self._sets, self._modes, device))
+        return self._packs[1]
 
     def forward(self, x, conditions, return_loss: bool = True, survival_time: Optional[torch.Tensor] = None):
         """Total multi-task loss (models/cvae.py:304-341). Under no_grad / eval, or with return_loss=False, this is the wrapped
