@@ -63,6 +63,7 @@ static int ensure_train_ws(osteo_ddpm_ctx* c) {
     OSTEO_CUDA(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
     (void)max_w;
     w.cap = cap;
+    ++c->generation;
     return 0;
 }
 
@@ -446,6 +447,7 @@ int osteo_ddpm_enable_training(osteo_ddpm_ctx* c, int enable) {
     OSTEO_CUDA(cudaDeviceSynchronize());
     for (auto& hb : c->halves) OSTEO_TRY(hb->lin.init_transposed());
     OSTEO_TRY(c->out_proj.init_transposed());
+    ++c->generation;
     c->have_weights = false;   // W^T copies are filled by the next osteo_ddpm_set_weights
     return 0;
 }
@@ -486,7 +488,7 @@ int osteo_ddpm_train_step(osteo_ddpm_ctx* c, const float* x0_dev, const float* c
     std::vector<unsigned long long> key{static_cast<unsigned long long>(n), static_cast<unsigned long long>(train != 0), static_cast<unsigned long long>(row_base),
                                         static_cast<unsigned long long>(c->precision), static_cast<unsigned long long>(c->ws_enable),
                                         reinterpret_cast<unsigned long long>(c->acts[0]->ptr()), reinterpret_cast<unsigned long long>(w.deps.p),
-                                        reinterpret_cast<unsigned long long>(c->out_proj.wt.p)};
+                                        reinterpret_cast<unsigned long long>(c->out_proj.wt.p), c->generation};
     for (int i = 0; i < n_tensors; ++i) key.push_back(reinterpret_cast<unsigned long long>(grads_dev[i]));
     OSTEO_TRY(run_cached(c, c->train_graph, key, s, [&](cudaStream_t q) {
         return train_body(c, w.cond_copy.as<float>(), n, w.t_copy.as<int>(), nullptr, train, seed, c->seed_dev.as<unsigned long long>(), row_base, w.loss_tmp.as<float>(),
@@ -520,7 +522,7 @@ int osteo_ddpm_train_forward(osteo_ddpm_ctx* c, const float* x0_dev, const float
         std::vector<unsigned long long> key{static_cast<unsigned long long>(n), static_cast<unsigned long long>(train != 0), static_cast<unsigned long long>(row_base),
                                             static_cast<unsigned long long>(c->precision), static_cast<unsigned long long>(c->ws_enable),
                                             reinterpret_cast<unsigned long long>(c->acts[0]->ptr()), reinterpret_cast<unsigned long long>(w.deps.p),
-                                            reinterpret_cast<unsigned long long>(c->out_proj.wt.p)};
+                                            reinterpret_cast<unsigned long long>(c->out_proj.wt.p), c->generation};
         OSTEO_TRY(run_cached(c, c->train_fwd_graph, key, s, [&](cudaStream_t q) {
             return train_body(c, w.cond_copy.as<float>(), n, w.t_copy.as<int>(), nullptr, train, seed, c->seed_dev.as<unsigned long long>(), row_base,
                               w.loss_tmp.as<float>(), nullptr, 0, q, /*phase=*/1);
@@ -572,7 +574,7 @@ int osteo_ddpm_train_backward(osteo_ddpm_ctx* c, const float* cond_dev, long lon
         std::vector<unsigned long long> key{static_cast<unsigned long long>(n), static_cast<unsigned long long>(train != 0), static_cast<unsigned long long>(row_base),
                                             static_cast<unsigned long long>(c->precision), static_cast<unsigned long long>(c->ws_enable),
                                             reinterpret_cast<unsigned long long>(c->acts[0]->ptr()), reinterpret_cast<unsigned long long>(w.deps.p),
-                                            reinterpret_cast<unsigned long long>(c->out_proj.wt.p)};
+                                            reinterpret_cast<unsigned long long>(c->out_proj.wt.p), c->generation};
         for (int i = 0; i < n_tensors; ++i) key.push_back(reinterpret_cast<unsigned long long>(grads_dev[i]));
         OSTEO_TRY(run_cached(c, c->train_bwd_graph, key, s, [&](cudaStream_t q) {
             return train_body(c, w.cond_copy.as<float>(), n, w.t_copy.as<int>(), nullptr, train, seed, c->seed_dev.as<unsigned long long>(), row_base, nullptr,

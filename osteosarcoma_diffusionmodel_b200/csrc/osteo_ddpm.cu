@@ -227,6 +227,7 @@ struct osteo_ddpm_ctx {
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every GEMM launch
     // graph caches of the training path (api_train.inl): weight repack after an optimizer step, forward + backward
     GraphSlot weights_graph, train_graph, train_fwd_graph, train_bwd_graph;      // the last two: the halves of the two-phase step
+    unsigned long long generation = 0;   // bumped by every (re)allocation of device buffers: part of every graph key (an address can be reused)
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};      // lanes of the weight repack
     cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};
     int train_graph_enable = 1;
@@ -871,6 +872,7 @@ int osteo_ddpm_reserve(osteo_ddpm_ctx* c, long long rows) {
     }
     c->train.release();
     c->cap = cap;
+    ++c->generation;
     c->h0_primed = false;
     c->shadow_valid = false;
     return 0;
@@ -937,7 +939,7 @@ int osteo_ddpm_set_weights(osteo_ddpm_ctx* c, const float* const* w, int n_tenso
         return 0;
     };
     std::vector<unsigned long long> key{static_cast<unsigned long long>(c->precision), reinterpret_cast<unsigned long long>(c->out_proj.wt.p),
-                                        static_cast<unsigned long long>(c->have_emb)};
+                                        static_cast<unsigned long long>(c->have_emb), c->generation};
     for (int i = 0; i < n_tensors; ++i) key.push_back(reinterpret_cast<unsigned long long>(w[i]));
     const bool had = c->have_weights;
     c->have_weights = true;       // rebuild_time_table (last step of `enqueue`) needs it

@@ -273,3 +273,35 @@ def test_fused_adamw_drives_the_model():
         losses.append(loss.item())
     assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5])
     model.check_status()
+
+
+def test_graph_replay_survives_batch_changes_and_reallocation():
+    """Alternating batch sizes (the larger one arrives late and forces the workspace to be re-allocated) and a sampling call in between:
+    the cached graphs are keyed by shape, addresses and an allocation generation, so every step equals the eager step."""
+    case = load_case("linear3")
+    x0, cond = synth.make_cohort(700, 20, 90, 10, 2, seed=6)
+    x0, cond = x0.cuda(), cond.cuda()
+    order = [64, 64, 64, 300, 300, 64, 300, 700, 700, 64, 700]
+
+    def run(graph):
+        model = build_model(case, "fp32x3")
+        model.set_train_graph(graph)
+        model.train()
+        model.manual_seed(3)
+        torch.manual_seed(3)
+        out = []
+        for i, b in enumerate(order):
+            model.zero_grad()
+            loss = model(x0[:b], cond[:b])
+            loss.backward()
+            out.append((loss.item(), model.unet.output_proj.weight.grad.norm().item(), model.unet.input_proj.weight.grad.norm().item()))
+            if i == 5:
+                model.eval()
+                model.sample(cond[:130], 130, seed=1, t_stop=995)
+                model.train()
+        model.check_status()
+        return out
+
+    for a, b in zip(run(True), run(False)):
+        for u, v in zip(a, b):
+            assert abs(u - v) < 2e-5 * abs(v)
