@@ -365,6 +365,7 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
     import torch
     from oracle import ddpm_oracle as O            # CPU-port legs only
     from oracle import validators_oracle as V      # CPU-port legs only
+    from osteosarcoma_diffusionmodel_b200 import _lib
     from osteosarcoma_diffusionmodel_b200 import synthetic as synth
     from osteosarcoma_diffusionmodel_b200.validation import BiologicalValidator
 
@@ -473,6 +474,33 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
         cpu_step()
     cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
     out["train_step"]["cpu_port"] = {"batch": 1024, "ms_per_step": cpu_ms, "samples_per_s": 1024 / (cpu_ms / 1e3), "cores": torch.get_num_threads()}
+
+    # -------- standalone elementwise kernels of the path on 100k x 5142 fp32 (north_star: q_sample / reverse update at >= 70 % of HBM)
+    try:
+        ne = 100_000
+        ex0 = torch.randn(ne, D, device=dev)
+        ez = torch.randn(ne, D, device=dev)
+        eeps = torch.randn(ne, D, device=dev)
+        et = torch.randint(0, T_STEPS, (ne,), device=dev)
+        eout = torch.empty_like(ex0)
+        model._ensure_ctx(ne)
+        lib_, s_ = _lib.load(), _lib.stream_handle()
+        row_b = D * 4
+        ecases = {
+            "q_sample_injected_noise": (lambda: model.q_sample(ex0, et, ez), 3 * row_b),
+            "q_sample_philox_noise": (lambda: model.q_sample(ex0, et), 3 * row_b),
+            "reverse_update_injected_z": (lambda: _lib.check(lib_.osteo_ddpm_reverse_update(model._ctx, eout.data_ptr(), eeps.data_ptr(), ez.data_ptr(), ne, 500, 0, 0, s_)), 4 * row_b),
+            "reverse_update_philox_z": (lambda: _lib.check(lib_.osteo_ddpm_reverse_update(model._ctx, eout.data_ptr(), eeps.data_ptr(), None, ne, 500, 7, 0, s_)), 3 * row_b),
+            "store_state": (lambda: _lib.check(lib_.osteo_ddpm_store_state(model._ctx, eout.data_ptr(), ne, s_)), 2 * row_b),
+        }
+        out["elementwise"] = {"rows": ne, "note": "algorithmic bytes (each tensor read or written once) / CUDA-event time, through the public calls"}
+        for name, (fn, bpr) in ecases.items():
+            ms = timed(fn, 2, 5)
+            gbs = bpr * ne / (ms / 1e3) / 1e9
+            out["elementwise"][name] = {"ms": ms, "gb_per_s": gbs, "hbm_frac": gbs / hbm_peak}
+        del ex0, ez, eeps, eout
+    except Exception as e:
+        out["elementwise"] = {"error": repr(e)}
 
     # -------- RBF-MMD (utils/validation.py:273-298): N = M = 16384 rows of 5142 features
     n = 16384

@@ -76,8 +76,14 @@ __global__ void load_state_kernel(const float* __restrict__ src, long long n, in
         const long long r = i / q;
         const int c = static_cast<int>(i % q) * 4;
         float v[4];
+        if ((d & 1) == 0 && c + 3 < d) {
+            // even row pitch: every (row, even column) is 8-byte aligned -> two 64-bit loads instead of four 32-bit ones
+            const float2 a = *reinterpret_cast<const float2*>(src + r * d + c), b = *reinterpret_cast<const float2*>(src + r * d + c + 2);
+            v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) v[j] = (c + j < d) ? src[r * d + c + j] : 0.0f;
+            for (int j = 0; j < 4; ++j) v[j] = (c + j < d) ? src[r * d + c + j] : 0.0f;
+        }
         if (x) *reinterpret_cast<float4*>(x + x_blocked_off(r, c, x_nbox, x_shift)) = make_float4(v[0], v[1], v[2], v[3]);
         *reinterpret_cast<uint2*>(xb + xb_blocked_off(r, c, xb_nbox)) = make_uint2(pack2(v[0], v[1]), pack2(v[2], v[3]));
         if (lo_boxes > 0)
@@ -100,11 +106,21 @@ __global__ void reshadow_kernel(const float* __restrict__ x, int x_nbox, int x_s
 }
 
 __global__ void store_state_kernel(const float* __restrict__ x, int x_nbox, int x_shift, float* __restrict__ dst, long long n, int d) {
-    const long long total = n * d;
+    const int q = (d + 3) / 4;       // one thread per 4 columns: a 128-bit read of the blocked state, 64-bit writes when the row pitch is even
+    const long long total = n * q;
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const long long r = i / d;
-        const int c = static_cast<int>(i % d);
-        dst[i] = x[x_blocked_off(r, c, x_nbox, x_shift)];
+        const long long r = i / q;
+        const int c = static_cast<int>(i % q) * 4;
+        const float4 v = *reinterpret_cast<const float4*>(x + x_blocked_off(r, c, x_nbox, x_shift));
+        float* o = dst + r * d + c;
+        if ((d & 1) == 0 && c + 3 < d) {
+            *reinterpret_cast<float2*>(o) = make_float2(v.x, v.y);
+            *reinterpret_cast<float2*>(o + 2) = make_float2(v.z, v.w);
+        } else {
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+            for (int j = 0; j < 4; ++j)
+                if (c + j < d) o[j] = vv[j];
+        }
     }
 }
 
@@ -202,14 +218,30 @@ __global__ void q_sample_kernel(const float* __restrict__ x0, const int* __restr
             const float4 zz = philox_normal4(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), STREAM_QNOISE, salt);
             z[0] = zz.x; z[1] = zz.y; z[2] = zz.z; z[3] = zz.w;
         }
+        const int c0 = c4 * 4;
+        if ((d & 1) == 0 && c0 + 3 < d) {
+            // even row pitch: 64-bit accesses (every (row, even column) is 8-byte aligned)
+            const long long o = r * d + c0;
+            const float2 xa = *reinterpret_cast<const float2*>(x0 + o), xb2 = *reinterpret_cast<const float2*>(x0 + o + 2);
+            if (GEN) {
+                *reinterpret_cast<float2*>(noise + o) = make_float2(z[0], z[1]);
+                *reinterpret_cast<float2*>(noise + o + 2) = make_float2(z[2], z[3]);
+            } else {
+                const float2 na = *reinterpret_cast<const float2*>(noise + o), nb = *reinterpret_cast<const float2*>(noise + o + 2);
+                z[0] = na.x; z[1] = na.y; z[2] = nb.x; z[3] = nb.y;
+            }
+            // two rounded products then a rounded add, as the reference's elementwise ops do (bit-exact)
+            *reinterpret_cast<float2*>(xt + o) = make_float2(__fadd_rn(__fmul_rn(a, xa.x), __fmul_rn(b, z[0])), __fadd_rn(__fmul_rn(a, xa.y), __fmul_rn(b, z[1])));
+            *reinterpret_cast<float2*>(xt + o + 2) = make_float2(__fadd_rn(__fmul_rn(a, xb2.x), __fmul_rn(b, z[2])), __fadd_rn(__fmul_rn(a, xb2.y), __fmul_rn(b, z[3])));
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = c4 * 4 + j;
-            if (c < d) {
-                const long long o = r * d + c;
-                if (GEN) noise[o] = z[j]; else z[j] = noise[o];
-                // two rounded products then a rounded add, as the reference's elementwise ops do (bit-exact)
-                xt[o] = __fadd_rn(__fmul_rn(a, x0[o]), __fmul_rn(b, z[j]));
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j;
+                if (c < d) {
+                    const long long o = r * d + c;
+                    if (GEN) noise[o] = z[j]; else z[j] = noise[o];
+                    xt[o] = __fadd_rn(__fmul_rn(a, x0[o]), __fmul_rn(b, z[j]));
+                }
             }
         }
     }
@@ -228,13 +260,27 @@ __global__ void reverse_update_kernel(float* __restrict__ x, const float* __rest
             const float4 g = philox_normal4(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), STREAM_REVERSE, t);
             zz[0] = g.x; zz[1] = g.y; zz[2] = g.z; zz[3] = g.w;
         }
+        const int c0 = c4 * 4;
+        if ((d & 1) == 0 && c0 + 3 < d) {
+            // even row pitch: 64-bit accesses (every (row, even column) is 8-byte aligned); same arithmetic as the scalar tail
+            const long long o = r * d + c0;
+            if (sg != 0.0f && z) {
+                const float2 za = *reinterpret_cast<const float2*>(z + o), zb = *reinterpret_cast<const float2*>(z + o + 2);
+                zz[0] = za.x; zz[1] = za.y; zz[2] = zb.x; zz[3] = zb.y;
+            }
+            const float2 xa = *reinterpret_cast<const float2*>(x + o), xb2 = *reinterpret_cast<const float2*>(x + o + 2);
+            const float2 ea = *reinterpret_cast<const float2*>(eps + o), eb = *reinterpret_cast<const float2*>(eps + o + 2);
+            *reinterpret_cast<float2*>(x + o) = make_float2(fmaf(sg, zz[0], fmaf(cx, xa.x, -ce * ea.x)), fmaf(sg, zz[1], fmaf(cx, xa.y, -ce * ea.y)));
+            *reinterpret_cast<float2*>(x + o + 2) = make_float2(fmaf(sg, zz[2], fmaf(cx, xb2.x, -ce * eb.x)), fmaf(sg, zz[3], fmaf(cx, xb2.y, -ce * eb.y)));
+        } else {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int c = c4 * 4 + j;
-            if (c < d) {
-                const long long o = r * d + c;
-                const float zv = (sg != 0.0f && z) ? z[o] : zz[j];
-                x[o] = fmaf(sg, zv, fmaf(cx, x[o], -ce * eps[o]));
+            for (int j = 0; j < 4; ++j) {
+                const int c = c0 + j;
+                if (c < d) {
+                    const long long o = r * d + c;
+                    const float zv = (sg != 0.0f && z) ? z[o] : zz[j];
+                    x[o] = fmaf(sg, zv, fmaf(cx, x[o], -ce * eps[o]));
+                }
             }
         }
     }

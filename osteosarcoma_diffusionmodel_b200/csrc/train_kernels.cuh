@@ -82,13 +82,26 @@ __global__ void train_prepare_kernel(const float* __restrict__ x0, const float* 
                 const float4 g = philox_normal4(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), STREAM_QNOISE, 0u);
                 z[0] = g.x; z[1] = g.y; z[2] = g.z; z[3] = g.w;
             }
+            if ((d & 1) == 0 && c + 3 < d) {
+                // even row pitch: 64-bit loads of the caller's rows (every (row, even column) is 8-byte aligned)
+                const float2 xa = *reinterpret_cast<const float2*>(x0 + r * d + c), xb2 = *reinterpret_cast<const float2*>(x0 + r * d + c + 2);
+                if (noise_in) {
+                    const float2 na = *reinterpret_cast<const float2*>(noise_in + r * d + c), nb = *reinterpret_cast<const float2*>(noise_in + r * d + c + 2);
+                    z[0] = na.x; z[1] = na.y; z[2] = nb.x; z[3] = nb.y;
+                }
+                xt[0] = __fadd_rn(__fmul_rn(a, xa.x), __fmul_rn(b, z[0]));
+                xt[1] = __fadd_rn(__fmul_rn(a, xa.y), __fmul_rn(b, z[1]));
+                xt[2] = __fadd_rn(__fmul_rn(a, xb2.x), __fmul_rn(b, z[2]));
+                xt[3] = __fadd_rn(__fmul_rn(a, xb2.y), __fmul_rn(b, z[3]));
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if (c + j < d) {
-                    if (noise_in) z[j] = noise_in[r * d + c + j];
-                    xt[j] = __fadd_rn(__fmul_rn(a, x0[r * d + c + j]), __fmul_rn(b, z[j]));
-                } else {
-                    z[j] = 0.f;
+                for (int j = 0; j < 4; ++j) {
+                    if (c + j < d) {
+                        if (noise_in) z[j] = noise_in[r * d + c + j];
+                        xt[j] = __fadd_rn(__fmul_rn(a, x0[r * d + c + j]), __fmul_rn(b, z[j]));
+                    } else {
+                        z[j] = 0.f;
+                    }
                 }
             }
         }

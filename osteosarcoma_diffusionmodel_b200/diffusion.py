@@ -367,7 +367,7 @@ class BiologyAwareDiffusionModel(nn.Module):
         n = x_0.shape[0]
         t32 = t.to(device=dev, dtype=torch.int32).contiguous()
         gen = noise is None
-        noise_t = torch.empty_like(x_0) if gen else self._as_f32(noise, dev).clone()
+        noise_t = torch.empty_like(x_0) if gen else self._as_f32(noise, dev)      # injected noise is only read (the reference returns the caller's tensor too)
         x_t = torch.empty_like(x_0)
         _lib.check(lib.osteo_ddpm_q_sample(self._ctx, x_0.data_ptr(), t32.data_ptr(), noise_t.data_ptr(), x_t.data_ptr(), n, int(gen),
                                            self._next_seed() if gen else 0, 0, 0, _lib.stream_handle()))
