@@ -502,6 +502,27 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
     except Exception as e:
         out["elementwise"] = {"error": repr(e)}
 
+    # -------- training ingress: one 8192-row batch gathered from a device-resident cohort with the mixup fused in
+    try:
+        from osteosarcoma_diffusionmodel_b200.ingress import GpuResidentDataset, MixupAugmentation
+        nd = 32768
+        dsx, dsc = synth.make_cohort(nd, D_MUT, D_EXPR, D_PATH, N_COND, seed=5)
+        ds = GpuResidentDataset(dsx, dsc, dsc[:, 0].contiguous(), device=dev)
+        gi = torch.Generator(device=dev).manual_seed(0)
+        index = torch.randperm(nd, device=dev, generator=gi)[:8192].contiguous()
+        perm = torch.randperm(8192, device=dev, generator=gi)
+        mixer = MixupAugmentation(0.2)
+        ms = timed(lambda: mixer.gather(ds, index, lam=0.3, perm=perm), 2, 10)
+        moved = 8192 * (D + N_COND + 1) * 4 * 3
+        host_batch = {"data": dsx[:8192].clone(), "conditions": dsc[:8192].clone()}
+        ms_h2d = timed(lambda: (host_batch["data"].to(dev), host_batch["conditions"].to(dev)), 1, 5)
+        out["ingress"] = {"batch": 8192, "dataset_rows": nd, "fused_gather_mixup_ms": ms, "gb_per_s": moved / (ms / 1e3) / 1e9, "hbm_frac": moved / (ms / 1e3) / 1e9 / hbm_peak,
+                          "reference_style_pageable_h2d_ms": ms_h2d,
+                          "note": "read two dataset rows + write one per batch row (data, conditions, survival); the reference copies each batch from pageable host memory (utils/train.py:214-216) and mixes with three elementwise passes"}
+        del ds, dsx
+    except Exception as e:
+        out["ingress"] = {"error": repr(e)}
+
     # -------- RBF-MMD (utils/validation.py:273-298): N = M = 16384 rows of 5142 features
     n = 16384
     g = torch.Generator(device=dev).manual_seed(1)

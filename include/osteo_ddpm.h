@@ -248,6 +248,14 @@ int osteo_corr_moments(const float* data_dev, long long n, int ld, const int* co
 int osteo_corr_moments_batched(const float* data_dev, long long n, int ld, int ncols, const int* cols_dev, int n_sets,
                                const float* shift_dev, long long row_begin, long long row_end, double* out_dev, void* stream);
 
+/* ---- training ingress (utils/train.py:22-126, :204-227): one batch of a DEVICE-RESIDENT dataset, gathered by row index,
+ * with MixupAugmentation fused in:  out[i, :] = lam * src[idx_a[i], :] + one_minus_lam * src[idx_b[i], :]   (src_dev [src_rows, d] fp32,
+ * idx_*_dev int64 [n] device, out_dev [n, d]).  idx_a_dev == NULL: rows 0..n-1; idx_b_dev == NULL: plain gather, lam ignored.
+ * lam / one_minus_lam are the fp32 roundings of the Python scalars lam and 1 - lam; products and sum are rounded separately, so the
+ * result is bit-identical to the reference's `lam * data + (1 - lam) * data[index]` (utils/train.py:118). */
+int osteo_mixup_rows(const float* src_dev, long long src_rows, int d, const long long* idx_a_dev, const long long* idx_b_dev,
+                     long long n, float lam, float one_minus_lam, float* out_dev, void* stream);
+
 /* ---- differentiable biology losses (the reference has only stubs: models/cvae.py:262-302).
  * Per column set s of data_dev [n, ld] (cols_dev [n_sets][32] int32, -1 padded; the first `ncols` columns are staged):
  *   modes_dev[s] == 0      loss_s = 1 - mean_{i<j} Pearson(x_i, x_j)   = 1 - the per-pathway score of validate_pathway_coherence

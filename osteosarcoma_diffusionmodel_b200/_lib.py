@@ -75,6 +75,7 @@ SIGNATURES = {
     "osteo_mmd_partial": (_i, [_vp, _ll, _vp, _ll, _i, _f, _vp, _ll, _ll, _ll, _ll, _i, _vp, _vp]),
     "osteo_corr_moments": (_i, [_vp, _ll, _i, _vp, _i, _vp, _ll, _ll, _vp, _vp]),
     "osteo_corr_moments_batched": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _ll, _ll, _vp, _vp]),
+    "osteo_mixup_rows": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _f, _f, _vp, _vp]),
     "osteo_corr_loss_finish": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "osteo_corr_loss_backward": (_i, [_vp, _ll, _i, _vp, _i, _vp, _vp, _vp, _vp]),
 }

@@ -281,4 +281,16 @@ int osteo_corr_loss_backward(const float* data_dev, long long n, int ld, const i
     return 0;
 }
 
+int osteo_mixup_rows(const float* src_dev, long long src_rows, int d, const long long* idx_a_dev, const long long* idx_b_dev, long long n, float lam, float one_minus_lam,
+                     float* out_dev, void* stream) {
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (!src_dev || !out_dev || d <= 0 || src_rows <= 0) return fail("mixup_rows: bad arguments");
+    if (n <= 0) return 0;
+    if (!idx_a_dev && n > src_rows) return fail("mixup_rows: %lld rows requested from a %lld-row source without an index", n, src_rows);
+    const long long items = n * ((d & 1) == 0 ? d / 2 : d);
+    mixup_gather_kernel<<<grid_for(items, 256, current_sms()), 256, 0, static_cast<cudaStream_t>(stream)>>>(src_dev, d, idx_a_dev, idx_b_dev, lam, one_minus_lam, out_dev, n);
+    OSTEO_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // extern "C"

@@ -153,6 +153,35 @@ __global__ void store_split_kernel(const float* __restrict__ x, int x_nbox, int 
     }
 }
 
+// Training ingress: one batch of a device-resident dataset with the reference's mixup fused in
+// (utils/train.py:85-126: mixed = lam * batch + (1 - lam) * batch[index]):
+//   out[i, :] = lam * src[ia[i], :] + oml * src[ib[i], :]        ia = the batch's dataset rows, ib = ia permuted
+// lam and oml = 1 - lam arrive as the fp32 roundings torch makes of the Python scalars, and the two products and the sum are rounded
+// separately like torch's three elementwise kernels: bit-exact. ib == nullptr: plain gather (no mixup / validation batches).
+__global__ void mixup_gather_kernel(const float* __restrict__ src, int d, const long long* __restrict__ ia, const long long* __restrict__ ib, float lam, float oml,
+                                    float* __restrict__ out, long long n) {
+    const bool vec = (d & 1) == 0;                 // even row pitch: 64-bit accesses
+    const int q = vec ? d / 2 : d;
+    const long long total = n * q;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long r = i / q;
+        const int c = static_cast<int>(i % q);
+        const long long ra = ia ? ia[r] : r;
+        if (vec) {
+            const float2 a = reinterpret_cast<const float2*>(src + ra * d)[c];
+            float2 o = a;
+            if (ib) {
+                const float2 b = reinterpret_cast<const float2*>(src + ib[r] * d)[c];
+                o = make_float2(__fadd_rn(__fmul_rn(lam, a.x), __fmul_rn(oml, b.x)), __fadd_rn(__fmul_rn(lam, a.y), __fmul_rn(oml, b.y)));
+            }
+            reinterpret_cast<float2*>(out + r * d)[c] = o;
+        } else {
+            const float a = src[ra * d + c];
+            out[r * d + c] = ib ? __fadd_rn(__fmul_rn(lam, a), __fmul_rn(oml, src[ib[r] * d + c])) : a;
+        }
+    }
+}
+
 // x_T ~ N(0, I): models/diffusion.py:443. One Philox call per 4 columns.
 __global__ void init_noise_kernel(float* __restrict__ x, int x_nbox, int x_shift, int dp, __nv_bfloat16* __restrict__ xb, int xb_nbox, int lo_boxes, long long n, int d,
                                   unsigned long long seed, long long row_base, uint32_t stream_id, uint32_t step) {

@@ -67,3 +67,16 @@ def test_pack_column_sets_groups_of_32_and_checks():
         pack_column_sets([[0, 1, 2]], [1], "cpu")
     with pytest.raises(ValueError):
         pack_column_sets([[0, 1]], [0, 1], "cpu")
+
+
+def test_ingress_has_no_cpu_fallback_and_checks_shapes():
+    from osteosarcoma_diffusionmodel_b200.ingress import GpuResidentDataset, MixupAugmentation
+    x, c, sv = torch.zeros(8, 6), torch.zeros(8, 2), torch.zeros(8)
+    with pytest.raises(ValueError):
+        GpuResidentDataset(x, c[:4], sv, device="cpu")
+    ds = GpuResidentDataset(x, c, sv, device="cpu")            # construction is plain tensor plumbing ...
+    assert len(ds) == 8
+    with pytest.raises(RuntimeError):                          # ... every batch is a kernel of the library
+        ds.gather(torch.arange(4))
+    with pytest.raises(RuntimeError):
+        MixupAugmentation(0.2)({"data": x, "conditions": c, "survival": sv}, lam=0.5, index=torch.arange(8))
