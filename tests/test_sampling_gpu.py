@@ -239,3 +239,20 @@ def test_sample_components_is_the_split_and_thresholded_sample():
     assert np.array_equal(unpacked.astype(bool), calls.cpu().numpy())
     assert 0 < calls.float().mean().item() < 1       # both outcomes occur
     model.check_status()
+
+
+def test_parallel_row_branches_do_not_change_the_samples():
+    """Sampling graphs split big batches into parallel row branches with their own step words (osteo_ddpm_set_branches; two waves of row
+    tiles per branch are required, i.e. >= 75 776 rows on 148 SMs): bit-identical to the single-branch graph, ragged last tile included,
+    across a 10-step unrolled graph plus single-step graphs."""
+    case = load_case("config")
+    model = build_model(case, "bf16")
+    n = 76_001
+    cond = synth.scenario_conditions(n, 3).cuda()
+    outs = []
+    for nb in (1, 2, 1):
+        model.set_branches(nb)
+        outs.append(model.sample(cond, n, seed=3, t_stop=987)[::97].clone())       # 13 steps = one 10-step graph + three 1-step graphs
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert torch.isfinite(outs[0]).all()
+    model.check_status()
