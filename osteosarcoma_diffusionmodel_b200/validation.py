@@ -83,6 +83,7 @@ class BiologicalValidator:
         if precision not in _PRECISIONS:
             raise ValueError(f"unknown precision {precision!r}")
         self.precision = precision
+        self._index_cache: Dict[tuple, list] = {}          # (device, column sets) -> device index tensors of the moment kernel
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device() if torch.cuda.is_available() else 0)
 
     def _require_cuda(self):
@@ -113,24 +114,38 @@ class BiologicalValidator:
         return float(np.sqrt(max(mmd, 0.0)))
 
     # ------------------------------------------------------------------ utils/validation.py:125-175
-    def _coherence_scores(self, data: torch.Tensor, member_cols: List[List[int]]) -> List[float]:
-        """All pathways in one pass over the cohort (osteo_corr_moments_batched: warp p owns pathway p, whole rows are streamed
-        through shared memory), then a single all-reduce and a single device->host copy."""
+    def _coherence_moments(self, data: torch.Tensor, member_cols: List[List[int]]) -> torch.Tensor:
+        """Device tensor [n_sets, _CM_STRIDE] of all-reduced moment blocks: all pathways in one pass over the cohort
+        (osteo_corr_moments_batched: warp p owns pathway p, whole rows are streamed through shared memory). Nothing here waits for the
+        device: the index tensors are cached per (device, column sets) and the result stays in HBM."""
         rank, ws = D.world()
         rows = D.shard_rows(data.shape[0], rank, ws)
         if any(len(c) > 32 for c in member_cols):
             raise ValueError("a pathway with more than 32 member genes is not supported by the moment kernel")
+        key = (str(data.device), tuple(tuple(c) for c in member_cols))
+        packs = self._index_cache.get(key)
+        if packs is None:
+            packs = []
+            for b0 in range(0, len(member_cols), 32):
+                sets = member_cols[b0:b0 + 32]
+                ci = np.full((len(sets), 32), -1, dtype=np.int32)
+                for i, cols in enumerate(sets):
+                    ci[i, :len(cols)] = cols
+                ci_t = torch.from_numpy(ci).to(data.device)
+                packs.append((ci_t, ci_t.clamp(min=0).long()))
+            if len(self._index_cache) > 16:
+                self._index_cache.clear()
+            self._index_cache[key] = packs
         parts = []
-        for b0 in range(0, len(member_cols), 32):
-            sets = member_cols[b0:b0 + 32]
-            ci = np.full((len(sets), 32), -1, dtype=np.int32)
-            for i, cols in enumerate(sets):
-                ci[i, :len(cols)] = cols
-            ci_t = torch.from_numpy(ci).to(data.device)
-            # any value near the column mean conditions the fp64 moments: the first row's
-            shift = data[0, ci_t.clamp(min=0).long()].contiguous()
+        for ci_t, gather_idx in packs:
+            # any value near the column mean conditions the fp64 moments: the first row's (every rank holds the whole cohort and reduces its
+            # share of the rows, so all ranks pick the same shift)
+            shift = data[0, gather_idx].contiguous()
             parts.append(_moments_batched(data, ci_t, shift, rows))
-        flat = D.all_reduce_sum_(torch.cat(parts)).cpu().numpy()
+        return D.all_reduce_sum_(torch.cat(parts))
+
+    @staticmethod
+    def _scores_from_moments(flat: np.ndarray, member_cols: List[List[int]]) -> List[float]:
         scores = []
         for i, cols in enumerate(member_cols):
             k = len(cols)
@@ -139,6 +154,16 @@ class BiologicalValidator:
             corr = _corr_from_moments(mom, k)
             scores.append(float(corr[np.triu_indices(k, k=1)].mean()))
         return scores
+
+    def _coherence_scores(self, data: torch.Tensor, member_cols: List[List[int]]) -> List[float]:
+        return self._scores_from_moments(self._coherence_moments(data, member_cols).cpu().numpy(), member_cols)
+
+    def _coherence_scores_pair(self, real: torch.Tensor, members_real, synthetic: torch.Tensor, members_syn):
+        """Both cohorts enqueued back to back, ONE device-to-host copy for the pair."""
+        mr = self._coherence_moments(real, members_real)
+        ms = self._coherence_moments(synthetic, members_syn)
+        flat = torch.cat([mr, ms]).cpu().numpy()
+        return self._scores_from_moments(flat[:len(members_real)], members_real), self._scores_from_moments(flat[len(members_real):], members_syn)
 
     def validate_pathway_coherence(self, real_data, synthetic_data, pathway_gene_matrix) -> Dict[str, float]:
         """Mean within-pathway pairwise Pearson correlation for the first 10 pathways (>= 3 member genes present), for the
@@ -163,8 +188,7 @@ class BiologicalValidator:
             return results
         real_t = _to_device(real_data, self.device)
         syn_t = _to_device(synthetic_data, self.device)
-        real_scores = self._coherence_scores(real_t, members_real)
-        syn_scores = self._coherence_scores(syn_t, members_syn)
+        real_scores, syn_scores = self._coherence_scores_pair(real_t, members_real, syn_t, members_syn)
         results["real_pathway_coherence"] = float(np.mean(real_scores))
         results["synthetic_pathway_coherence"] = float(np.mean(syn_scores))
         results["pathway_coherence_correlation"] = float(np.corrcoef(real_scores, syn_scores)[0, 1])
@@ -179,8 +203,7 @@ class BiologicalValidator:
         members = [list(m) for m in list(members)[:10] if len(m) >= 3]
         if not members:
             return {}
-        rs = self._coherence_scores(_to_device(real, self.device), members)
-        ss = self._coherence_scores(_to_device(synthetic, self.device), members)
+        rs, ss = self._coherence_scores_pair(_to_device(real, self.device), members, _to_device(synthetic, self.device), members)
         return {"real_pathway_coherence": float(np.mean(rs)), "synthetic_pathway_coherence": float(np.mean(ss)),
                 "pathway_coherence_correlation": float(np.corrcoef(rs, ss)[0, 1])}
 
