@@ -27,7 +27,11 @@ __device__ long long g_ws_trace[3 * 32 * 4];      // [role][tile < 32][event] cl
 #define WS_TRACE(role, tile, ev) do { } while (0)
 #endif
 
-template <int GW>
+// CS = 2: the kernel is launched in clusters of two CTAs that own ADJACENT column slices and therefore walk the same row blocks: every A
+// stage is fetched from the L2 once, by one of the two in turn, and multicast into both shared memories; a stage is recycled when BOTH
+// CTAs' MMAs have consumed it (multicast tcgen05.commit onto both "empty" barriers). Without it every A tile crosses the L2 -> SM fabric
+// N / 128 times (four times for the 512-wide layers), which is what bounds those layers.
+template <int GW, int CS = 1>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __grid_constant__ GemmParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment by pointer arithmetic ON the __shared__ array: an integer round trip would turn every later access into a
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < stages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], CS);
         }
         for (int i = 0; i < NUM_ACC; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -84,8 +88,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
     }
     tc_fence_before_sync();
     __syncthreads();
+    if constexpr (CS > 1) cluster_sync_all();            // the peer's barriers exist before anything is multicast at them
     tc_fence_after_sync();
     const uint32_t tmem_base = *tmem_slot;
+    const uint32_t crank = CS > 1 ? cluster_ctarank() : 0u;
+    constexpr uint16_t CMASK = static_cast<uint16_t>((1u << CS) - 1u);
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
@@ -101,6 +108,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
             int stage = 0;
             uint32_t phase = 0;
             int tcount = 0;
+            uint32_t gstage = 0;                        // running stage count: CTA (gstage % CS) of the cluster fetches this one
             for (int m = m_first; ok && m < p.m_tiles; m += m_step, ++tcount) {
                 const int m_blk = p.m_tile0 + m;
                 WS_TRACE(0, tcount, 0);
@@ -110,7 +118,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
                     for (int kb = 0; kb < sg.nkb; ++kb) {
                         if (!mbar_wait_relaxed(&empty_bar[stage], phase ^ 1u)) { ok = false; break; }
                         mbar_arrive_expect_tx(&full_bar[stage], A_TILE_BYTES);
-                        tma_load_2d(ta, s_a + stage * A_TILE_BYTES, &full_bar[stage], sg.a_col + kb * BK, m_blk * BM);
+                        if constexpr (CS > 1) {
+                            if (gstage % CS == crank) tma_load_2d_multicast(ta, s_a + stage * A_TILE_BYTES, &full_bar[stage], sg.a_col + kb * BK, m_blk * BM, CMASK);
+                            ++gstage;
+                        } else {
+                            tma_load_2d(ta, s_a + stage * A_TILE_BYTES, &full_bar[stage], sg.a_col + kb * BK, m_blk * BM);
+                        }
                         if (++stage == stages) { stage = 0; phase ^= 1u; }
                     }
                 }
@@ -143,7 +156,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
                     const uint64_t bdesc = wdesc0 + static_cast<uint64_t>((idx * B_TILE_BYTES) >> 4);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (idx | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty_bar[stage]);
+                    if constexpr (CS > 1) umma_commit_multicast(&empty_bar[stage], CMASK);
+                    else umma_commit(&empty_bar[stage]);
                 }
                 __syncwarp();
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
@@ -182,6 +196,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
 
     tc_fence_before_sync();
     __syncthreads();
+    if constexpr (CS > 1) cluster_sync_all();            // no CTA leaves while its peer may still signal its barriers
     if (warp == 2) tmem_dealloc(tmem_base, 512);
 }
 
@@ -195,15 +210,55 @@ inline bool gemm_ws_eligible(const GemmParams& p) {
 template <int GW>
 int launch_gemm_ws_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
     static bool configured = false;
+    static int max_pairs = 0;               // co-resident 2-CTA clusters (1 CTA / SM, both SMs in one GPC); 0 = clusters unavailable
+    static const bool want_cluster = getenv("OSTEO_WS_CLUSTER") && atoi(getenv("OSTEO_WS_CLUSTER")) != 0;      // opt-in until measured
     if (!configured) {
-        OSTEO_CUDA(cudaFuncSetAttribute(gemm_ws_gn_silu_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
+        OSTEO_CUDA(cudaFuncSetAttribute(gemm_ws_gn_silu_kernel<GW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
+        OSTEO_CUDA(cudaFuncSetAttribute(gemm_ws_gn_silu_kernel<GW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
+        if (want_cluster) {
+            cudaLaunchConfig_t qc = {};
+            qc.gridDim = dim3(static_cast<unsigned>(num_sms & ~1), 1, 1);
+            qc.blockDim = dim3(WS_THREADS, 1, 1);
+            qc.dynamicSmemBytes = WS_SMEM_BYTES;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 2;
+            qa[0].val.clusterDim.y = 1;
+            qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa;
+            qc.numAttrs = 1;
+            int n = 0;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_ws_gn_silu_kernel<GW, 2>, &qc) == cudaSuccess) max_pairs = n;
+            else cudaGetLastError();
+        }
         configured = true;
     }
     if (p.m_tiles <= 0) return 0;
     int per_slice = num_sms / p.n_tiles;                // CTAs per column slice
     if (per_slice > p.m_tiles) per_slice = p.m_tiles;
     if (per_slice < 1) return -2;
-    gemm_ws_gn_silu_kernel<GW><<<per_slice * p.n_tiles, WS_THREADS, WS_SMEM_BYTES, stream>>>(p);
+    // clusters of two adjacent column slices: worth it only if (nearly) every SM can still be used
+    if (max_pairs > 0 && (p.n_tiles & 1) == 0 && 2 * max_pairs >= (num_sms * 15) / 16) {
+        int ps = (2 * max_pairs) / p.n_tiles;
+        if (ps > per_slice) ps = per_slice;
+        if (ps >= 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(static_cast<unsigned>(ps * p.n_tiles), 1, 1);
+            cfg.blockDim = dim3(WS_THREADS, 1, 1);
+            cfg.dynamicSmemBytes = WS_SMEM_BYTES;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = 2;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            OSTEO_CUDA(cudaLaunchKernelEx(&cfg, gemm_ws_gn_silu_kernel<GW, 2>, p));
+            return 0;
+        }
+    }
+    gemm_ws_gn_silu_kernel<GW, 1><<<per_slice * p.n_tiles, WS_THREADS, WS_SMEM_BYTES, stream>>>(p);
     OSTEO_CUDA(cudaGetLastError());
 #ifdef OSTEO_WS_TRACE
     if (getenv("OSTEO_DDPM_TRACE")) {      // diagnostics build: print CTA 0's timeline of this launch (synchronises)

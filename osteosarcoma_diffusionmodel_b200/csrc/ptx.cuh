@@ -145,6 +145,28 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- thread-block clusters: multicast TMA loads and multicast MMA-completion arrivals (gemm_ws.cuh pairs two CTAs on one A stream)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// One 2-D tile delivered to the SAME shared-memory offset of every CTA in `cta_mask`, each destination's mbarrier (same offset) getting
+// the complete_tx for its copy.
+__device__ __forceinline__ void tma_load_2d_multicast(const CUtensorMap* m, void* smem_dst, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at this offset in every CTA of `cta_mask`.
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+
 // TMEM -> registers: this warp's 32 lanes (rows) x 32 consecutive fp32 columns.
 __device__ __forceinline__ void tmem_ld_32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
