@@ -71,6 +71,25 @@ def _worker(rank, ws, port, q):
     val = BiologicalValidator({"evaluation": {}}, device=dev)
     res["mmd"] = val.compute_mmd(X, Y)
     res["coh"] = val.pathway_coherence_from_tensors(torch.from_numpy(X), torch.from_numpy(Y[:, :96]), [[0, 1, 2, 3], [10, 11, 12], [20, 30, 40, 50, 60]])
+    # ---- data-parallel correlation losses (multi-task step): every rank holds a row shard, the moments are all-reduced, so the loss is
+    # the GLOBAL batch's and each rank's gradient is world_size x its rows of the global gradient (DP averaging divides it back)
+    from osteosarcoma_diffusionmodel_b200.multitask import correlation_losses
+    rs = np.random.RandomState(7)
+    G = torch.from_numpy((rs.standard_normal((600, 3)) @ rs.standard_normal((3, 24)) + rs.standard_normal((600, 24))).astype(np.float32))
+    sets, modes = [[0, 1, 2, 3, 4], [5, 6, 7], [8, 9], [10, 11]], [0, 0, 1, -1]
+    lo, hi = D.shard_rows(600, rank, ws)
+    xs = G[lo:hi].to(dev).requires_grad_(True)
+    ls = correlation_losses(xs, sets, modes)
+    ls.sum().backward()
+    xf = G.double().requires_grad_(True)
+    from oracle import bio_losses_oracle as Bo
+    lf = Bo.correlation_losses(xf, sets, modes)
+    lf.sum().backward()
+    res["corr_loss_err"] = float((ls.detach().cpu().double() - lf.detach()).abs().max())
+    res["corr_grad_err"] = rel(xs.grad.cpu(), ws * xf.grad[lo:hi])
+    errs = torch.tensor([res["corr_loss_err"], res["corr_grad_err"]], device=dev, dtype=torch.float64)
+    dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+    res["corr_loss_err"], res["corr_grad_err"] = errs.tolist()
     if rank == 0:
         q.put(res)
     dist.destroy_process_group()
@@ -98,3 +117,4 @@ def test_two_rank_paths():
     ref = V.pathway_coherence(X, Y, [[0, 1, 2, 3], [10, 11, 12], [20, 30, 40, 50, 60]])
     for k in ref:
         assert abs(res["coh"][k] - ref[k]) < 1e-6
+    assert res["corr_loss_err"] < 5e-6 and res["corr_grad_err"] < 5e-5
