@@ -16,7 +16,9 @@
  *   - calls enqueue work on `stream` and do not synchronise unless stated.
  *   - the library owns its workspace (repacked weights, activations, padded state);
  *     it never allocates or frees caller-visible memory and never keeps caller pointers
- *     beyond the call, except weights which are repacked (copied) in set_weights.
+ *     beyond the call, except weights which are repacked (copied) in set_weights.  Cached executable
+ *     graphs (set_weights, train_step) record the addresses they were captured with and are replayed
+ *     only by a later call that passes exactly those addresses again; any other call runs eagerly.
  *   - there is NO CPU fallback: without a CUDA device every compute call fails.
  */
 #ifndef OSTEO_DDPM_H
