@@ -122,6 +122,18 @@ def sample_sharded(model, conditions: torch.Tensor, num_samples: int, seed: int 
     return torch.cat(outs)
 
 
+def sample_sharded_to_shards(model, conditions: torch.Tensor, num_samples: int, out_dir, seed: int = 0, rows_per_shard: int = 100_000, pack_bits: bool = True):
+    """Batch-sharded sampling straight to disk (BASELINE.json configs[2]: 10 M patients): rank r samples its contiguous slice of the global
+    cohort and streams it to `out_dir/rank_{r:03d}` with egress.generate_to_shards (rows keep their global index, so the union of the
+    directories is the same cohort for any GPU count). No collective. Returns this rank's manifest."""
+    from pathlib import Path
+
+    from .egress import generate_to_shards
+    rank, ws = world()
+    b, e = shard_rows(num_samples, rank, ws)
+    return generate_to_shards(model, conditions[b:e], Path(out_dir) / f"rank_{rank:03d}", shard_rows=rows_per_shard, seed=seed, row_base=b, pack_bits=pack_bits)
+
+
 def _all_gather_ragged(outs, local, sizes):
     for r, o in enumerate(outs):
         if o.numel():

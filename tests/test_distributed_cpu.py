@@ -192,3 +192,36 @@ def test_sample_sharded_world2_covers_every_global_row_once():
     assert calls[0] == (6, 9, 0)
     assert local == [0, 1, 2, 3, 4, 5]
     assert full == list(range(11))
+
+
+def _worker_shards(rank, ws, port, q, out_dir):
+    _init(rank, ws, port)
+    from tests.test_egress_cpu import _FakeModel
+    n = 37
+    cond = torch.arange(n * 2, dtype=torch.float32).reshape(n, 2)
+    man = D.sample_sharded_to_shards(_FakeModel(), cond, n, out_dir, seed=2, rows_per_shard=8)
+    if rank == 0:
+        q.put(man["rows"])
+    dist.destroy_process_group()
+
+
+def test_sample_sharded_to_shards_world2_writes_the_whole_cohort_once(tmp_path):
+    """Two ranks stream their row ranges to rank_000 / rank_001: together exactly the single-process cohort."""
+    from osteosarcoma_diffusionmodel_b200.egress import load_shards
+    from tests.test_egress_cpu import _FakeModel
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_shards, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    rows0 = q.get(timeout=10)
+    a, b = load_shards(tmp_path / "rank_000"), load_shards(tmp_path / "rank_001")
+    assert rows0 == a["expression"].shape[0] and a["expression"].shape[0] + b["expression"].shape[0] == 37
+    n = 37
+    cond = torch.arange(n * 2, dtype=torch.float32).reshape(n, 2)
+    ref = _FakeModel().sample_components(cond, n, seed=2, row_base=0)
+    for k in ("expression", "pathways", "conditions"):
+        assert np.array_equal(np.concatenate([a[k], b[k]]), ref[k].numpy())
+    assert np.array_equal(np.concatenate([a["mutations"], b["mutations"]]), ref["mutations"].numpy().astype(float))
