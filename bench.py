@@ -104,53 +104,117 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
-def cpu_reference_rate(rows: int, steps: int, repeats: int = 1):
-    """patients/s of the reference's CPU algorithm: `steps` reverse steps on `rows` rows (torch CPU, all threads),
-    scaled to the 1000 steps a patient needs. Noise is drawn inside the timed region as the reference does."""
+def reference_model(device="cpu"):
+    """The UNMODIFIED reference class (models/diffusion.py:259-449) from the staged copy oracle/_ref/reference (oracle/stage_reference.py;
+    /root/reference in the build container), random-init weights of the bench workload. None when no copy is present."""
     import torch
-    from oracle import ddpm_oracle as O
+    from oracle import reference_import as R
+    from osteosarcoma_diffusionmodel_b200 import synthetic as synth
+
+    if not R.available():
+        return None
+    ref_diffusion, _ = R.import_reference()
+    m = ref_diffusion.BiologyAwareDiffusionModel(D_MUT, D_EXPR, D_PATH, N_COND, synth.model_config(hidden_dims=HIDDEN))
+    m.load_state_dict(synth.make_params(D, N_COND, HIDDEN, seed=0), strict=False)
+    return m.to(device).eval()
+
+
+def cpu_reference_rate(rows: int, steps: int, repeats: int = 1, model=None):
+    """patients/s of the reference's CPU path: `steps` reverse steps (p_sample, models/diffusion.py:382-425; noise drawn inside the timed
+    region as the reference does) on `rows` rows, torch CPU with all host threads, scaled to the 1000 steps a patient needs.
+    Runs the staged reference itself (kind "reference") or, without it, the oracle port (kind "port")."""
+    import torch
     from osteosarcoma_diffusionmodel_b200 import synthetic as synth
 
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = synth.make_params(D, N_COND, HIDDEN, seed=0)
-    sd.update(O.schedule_buffers("cosine", T_STEPS))
     cond = synth.scenario_conditions(rows, N_COND)
     x = torch.randn(rows, D)
+    if model is None:
+        model = reference_model()
+    if model is not None:
+        kind = "reference"
+
+        def one(xx, t):
+            return model.p_sample(xx, t, cond)
+    else:
+        from oracle import ddpm_oracle as O
+
+        kind = "port"
+        sd = synth.make_params(D, N_COND, HIDDEN, seed=0)
+        sd.update(O.schedule_buffers("cosine", T_STEPS))
+
+        def one(xx, t):
+            return O.p_sample(sd, xx, t, cond, torch.randn_like(xx), T_STEPS)
     best = None
     for _ in range(repeats):
         xx = x.clone()
         t0 = time.perf_counter()
         for i in range(steps):
-            t = T_STEPS - 1 - i
-            xx = O.p_sample(sd, xx, t, cond, torch.randn_like(xx), T_STEPS)
+            xx = one(xx, T_STEPS - 1 - i)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     per_step = best / steps
-    return rows / (per_step * T_STEPS), per_step, torch.get_num_threads()
+    return rows / (per_step * T_STEPS), per_step, torch.get_num_threads(), kind
 
 
 def run_reference_arm(args):
+    """The reference's own CPU implementation of the path on this box's host cores (all threads): every bench step is a bounded sample
+    -- 1024 rows (the reference's CPU throughput peak) x 20 of the 1000 reverse steps, scaled -- plus, once, a TRUE
+    1000-step sample() of 100 patients (BASELINE.json configs[0]'s sampling half) and compute_mmd at N = 2000."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    import torch
+    from osteosarcoma_diffusionmodel_b200 import synthetic as synth
+
     rows, sub_steps = 1024, 20
-    vals = []
-    ms = []
+    model = reference_model()
+    vals, ms = [], []
     for _ in range(args.warmup):
-        cpu_reference_rate(rows, 2)
+        cpu_reference_rate(rows, 2, model=model)
     for _ in range(args.steps):
-        v, per_step, threads = cpu_reference_rate(rows, sub_steps)
+        v, per_step, threads, kind = cpu_reference_rate(rows, sub_steps, model=model)
         vals.append(v)
-        ms.append(per_step * T_STEPS * 1e3)
+        ms.append(per_step * sub_steps * 1e3)
     value = statistics.mean(vals)
-    sample = f"{rows} rows x {sub_steps} of {T_STEPS} reverse steps per bench step, scaled to {T_STEPS} steps (B=1024 is the reference's CPU throughput peak, BASELINE.md §2)"
+    sample = (f"{rows} rows x {sub_steps} of {T_STEPS} reverse steps per bench step, scaled to {T_STEPS} steps (B=1024 is the reference's CPU "
+              f"throughput peak, BASELINE.md §2); {'the staged reference itself (oracle/_ref/reference)' if kind == 'reference' else 'oracle port (no staged reference found)'}")
+    secondary = {}
+    if model is not None and not args.no_secondary:
+        cond = synth.scenario_conditions(100, N_COND)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            out = model.sample(cond, num_samples=100)
+        dt = time.perf_counter() - t0
+        secondary["true_1000_step_sample"] = {"rows": 100, "s": dt, "patients_per_s": 100 / dt, "finite": bool(torch.isfinite(out).all()),
+                                             "note": "model.sample(conditions, 100): the full 1000-step loop, not scaled"}
+        try:
+            import numpy as np
+            from oracle import reference_import as R
+
+            _, ref_validation = R.import_reference()
+            val = ref_validation.BiologicalValidator({"evaluation": {"driver_genes": [], "mutually_exclusive_pairs": [], "required_correlations": []}})
+            rs = np.random.RandomState(0)
+            n = 2000
+            X, Y = rs.standard_normal((n, D)) + 4.0, rs.standard_normal((n, D)) * 1.1 + 4.1
+            t0 = time.perf_counter()
+            mmd = val.compute_mmd(X, Y)
+            dt = time.perf_counter() - t0
+            secondary["compute_mmd"] = {"rows": n, "features": D, "s": dt, "kernel_pairs_per_s": 3.0 * n * n / dt, "value": float(mmd),
+                                        "note": "utils/validation.py:273-298 (scipy cdist, float64); O(N^2): 1 M x 1 M extrapolates to ~%.0f days" % (3.0e12 / (3.0 * n * n / dt) / 86400)}
+        except Exception as e:
+            secondary["compute_mmd"] = {"error": repr(e)}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": statistics.mean(ms), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, args.rows),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "config": {"workload": "1000-step conditional DDPM sampling, config.yaml dims (5142 features, 3 conditions, hidden [256,512,256], cosine), three config.yaml "
+                               "scenarios (BASELINE.json configs[1]) -- CPU arm: a bounded sample of it per bench step",
+                   "rows_per_bench_step": rows, "reverse_steps_per_bench_step": sub_steps, "num_steps": T_STEPS, "precision": "fp32 (torch CPU eager)",
+                   "rng": "torch.randn_like inside p_sample", "weights": "random init (synthetic.make_params seed 0)",
+                   "value_is": "rows / (seconds per reverse step x 1000)", "ms_per_step_is": f"wall time of the {sub_steps} reverse steps actually run"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "secondary": secondary,
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -356,9 +420,10 @@ def run_ours(args):
     # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, per_step, threads = cpu_reference_rate(1024, 20)
-        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"1024 rows x 20 of {T_STEPS} reverse steps of the torch-CPU oracle port (oracle/ddpm_oracle.py), scaled to {T_STEPS} steps"}
+        v, per_step, threads, kind = cpu_reference_rate(1024, 20)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": kind,
+                        "sample": f"1024 rows x 20 of {T_STEPS} reverse steps of " + ("the staged reference's own p_sample (oracle/_ref/reference)" if kind == "reference"
+                                  else "the torch-CPU oracle port (oracle/ddpm_oracle.py)") + f", scaled to {T_STEPS} steps"}
 
     if rank == 0:
         line = {
@@ -568,6 +633,44 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
     out["coherence"] = {"rows": rows, "genes": 371, "pathways": 10, "ms": ms, "gathered_gb_per_s": rows * 150 * 4 / (ms / 1e3) / 1e9,
                         "streamed_gb_per_s": rows * 371 * 4 / (ms / 1e3) / 1e9, "hbm_frac": rows * 371 * 4 / (ms / 1e3) / 1e9 / hbm_peak,
                         "note": "one pass over whole rows for all pathways (osteo_corr_moments_batched); includes the host-side finish of both cohorts"}
+    del cohort, X, Y
+
+    # -------- fp32x3 (split-bf16, fp32-tolerance) sampling throughput beside the bf16 headline: same workload, one full loop
+    try:
+        nrows = 100_000
+        cond_dev = synth.scenario_conditions(nrows, N_COND).to(dev)
+        model.set_precision("fp32x3")
+        model.sample(cond_dev, nrows, seed=1, t_stop=T_STEPS - 20)
+        ms = timed(lambda: model.sample(cond_dev, nrows, seed=2), 0, 1)
+        out["sampling_fp32x3"] = {"rows": nrows, "ms": ms, "patients_per_s": nrows / (ms / 1e3), "tolerance_vs_reference": "rel 1e-4 (tests/helpers.py TOL_FP32X3)"}
+    except Exception as e:
+        out["sampling_fp32x3"] = {"error": repr(e)}
+    finally:
+        model.set_precision("bf16")
+
+    # -------- the reference itself on THIS GPU under PyTorch eager (SURVEY.md §2.1 bar (i)): fp32 cuBLAS + ~45 launches per step
+    try:
+        ref = reference_model(dev)
+        if ref is None:
+            out["gpu_eager_reference"] = {"unavailable": "no staged reference (oracle/_ref/reference)"}
+        else:
+            out["gpu_eager_reference"] = {}
+            for nrows in (1024, 32768):
+                cond_r = synth.scenario_conditions(nrows, N_COND).to(dev)
+                state = {"x": torch.randn(nrows, D, device=dev), "t": T_STEPS - 1}
+
+                def ref_step():
+                    with torch.no_grad():
+                        state["x"] = ref.p_sample(state["x"], state["t"], cond_r)
+                    state["t"] = state["t"] - 1 if state["t"] > 1 else T_STEPS - 1
+
+                ms = timed(ref_step, 5, 40)
+                out["gpu_eager_reference"][f"rows_{nrows}"] = {"ms_per_reverse_step": ms, "patients_per_s": nrows / (ms * T_STEPS / 1e3)}
+            out["gpu_eager_reference"]["note"] = ("the staged reference's own p_sample (models/diffusion.py:382-425) on this B200, PyTorch eager fp32 (TF32 off, torch default), "
+                                                  "40 reverse steps scaled to 1000")
+            del ref
+    except Exception as e:
+        out["gpu_eager_reference"] = {"error": repr(e)}
     return out
 
 
@@ -613,8 +716,84 @@ def run_secondary_dp(model, dev, dist, rank, world, tf_peak):
     ms = timed(lambda: val.compute_mmd(X, Y), 1, 3)
     out["mmd_bf16_row_sharded"] = {"rows": n, "ms": ms, "kernel_pairs_per_s": 3.0 * n * n / (ms / 1e3), "value": val.compute_mmd(X, Y),
                                    "note": "every rank holds X and Y and reduces its share of the Gram rows; full (not symmetric-half) Grams when sharded"}
+    # ---- correctness of every sharded path, outside any timed region, reported in the JSON line (secondary.checks)
+    out["checks"] = multi_gpu_checks(model, dev, dist, rank, world, opt, X, Y)
     model.check_status()
     return out if rank == 0 else None
+
+
+def multi_gpu_checks(model, dev, dist, rank, world, opt, X, Y):
+    """Driver-visible multi-GPU correctness (every rank takes part; all comparisons are all-reduced so every rank agrees on the verdict):
+      sampling_shards_equal_single_gpu   rows sampled by rank r inside its shard == the same GLOBAL rows sampled by rank 0 alone (bit-equal)
+      dp_replicas_bit_identical          parameters (and AdamW moments) identical on all ranks after data-parallel optimiser steps
+      mmd_sharded_equals_unsharded       row-sharded RBF-MMD == the single-GPU reduction of the same X, Y (relative 1e-6)
+      coherence_sharded_equals_unsharded row-sharded pathway-coherence scores == the single-GPU ones (absolute 1e-9)"""
+    import torch
+    from osteosarcoma_diffusionmodel_b200 import distributed as Dm
+    from osteosarcoma_diffusionmodel_b200 import synthetic as synth
+    from osteosarcoma_diffusionmodel_b200 import validation as Vm
+    from osteosarcoma_diffusionmodel_b200.validation import BiologicalValidator
+
+    checks = {}
+
+    def agree(ok: bool) -> bool:
+        t = torch.tensor([1 if ok else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    # -- sampling: full 1000-step loop, a global cohort of world x 384 patients (three row tiles per rank, ragged against 128)
+    model.eval()
+    per, seed = 384 - 7, 4321
+    n_glob = per * world
+    cond_glob = synth.scenario_conditions(n_glob, N_COND).to(dev)
+    local = Dm.sample_sharded(model, cond_glob, n_glob, seed=seed)                     # this rank's contiguous slice
+    gathered = [torch.empty_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    ok = True
+    if rank == 0:
+        whole = model.sample(cond_glob, n_glob, seed=seed, row_base=0)                  # all global rows on ONE GPU
+        ok = bool(torch.equal(whole, torch.cat(gathered))) and bool(torch.isfinite(whole).all())
+    checks["sampling_shards_equal_single_gpu"] = agree(ok)
+    checks["sampling_rows_checked"] = n_glob
+
+    # -- data-parallel training: after the steps timed above plus two more, every replica holds the same bits
+    model.train()
+    x0, cond = synth.make_cohort(2048, D_MUT, D_EXPR, D_PATH, N_COND, seed=100 + rank)
+    for _ in range(2):
+        Dm.dp_train_step(model, opt, x0.to(dev), cond.to(dev))
+    model.eval()
+    flat = torch.cat([p.detach().reshape(-1) for p in model.parameters()])
+    state = [v for st in opt.state.values() for k, v in sorted(st.items()) if torch.is_tensor(v) and v.numel() > 1]
+    flat = torch.cat([flat] + [v.detach().reshape(-1).float() for v in state])
+    ref = flat.clone()
+    dist.broadcast(ref, src=0)
+    checks["dp_replicas_bit_identical"] = agree(bool(torch.equal(ref.view(torch.int32), flat.view(torch.int32))) and bool(torch.isfinite(flat).all()))
+
+    # -- RBF-MMD: sharded Gram rows + all-reduce vs the whole reduction on one GPU
+    for prec in ("bf16", "fp32x3"):
+        val = BiologicalValidator({"evaluation": {}}, precision=prec)
+        n = 4096 + 100
+        sharded = val.compute_mmd(X[:n], Y[:n - 333])
+        center = ((X[:n].sum(0, dtype=torch.float64) + Y[:n - 333].sum(0, dtype=torch.float64)) / (2 * n - 333)).float().contiguous()
+        sums = Vm._gram_partial_sums(X[:n].contiguous(), Y[:n - 333].contiguous(), 1.0 / D, center, (0, n), (0, n - 333), Vm._PRECISIONS[prec]).cpu()
+        sxx, syy, sxy = (float(v) for v in sums)
+        whole = max(sxx / n ** 2 + syy / (n - 333) ** 2 - 2 * sxy / (n * (n - 333.0)), 0.0) ** 0.5
+        checks[f"mmd_sharded_equals_unsharded_{prec}"] = agree(abs(sharded - whole) <= 1e-6 * max(whole, 1e-12))
+    checks["mmd_sharded_equals_unsharded"] = checks["mmd_sharded_equals_unsharded_bf16"] and checks["mmd_sharded_equals_unsharded_fp32x3"]
+
+    # -- pathway coherence: sharded cohort rows + all-reduced moment blocks vs one GPU
+    g = torch.Generator(device=dev).manual_seed(7)
+    cohort = torch.randn(50_001, 371, device=dev, generator=g)
+    cohort[:, 1] += 0.5 * cohort[:, 0]
+    members = [list(range(15 * p, 15 * p + 15)) for p in range(10)]
+    val = BiologicalValidator({"evaluation": {}})
+    sharded = val._coherence_scores(cohort, members)
+    packs_key = (str(cohort.device), tuple(tuple(c) for c in members))
+    ci_t, gather_idx = val._index_cache[packs_key][0]
+    mom = Vm._moments_batched(cohort, ci_t, cohort[0, gather_idx].contiguous(), (0, cohort.shape[0])).cpu().numpy()
+    whole = val._scores_from_moments(mom, members)
+    checks["coherence_sharded_equals_unsharded"] = agree(max(abs(a - b) for a, b in zip(sharded, whole)) <= 1e-9)
+    return checks
 
 
 def main():

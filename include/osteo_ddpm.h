@@ -75,6 +75,9 @@ int osteo_ddpm_set_precision(osteo_ddpm_ctx* ctx, int precision);
  * init_noise. osteo_ddpm_step_is_fused reports which path the current settings select. */
 int osteo_ddpm_set_fused(osteo_ddpm_ctx* ctx, int enable);
 int osteo_ddpm_step_is_fused(const osteo_ddpm_ctx* ctx);
+/* Row branches of the cached sampling graph (0 = no graph has been captured yet): how the last graph-replayed
+ * osteo_ddpm_sample_loop actually ran (tests assert the benchmarked configuration was exercised). */
+int osteo_ddpm_graph_branches(const osteo_ddpm_ctx* ctx);
 
 /* ---- parameters: replaces nn.Module.load_state_dict / optimizer updates.
  * `weights_dev[i]` are fp32 device tensors in state_dict order (SURVEY.md §8a layer table):

@@ -183,6 +183,33 @@ def gen_ddpm_case(ref_diffusion, name, dims, hidden, schedule, batch, seed, full
     print(f"wrote ddpm_{name}.npz  loss_eval={loss_eval.item():.6f} loss_train={loss_train.item():.6f} |final|={final.norm().item():.4e}")
 
 
+def gen_production_case(ref_diffusion):
+    """The reference's sample() on the 208 rows of oracle/production_case.py with x_T / z taken from the restated Philox streams: what
+    the benchmarked mode (in-kernel RNG, graphs, branches) must reproduce for those rows of a 76 100-patient run."""
+    from oracle import philox_oracle as P
+    from oracle import production_case as PC
+
+    torch.manual_seed(0)
+    dims = synth.CONFIG_YAML_DIMS
+    model, _ = build_reference_model(ref_diffusion, dims, (256, 512, 256), "cosine", PC.PARAM_SEED)
+    model.eval()
+    D, T = model.data_dim, model.num_steps
+    rows = PC.rows()
+    cond = synth.scenario_conditions(PC.N_TOTAL, 3)[torch.from_numpy(rows)]
+    f32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+    with Injector() as inj:
+        inj.randn_q.append(f32(P.normals(PC.SEED, rows.astype(np.uint64), D, PC.STREAM_XT, 0)))
+        for t in reversed(range(1, T)):
+            inj.randn_like_q.append(f32(P.normals(PC.SEED, rows.astype(np.uint64), D, PC.STREAM_REVERSE, t)))
+        final = model.sample(cond, num_samples=len(rows))
+        assert not inj.randn_like_q
+    final = final.numpy()
+    cols = PC.stored_columns(dims["mutation_dim"], dims["expression_dim"], dims["pathway_dim"])
+    np.savez_compressed(GOLDEN / "ddpm_production.npz", rows=rows, n_total=PC.N_TOTAL, seed=PC.SEED, cols=cols, final_cols=final[:, cols],
+                        final_norm=np.float64(np.linalg.norm(final.astype(np.float64))), final_absmax=np.float32(np.abs(final).max()))
+    print(f"wrote ddpm_production.npz rows={len(rows)} |final|={np.linalg.norm(final):.4e} max|x|={np.abs(final).max():.4e}")
+
+
 def gen_validators(ref_validation):
     import pandas as pd
     import importlib.util
@@ -240,18 +267,59 @@ def gen_validators(ref_validation):
     print("wrote validators.npz", {k: float(v) for k, v in out.items() if np.ndim(v) == 0})
 
 
+def gen_validate_all(ref_validation):
+    """Outputs of the reference's remaining validators (utils/validation.py:27-123, :225-271, :300-387) on oracle/validator_inputs.py;
+    the numpy global RNG is seeded before each call (np.random.choice of the 50 genes, sklearn's randomized PCA)."""
+    from oracle import validator_inputs as VI
+
+    val = ref_validation.BiologicalValidator(VI.CONFIG)
+    out = {}
+    real_mut, syn_mut = VI.mutation_frames()
+    np.random.seed(123)
+    for k, v in val.validate_mutation_cooccurrence(real_mut, syn_mut).items():
+        out[f"cooc_{k}"] = np.float64(v)
+    real, syn = VI.stat_matrices()
+    np.random.seed(5)
+    for k, v in val.statistical_tests(real, syn).items():
+        out[f"stat_{k}"] = np.float64(v)
+    # an asymptotic-branch KS case (n > 10 000): the statistic and p-value of the first 3 features
+    from scipy import stats
+    rs = np.random.RandomState(31)
+    a, b = rs.standard_normal((12000, 3)), rs.standard_normal((10500, 3)) * 1.02 + 0.01
+    ks = [stats.ks_2samp(a[:, i], b[:, i]) for i in range(3)]
+    out["ks_big_stat"] = np.array([k.statistic for k in ks])
+    out["ks_big_pvalue"] = np.array([k.pvalue for k in ks])
+    frames = VI.validate_all_frames()
+    np.random.seed(77)
+    res = val.validate_all(*frames)
+    out["all_keys"] = np.array(list(res.keys()))
+    for k, v in res.items():
+        out[f"all_{k}"] = np.float64(v)
+    np.savez_compressed(GOLDEN / "validate_all.npz", **out)
+    print("wrote validate_all.npz", {k: (float(v) if np.ndim(v) == 0 else v.tolist()) for k, v in out.items() if k != "all_keys"})
+
+
 def main():
     ref_diffusion, ref_validation = reference_import.import_reference()
     torch.set_num_threads(os.cpu_count() or 1)
     GOLDEN.mkdir(parents=True, exist_ok=True)
     if "--only-validators" in sys.argv:
         gen_validators(ref_validation)
+        gen_validate_all(ref_validation)
+        return
+    if "--only-production" in sys.argv:
+        gen_production_case(ref_diffusion)
+        return
+    if "--only-validate-all" in sys.argv:
+        gen_validate_all(ref_validation)
         return
     gen_ddpm_case(ref_diffusion, "smoke", synth.SMOKE_DIMS, (256, 512, 256), "cosine", batch=4, seed=1, full_loop_rows=4)
     gen_ddpm_case(ref_diffusion, "config", synth.CONFIG_YAML_DIMS, (256, 512, 256), "cosine", batch=4, seed=2, full_loop_rows=3)
     gen_ddpm_case(ref_diffusion, "linear3", dict(mutation_dim=20, expression_dim=90, pathway_dim=10, condition_dim=2), (128, 256), "linear", batch=5, seed=3,
                   full_loop_rows=2)
+    gen_production_case(ref_diffusion)
     gen_validators(ref_validation)
+    gen_validate_all(ref_validation)
 
 
 if __name__ == "__main__":

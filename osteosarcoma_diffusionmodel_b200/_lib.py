@@ -42,6 +42,7 @@ SIGNATURES = {
     "osteo_ddpm_set_branches": (_i, [_vp, _i]),
     "osteo_ddpm_set_train_graph": (_i, [_vp, _i]),
     "osteo_ddpm_step_is_fused": (_i, [_vp]),
+    "osteo_ddpm_graph_branches": (_i, [_vp]),
     "osteo_ddpm_set_weights": (_i, [_vp, C.POINTER(_vp), _i, _vp]),
     "osteo_ddpm_set_schedule": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "osteo_ddpm_set_time_embedding": (_i, [_vp, _vp]),
@@ -123,7 +124,29 @@ def ptr(t) -> int | None:
     return t.ctypes.data
 
 
-def stream_handle() -> int:
+def stream_handle(device=None) -> int:
+    """cudaStream_t of torch's current stream on `device` (default: the current device; the callers run under
+    `torch.cuda.device(model device)`, see on_device)."""
     import torch
 
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def on_device(device_of):
+    """Decorator factory for methods that call the C-ABI: run the method with `device_of(self)` as the current CUDA device, so
+    allocations, torch's current stream and the library's launches all refer to the object's device -- not to whatever device the
+    process happens to have current (a model on cuda:1 in a process whose current device is cuda:0)."""
+    import functools
+
+    def deco(fn):
+        @functools.wraps(fn)
+        def wrapper(self, *args, **kwargs):
+            import torch
+
+            dev = device_of(self)
+            if dev is not None and getattr(dev, "type", None) == "cuda" and torch.cuda.is_available():
+                with torch.cuda.device(dev):
+                    return fn(self, *args, **kwargs)
+            return fn(self, *args, **kwargs)
+        return wrapper
+    return deco

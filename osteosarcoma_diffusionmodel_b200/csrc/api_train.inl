@@ -139,7 +139,7 @@ static int train_pre(osteo_ddpm_ctx* c, const float* x0_dev, const float* cond_d
 
 // Shared argument checks of the training entry points.
 static int train_check(osteo_ddpm_ctx* c, long long n, const int* t_idx_dev, float* const* grads_dev, int n_tensors, bool want_grads) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     OSTEO_TRY(require_ready(c, n));
     if (!t_idx_dev) return fail("train_step: t_idx_dev is required");
     if (want_grads) {
@@ -440,7 +440,7 @@ static int train_body(osteo_ddpm_ctx* c, const float* cond_dev, long long n, con
 extern "C" {
 
 int osteo_ddpm_enable_training(osteo_ddpm_ctx* c, int enable) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     OSTEO_CUDA(cudaSetDevice(c->device));
     if (!enable) return 0;
     if (c->out_proj.wt.p) return 0;
@@ -453,7 +453,7 @@ int osteo_ddpm_enable_training(osteo_ddpm_ctx* c, int enable) {
 }
 
 int osteo_ddpm_set_train_graph(osteo_ddpm_ctx* c, int enable) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     c->train_graph_enable = enable ? 1 : 0;
     if (!enable) {
         c->train_graph.reset();
@@ -534,7 +534,7 @@ int osteo_ddpm_train_forward(osteo_ddpm_ctx* c, const float* x0_dev, const float
 }
 
 int osteo_ddpm_train_x0hat(osteo_ddpm_ctx* c, const float* x0_dev, const int* t_idx_dev, long long n, const int* cols_dev, int n_cols, float* out_dev, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     TrainWorkspace& w = c->train;
     if (w.fwd_n != n || n <= 0) return fail("train_x0hat: no forward pass of %lld rows is pending (osteo_ddpm_train_forward)", n);
     if (n_cols <= 0) return fail("train_x0hat: n_cols must be positive");
@@ -548,7 +548,7 @@ int osteo_ddpm_train_x0hat(osteo_ddpm_ctx* c, const float* x0_dev, const int* t_
 }
 
 int osteo_ddpm_train_inject(osteo_ddpm_ctx* c, const int* t_idx_dev, long long n, const int* cols_dev, int n_cols, const float* g_dev, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     TrainWorkspace& w = c->train;
     if (w.fwd_n != n || n <= 0) return fail("train_inject: no forward pass of %lld rows is pending (osteo_ddpm_train_forward)", n);
     if (n_cols <= 0) return fail("train_inject: n_cols must be positive");
@@ -588,6 +588,7 @@ int osteo_ddpm_train_backward(osteo_ddpm_ctx* c, const float* cond_dev, long lon
 
 // ---- fused clip_grad_norm_ + AdamW (utils/train.py:242-244)
 struct osteo_adamw {
+    int device = -1;                         // device of the tables (the current device at create): every later call runs under a DeviceGuard
     int n = 0;
     std::vector<long long> numel;
     std::vector<const void*> host_ptrs;      // [4 * n]: last uploaded params | grads | exp_avg | exp_avg_sq
@@ -603,6 +604,7 @@ int osteo_adamw_create(osteo_adamw** out, int n_tensors, const long long* numel_
     if (!out || n_tensors <= 0 || !numel_host) return fail("adamw_create: bad arguments");
     if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
     std::unique_ptr<osteo_adamw> h(new osteo_adamw);
+    OSTEO_CUDA(cudaGetDevice(&h->device));
     h->n = n_tensors;
     h->numel.assign(numel_host, numel_host + n_tensors);
     std::vector<int> ct;
@@ -630,6 +632,8 @@ int osteo_adamw_create(osteo_adamw** out, int n_tensors, const long long* numel_
 }
 
 int osteo_adamw_destroy(osteo_adamw* h) {
+    if (!h) return 0;
+    DeviceGuard device_guard(h->device);
     delete h;
     return 0;
 }
@@ -639,6 +643,7 @@ int osteo_adamw_step(osteo_adamw* h, float* const* params_dev, float* const* gra
     if (!h) return fail("adamw_step: null handle");
     if (!params_dev || !grads_dev || !exp_avg_dev || !exp_avg_sq_dev) return fail("adamw_step: null pointer table");
     if (step < 1) return fail("adamw_step: step counts from 1");
+    DeviceGuard device_guard(h->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int n = h->n;
     std::vector<const void*> now(4 * n);

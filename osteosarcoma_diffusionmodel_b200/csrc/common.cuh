@@ -28,6 +28,26 @@ int fail(const char* fmt, ...);
 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 
+// RAII: make `device` the calling thread's current CUDA device for the duration of a C-ABI call and put the caller's device back on
+// exit. Every entry point that takes a context (or a handle that remembers its device) opens one, so a model on cuda:1 works while
+// the process's current device is cuda:0, and no call -- destroy included -- leaves the thread on a different device.
+struct DeviceGuard {
+    int prev = -1;
+    bool switched = false;
+    explicit DeviceGuard(int device) {
+        if (device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (switched) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+// context check + device guard: the first statement of every entry point that takes an osteo_ddpm_ctx*
+#define OSTEO_CTX(c)                   \
+    OSTEO_TRY(::osteo::check_ctx(c));  \
+    ::osteo::DeviceGuard _osteo_device_guard((c)->device)
+
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns,
 // 128-byte swizzle (matches make_kmajor_sw128_desc). Out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);

@@ -65,6 +65,8 @@ struct FusedParams {
     const float* bias_out;    // [>= DP], zero padded
     const float* noise;       // optional injected z, dense [M, noise_ld]
     int noise_ld;
+    long long noise_step_stride;   // != 0: `noise` is a per-step stack; this step's slice starts at (noise_t0 - t) * stride (graph replays)
+    int noise_t0;
     float* eps_out;           // optional dense eps [M, eps_ld]
     int eps_ld;
     unsigned long long seed;
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                 }
                 if (live && nvalid > 0 && kr != 0.0f) {
                     if (p.noise) {
-                        const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c0;
+                        const float* nz = p.noise + static_cast<size_t>(p.noise_t0 - t) * p.noise_step_stride + static_cast<size_t>(row) * p.noise_ld + c0;
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
                             if (i < nvalid) v[i] = fmaf(kr, nz[i], v[i]);
@@ -430,7 +432,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) ddpm_fused_kernel(const __grid_c
                         for (int i = 0; i < 16; ++i) z[i] = 0.0f;
                         if (live && nvalid > 0 && sg != 0.0f) {
                             if (p.noise) {
-                                const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c0;
+                                const float* nz = p.noise + static_cast<size_t>(p.noise_t0 - t) * p.noise_step_stride + static_cast<size_t>(row) * p.noise_ld + c0;
 #pragma unroll
                                 for (int i = 0; i < 16; ++i)
                                     if (i < nvalid) z[i] = sg * nz[i];

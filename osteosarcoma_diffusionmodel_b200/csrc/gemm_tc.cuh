@@ -125,6 +125,8 @@ struct GemmParams {
     int x_nbox;               // fp32 state is BLOCKED [m_tile][x_nbox][128][32] (each TMA box = 16 KB contiguous)
     const float* noise;       // injected z [M, noise_ld] (parity) or nullptr (Philox)
     int noise_ld;
+    long long noise_step_stride;   // != 0: `noise` is a per-step stack [steps][M, noise_ld]; the step's slice is (noise_t0 - t) * stride
+    int noise_t0;                  //       (lets a replayed graph, whose only changing input is the device step word, consume injected noise)
     float* eps_out;           // optional fp32 eps [M, eps_ld]
     int eps_ld;
     unsigned long long seed;
@@ -890,7 +892,7 @@ struct Epilogue<EPI_DDPM> {
         for (int j = 0; j < 32; ++j) z[j] = 0.0f;
         if (row >= p.M || c0 >= p.N || sg == 0.0f) return;
         if (p.noise) {
-            const float* nz = p.noise + static_cast<size_t>(row) * p.noise_ld + c0;
+            const float* nz = p.noise + static_cast<size_t>(p.noise_t0 - t) * p.noise_step_stride + static_cast<size_t>(row) * p.noise_ld + c0;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (c0 + j < p.N) z[j] = nz[j];

@@ -214,6 +214,8 @@ struct osteo_ddpm_ctx {
     DevBuf cproj;                        // fp32 [cap, h0]
     DevBuf step_dev, status_dev;      // step_dev: MAX_BRANCHES step words (equal outside a graph replay), one per row branch
     int branches = 2, cur_branch = 0;
+    long long noise_step_stride = 0;     // != 0 while a sample_loop with an injected per-step noise stack is being enqueued / captured
+    int noise_t0 = 0;
     DevBuf loss_acc;                     // fp64 scalar
     TrainWorkspace train;
 
@@ -222,7 +224,10 @@ struct osteo_ddpm_ctx {
     long long graph_n = -1;
     unsigned long long graph_seed = 0;
     long long graph_row_base = 0;
-    int graph_precision = -1, graph_chunk = -1, graph_fused = -1, graph_branches = -1;
+    int graph_precision = -1, graph_chunk = -1, graph_fused = -1, graph_branches = -1, graph_noise_t0 = 0;
+    int graph_nb = 0;                    // row branches the cached sampling graph was captured with
+    const float* graph_noise = nullptr;
+    unsigned long long graph_generation = ~0ull;
     long long graph_launches_per_step = 0;
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every GEMM launch
     // graph caches of the training path (api_train.inl): weight repack after an optimizer step, forward + backward
@@ -254,7 +259,7 @@ struct osteo_ddpm_ctx {
 
 namespace osteo {
 
-static int check_ctx(const osteo_ddpm_ctx* c) {
+int check_ctx(const osteo_ddpm_ctx* c) {
     if (!c) return fail("null context");
     return 0;
 }
@@ -411,6 +416,8 @@ static int launch_output_ddpm(osteo_ddpm_ctx* c, long long row0, long long row1,
     if (!(p.dbg & 32)) p.a_resident = 0;      // measured SLOWER than streaming A (2-stage W ring is latency-bound): off unless bit 5 is set
     p.noise = noise;
     p.noise_ld = c->D;
+    p.noise_step_stride = noise ? c->noise_step_stride : 0;
+    p.noise_t0 = c->noise_t0;
     p.eps_out = eps_out;
     p.eps_ld = c->D;
     p.seed = seed;
@@ -458,6 +465,8 @@ static int launch_fused(osteo_ddpm_ctx* c, long long row0, long long row1, const
     p.bias_out = c->out_proj.bias.as<float>();
     p.noise = noise;
     p.noise_ld = c->D;
+    p.noise_step_stride = noise ? c->noise_step_stride : 0;
+    p.noise_t0 = c->noise_t0;
     p.eps_out = eps_out;
     p.eps_ld = c->D;
     p.seed = seed;
@@ -556,11 +565,12 @@ constexpr int MAX_BRANCHES = 4;
 // count x (10 block GEMMs + fused tail) with its OWN device step word, decremented after each of its steps, and the branches only
 // join at the end of the graph. A persistent kernel's tail wave (782 row tiles on 148 SMs = 5.28 waves), its prologue and the
 // launch gap of one branch are then filled by the other branch's kernels instead of idling the SMs.
-static int capture_steps(osteo_ddpm_ctx* c, long long n, unsigned long long seed, long long row_base, int count, cudaGraphExec_t* out) {
+static int capture_steps(osteo_ddpm_ctx* c, long long n, const float* noise, unsigned long long seed, long long row_base, int count, cudaGraphExec_t* out) {
     const long long tiles = (n + BM - 1) / BM;
     int nb = c->branches < 1 ? 1 : (c->branches > MAX_BRANCHES ? MAX_BRANCHES : c->branches);
     if (const char* e = getenv("OSTEO_DDPM_BRANCHES")) nb = atoi(e) < 1 ? 1 : (atoi(e) > MAX_BRANCHES ? MAX_BRANCHES : atoi(e));
-    while (nb > 1 && tiles < 2LL * c->sms * nb) --nb;  // less than two waves per branch only adds launches (measured: 3 / 4 branches of 1.8 / 1.3 waves are 2.5 / 4.5 % slower than 2)
+    while (nb > 1 && tiles < 2LL * c->sms * nb) --nb;
+    c->graph_nb = nb;  // less than two waves per branch only adds launches (measured: 3 / 4 branches of 1.8 / 1.3 waves are 2.5 / 4.5 % slower than 2)
     cudaStream_t cs[MAX_BRANCHES] = {};
     cudaEvent_t fork = nullptr, join[MAX_BRANCHES] = {};
     cudaGraph_t graph = nullptr;
@@ -578,7 +588,7 @@ static int capture_steps(osteo_ddpm_ctx* c, long long n, unsigned long long seed
             const long long re = re_ < n ? re_ : n;
             c->cur_branch = b;
             for (int i = 0; i < count && rc == 0; ++i) {
-                rc = enqueue_reverse_step(c, n, nullptr, nullptr, seed, row_base, cs[b], rb, re);
+                rc = enqueue_reverse_step(c, n, noise, nullptr, seed, row_base, cs[b], rb, re);
                 if (rc == 0) {
                     add_int_kernel<<<1, 1, 0, cs[b]>>>(c->step_dev.as<int>() + b, -1);
                     ++c->launches;
@@ -699,6 +709,7 @@ int osteo_ddpm_create(osteo_ddpm_ctx** out, int device, int data_dim, int cond_d
             return fail("hidden dim %d unsupported: the tcgen05 path needs multiples of 128 in [128, 512]", hidden_dims[i]);
     if (time_dim % 2 != 0) return fail("time_dim must be even");
     if (dropout_p < 0.f || dropout_p >= 1.f) return fail("dropout must be in [0, 1)");
+    DeviceGuard device_guard(device);      // allocations below land on `device`; the caller's current device is restored on return
     OSTEO_CUDA(cudaSetDevice(device));
     std::unique_ptr<osteo_ddpm_ctx> c(new osteo_ddpm_ctx);
     c->device = device;
@@ -789,7 +800,7 @@ int osteo_ddpm_create(osteo_ddpm_ctx** out, int device, int data_dim, int cond_d
 
 int osteo_ddpm_destroy(osteo_ddpm_ctx* ctx) {
     if (!ctx) return 0;
-    cudaSetDevice(ctx->device);
+    DeviceGuard device_guard(ctx->device);      // garbage collection of a model must not move the thread to another device
     cudaDeviceSynchronize();
     delete ctx;
     return 0;
@@ -808,33 +819,34 @@ long long osteo_ddpm_workspace_bytes(const osteo_ddpm_ctx* c) {
 }
 
 int osteo_ddpm_set_chunk_rows(osteo_ddpm_ctx* c, int chunk_rows) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (chunk_rows < 0) return fail("chunk_rows must be >= 0");
     c->chunk_rows = chunk_rows;
     return 0;
 }
 int osteo_ddpm_set_branches(osteo_ddpm_ctx* c, int branches) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (branches < 1 || branches > MAX_BRANCHES) return fail("branches must be in [1, %d]", MAX_BRANCHES);
     c->branches = branches;
     return 0;
 }
 int osteo_ddpm_set_precision(osteo_ddpm_ctx* c, int precision) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (precision != OSTEO_PREC_BF16 && precision != OSTEO_PREC_FP32X3) return fail("unknown precision %d", precision);
     c->precision = precision;
     return 0;
 }
 
 int osteo_ddpm_set_fused(osteo_ddpm_ctx* c, int enable) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     c->fused_enable = enable ? 1 : 0;
     return 0;
 }
 int osteo_ddpm_step_is_fused(const osteo_ddpm_ctx* c) { return c && c->fused_ok() ? 1 : 0; }
+int osteo_ddpm_graph_branches(const osteo_ddpm_ctx* c) { return c && c->graph_exec ? c->graph_nb : 0; }
 
 int osteo_ddpm_reserve(osteo_ddpm_ctx* c, long long rows) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (rows <= c->cap) return 0;
     OSTEO_CUDA(cudaSetDevice(c->device));
     OSTEO_CUDA(cudaDeviceSynchronize());
@@ -879,7 +891,7 @@ int osteo_ddpm_reserve(osteo_ddpm_ctx* c, long long rows) {
 }
 
 int osteo_ddpm_set_weights(osteo_ddpm_ctx* c, const float* const* w, int n_tensors, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     const int expect = osteo_ddpm_num_weight_tensors(static_cast<int>(c->hidden.size()));
     if (n_tensors != expect) return fail("expected %d weight tensors, got %d", expect, n_tensors);
     for (int i = 0; i < n_tensors; ++i)
@@ -950,7 +962,7 @@ int osteo_ddpm_set_weights(osteo_ddpm_ctx* c, const float* const* w, int n_tenso
 }
 
 int osteo_ddpm_set_schedule(osteo_ddpm_ctx* c, const float* sqrt_ab, const float* sqrt_1mab, const float* coef_x, const float* coef_eps, const float* sigma) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     OSTEO_CUDA(cudaSetDevice(c->device));
     const size_t b = sizeof(float) * c->T;
     OSTEO_CUDA(cudaMemcpy(c->sqrt_ab.p, sqrt_ab, b, cudaMemcpyHostToDevice));
@@ -966,7 +978,7 @@ int osteo_ddpm_set_schedule(osteo_ddpm_ctx* c, const float* sqrt_ab, const float
 }
 
 int osteo_ddpm_set_time_embedding(osteo_ddpm_ctx* c, const float* emb_host) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     OSTEO_CUDA(cudaSetDevice(c->device));
     OSTEO_CUDA(cudaMemcpy(c->emb_table.p, emb_host, sizeof(float) * c->T * c->TD, cudaMemcpyHostToDevice));
     c->have_emb = true;
@@ -976,7 +988,7 @@ int osteo_ddpm_set_time_embedding(osteo_ddpm_ctx* c, const float* emb_host) {
 }
 
 int osteo_ddpm_load_state(osteo_ddpm_ctx* c, const float* x_dev, long long n, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (n <= 0 || n > c->cap) return fail("load_state: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long items = n * (c->DP / 4);
@@ -991,7 +1003,7 @@ int osteo_ddpm_load_state(osteo_ddpm_ctx* c, const float* x_dev, long long n, vo
 }
 
 int osteo_ddpm_store_state(osteo_ddpm_ctx* c, float* out_dev, long long n, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (n <= 0 || n > c->cap) return fail("store_state: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     store_state_kernel<<<grid_for(n * c->D, 256, c->sms), 256, 0, s>>>(c->x.as<float>(), c->xs_nbox(), c->xs_shift(), out_dev, n, c->D);
@@ -1001,7 +1013,7 @@ int osteo_ddpm_store_state(osteo_ddpm_ctx* c, float* out_dev, long long n, void*
 }
 
 int osteo_ddpm_store_split(osteo_ddpm_ctx* c, long long n, int mutation_dim, float threshold, uint8_t* calls_dev, uint8_t* call_bits_dev, float* rest_dev, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (n <= 0 || n > c->cap) return fail("store_split: %lld rows outside (0, capacity %lld]", n, c->cap);
     if (mutation_dim < 0 || mutation_dim > c->D) return fail("store_split: mutation_dim %d outside [0, %d]", mutation_dim, c->D);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1014,7 +1026,7 @@ int osteo_ddpm_store_split(osteo_ddpm_ctx* c, long long n, int mutation_dim, flo
 }
 
 int osteo_ddpm_init_noise(osteo_ddpm_ctx* c, long long n, uint64_t seed, long long row_base, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (n <= 0 || n > c->cap) return fail("init_noise: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long items = n * (c->DP / 4);
@@ -1029,7 +1041,7 @@ int osteo_ddpm_init_noise(osteo_ddpm_ctx* c, long long n, uint64_t seed, long lo
 }
 
 int osteo_ddpm_set_conditions(osteo_ddpm_ctx* c, const float* cond_dev, long long n, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (!c->have_weights) return fail("weights not set");
     if (n <= 0 || n > c->cap) return fail("set_conditions: %lld rows outside (0, capacity %lld]", n, c->cap);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1044,7 +1056,7 @@ int osteo_ddpm_set_conditions(osteo_ddpm_ctx* c, const float* cond_dev, long lon
 }
 
 int osteo_ddpm_reverse_step(osteo_ddpm_ctx* c, long long n, int t, const float* noise_dev, float* eps_out_dev, uint64_t seed, long long row_base, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     OSTEO_TRY(require_ready(c, n));
     if (t < 0 || t >= c->T) return fail("timestep %d outside [0, %d)", t, c->T);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1059,7 +1071,7 @@ int osteo_ddpm_reverse_step(osteo_ddpm_ctx* c, long long n, int t, const float* 
 
 int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_end, const float* noise_dev, uint64_t seed, long long row_base, int use_graph,
                            void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     OSTEO_TRY(require_ready(c, n));
     if (t_start >= c->T || t_end < 0 || t_end > t_start) return fail("bad step range [%d, %d]", t_start, t_end);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1069,14 +1081,22 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
     ++c->launches;
     if (c->x_c8 != c->fused_ok()) return fail("the state was loaded under a different precision / fused setting: call load_state or init_noise again");
     OSTEO_TRY(ensure_primed(c, n, t_start, s));
-    if (noise_dev || !use_graph) {
+    // Injected noise is a per-step stack [steps][n, D]: each kernel picks its slice from the device step word (noise_t0 - t), so the
+    // replayed graphs below consume it exactly like the in-kernel Philox stream (parity runs of the benchmarked graph path).
+    c->noise_step_stride = noise_dev ? n * static_cast<long long>(c->D) : 0;
+    c->noise_t0 = t_start;
+    if (!use_graph) {
         for (int i = 0; i < steps; ++i) {
-            const float* nz = noise_dev ? noise_dev + static_cast<size_t>(i) * n * c->D : nullptr;
-            OSTEO_TRY(enqueue_reverse_step(c, n, nz, nullptr, seed, row_base, s));
+            const int rc = enqueue_reverse_step(c, n, noise_dev, nullptr, seed, row_base, s);
+            if (rc != 0) {
+                c->noise_step_stride = 0;
+                return rc;
+            }
             add_int_kernel<<<1, MAX_BRANCHES, 0, s>>>(c->step_dev.as<int>(), -1);
             OSTEO_CUDA(cudaGetLastError());
             ++c->launches;
         }
+        c->noise_step_stride = 0;
         after_steps(c, t_start, steps);
         return 0;
     }
@@ -1084,17 +1104,22 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
     // changes between replays. The unrolled graph amortises the per-graph-launch gap over GRAPH_UNROLL steps.
     const bool reuse = c->graph_exec && c->graph_n == n && c->graph_seed == seed && c->graph_row_base == row_base &&
                        c->graph_precision == c->precision && c->graph_chunk == c->chunk_rows && c->graph_fused == (c->x_c8 ? 1 : 0) &&
-                       c->graph_branches == c->branches;
+                       c->graph_branches == c->branches && c->graph_noise == noise_dev && c->graph_noise_t0 == (noise_dev ? t_start : 0) &&
+                       c->graph_generation == c->generation;
     if (!reuse) {
         for (cudaGraphExec_t* g : {&c->graph_exec, &c->graph_exec_multi}) {
             if (*g) cudaGraphExecDestroy(*g);
             *g = nullptr;
         }
         const long long before = c->launches;
-        OSTEO_TRY(capture_steps(c, n, seed, row_base, 1, &c->graph_exec));
+        int rc = capture_steps(c, n, noise_dev, seed, row_base, 1, &c->graph_exec);
         c->graph_launches_per_step = c->launches - before;
-        OSTEO_TRY(capture_steps(c, n, seed, row_base, GRAPH_UNROLL, &c->graph_exec_multi));
+        if (rc == 0) rc = capture_steps(c, n, noise_dev, seed, row_base, GRAPH_UNROLL, &c->graph_exec_multi);
         c->launches = before;   // capture enqueued nothing; the replays below are what runs
+        if (rc != 0) {
+            c->noise_step_stride = 0;
+            return rc;
+        }
         c->graph_n = n;
         c->graph_seed = seed;
         c->graph_row_base = row_base;
@@ -1102,7 +1127,11 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
         c->graph_chunk = c->chunk_rows;
         c->graph_branches = c->branches;
         c->graph_fused = c->x_c8 ? 1 : 0;
+        c->graph_noise = noise_dev;
+        c->graph_noise_t0 = noise_dev ? t_start : 0;
+        c->graph_generation = c->generation;
     }
+    c->noise_step_stride = 0;
     int left = steps;
     for (; left >= GRAPH_UNROLL; left -= GRAPH_UNROLL) OSTEO_CUDA(cudaGraphLaunch(c->graph_exec_multi, s));
     for (; left > 0; --left) OSTEO_CUDA(cudaGraphLaunch(c->graph_exec, s));
@@ -1112,7 +1141,7 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
 }
 
 int osteo_ddpm_denoise(osteo_ddpm_ctx* c, const float* xt_dev, const int* t_idx_dev, long long n, float* eps_out_dev, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     OSTEO_TRY(require_ready(c, n));
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const long long items = n * (c->DP / 4);
@@ -1134,7 +1163,7 @@ int osteo_ddpm_denoise(osteo_ddpm_ctx* c, const float* xt_dev, const int* t_idx_
 
 int osteo_ddpm_q_sample(osteo_ddpm_ctx* c, const float* x0_dev, const int* t_idx_dev, float* noise_dev, float* xt_dev, long long n, int gen_noise,
                         uint64_t seed, long long row_base, uint32_t salt, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (!c->have_schedule) return fail("schedule not set");
     if (n <= 0) return fail("row count must be positive");
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1151,7 +1180,7 @@ int osteo_ddpm_q_sample(osteo_ddpm_ctx* c, const float* x0_dev, const int* t_idx
 
 int osteo_ddpm_reverse_update(osteo_ddpm_ctx* c, float* x_dev, const float* eps_dev, const float* z_dev, long long n, int t, uint64_t seed, long long row_base,
                               void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     if (!c->have_schedule) return fail("schedule not set");
     if (t < 0 || t >= c->T) return fail("timestep %d outside [0, %d)", t, c->T);
     if (n <= 0) return fail("row count must be positive");
@@ -1165,7 +1194,7 @@ int osteo_ddpm_reverse_update(osteo_ddpm_ctx* c, float* x_dev, const float* eps_
 }
 
 int osteo_ddpm_profile_step(osteo_ddpm_ctx* c, long long n, int t, uint64_t seed, long long row_base, float* ms_out, int max_out, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     OSTEO_TRY(require_ready(c, n));
     if (t < 0 || t >= c->T) return fail("timestep %d outside [0, %d)", t, c->T);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1193,7 +1222,7 @@ int osteo_ddpm_profile_step(osteo_ddpm_ctx* c, long long n, int t, uint64_t seed
 }
 
 int osteo_ddpm_status(osteo_ddpm_ctx* c, void* stream) {
-    OSTEO_TRY(check_ctx(c));
+    OSTEO_CTX(c);
     int h = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     OSTEO_CUDA(cudaMemcpyAsync(&h, c->status_dev.p, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -193,7 +193,9 @@ __global__ void corr_loss_finish_kernel(const double* __restrict__ mom, const in
     double rho = 0.0;
     for (int j = 0; j < k; ++j) {
         const double mean_j = __shfl_sync(0xffffffffu, mean, j), isd_j = __shfl_sync(0xffffffffu, isd, j);
-        if (has && j != lane) rho += (m[33 + lane * 32 + j] / n - mean * mean_j) * isd * isd_j;
+        // n == 0 (every row of the batch filtered out): no correlation is defined -- rho stays 0 so that the set's loss is a finite
+        // constant with zero gradient instead of 0 / 0
+        if (has && j != lane && n > 0) rho += (m[33 + lane * 32 + j] / n - mean * mean_j) * isd * isd_j;
     }
     double S = rho;
 #pragma unroll
@@ -202,7 +204,10 @@ __global__ void corr_loss_finish_kernel(const double* __restrict__ mom, const in
     const int mode = modes[set];
     const double npairs = 0.5 * k * (k - 1);
     double loss, dS;
-    if (mode == 0) {
+    if (!(n > 0)) {
+        loss = 0.0;       // empty batch: the term vanishes (value and gradient)
+        dS = 0.0;
+    } else if (mode == 0) {
         loss = npairs > 0 ? 1.0 - S / npairs : 0.0;
         dS = npairs > 0 ? -1.0 / npairs : 0.0;
     } else {

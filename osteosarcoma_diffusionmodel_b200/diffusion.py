@@ -24,6 +24,7 @@ from . import _lib
 __all__ = ["BiologyAwareDiffusionModel", "ConditionalEmbedding", "TimeEmbedding", "DiffusionUNet"]
 
 _PRECISIONS = {"bf16": _lib.PREC_BF16, "fp32x3": _lib.PREC_FP32X3}
+_ALWAYS_REPACK = bool(int(os.environ.get("OSTEO_DDPM_ALWAYS_REPACK", "0")))
 
 
 class ConditionalEmbedding(nn.Module):
@@ -118,6 +119,16 @@ class _TrainStep(torch.autograd.Function):
         return (None, None, None, None) + tuple(torch._foreach_mul(ctx.grads, grad_out * ctx.scale if ctx.scale != 1.0 else grad_out))
 
 
+def _model_device(model):
+    try:
+        return model._param_list()[0].device
+    except Exception:       # half-constructed / torn-down module
+        return None
+
+
+_on_model_device = _lib.on_device(_model_device)
+
+
 class BiologyAwareDiffusionModel(nn.Module):
     """B200-native mirror of models/diffusion.py:259-449."""
 
@@ -203,6 +214,7 @@ class BiologyAwareDiffusionModel(nn.Module):
         return cx, ce, sg
 
     # ------------------------------------------------------------------ configuration knobs
+    @_on_model_device
     def set_precision(self, precision: str) -> "BiologyAwareDiffusionModel":
         """'bf16' (bf16 operands, fp32 accumulate) or 'fp32x3' (split-bf16, three tensor-core passes, ~fp32)."""
         if precision not in _PRECISIONS:
@@ -213,6 +225,7 @@ class BiologyAwareDiffusionModel(nn.Module):
             self._weights_sig = None
         return self
 
+    @_on_model_device
     def set_fused(self, enable: bool) -> "BiologyAwareDiffusionModel":
         """bf16 sampling runs the fused step kernel (output_proj + reverse update + next input_proj) by default;
         set_fused(False) selects the unfused kernels (always used by 'fp32x3')."""
@@ -221,11 +234,13 @@ class BiologyAwareDiffusionModel(nn.Module):
             _lib.check(_lib.load().osteo_ddpm_set_fused(self._ctx, int(self._fused)))
         return self
 
+    @_on_model_device
     def set_chunk_rows(self, rows: int) -> None:
         self._chunk_rows = int(rows)
         if self._ctx is not None:
             _lib.check(_lib.load().osteo_ddpm_set_chunk_rows(self._ctx, self._chunk_rows))
 
+    @_on_model_device
     def set_train_graph(self, enable: bool) -> None:
         """Training steps with nothing injected are replayed as one executable graph per (batch size, gradient buffer) by default;
         set_train_graph(False) keeps every launch eager (same results)."""
@@ -233,6 +248,7 @@ class BiologyAwareDiffusionModel(nn.Module):
         if self._ctx is not None:
             _lib.check(_lib.load().osteo_ddpm_set_train_graph(self._ctx, int(self._train_graph)))
 
+    @_on_model_device
     def set_branches(self, branches: int) -> None:
         """Number of parallel row branches of the sampling graphs (1..4, default 2); results do not depend on it."""
         self._branches = int(branches)
@@ -316,7 +332,7 @@ class BiologyAwareDiffusionModel(nn.Module):
     def _sync_weights(self) -> None:
         ps = self._param_list()
         sig = tuple((p.data_ptr(), p._version) for p in ps) + (self._precision,)
-        if sig == self._weights_sig:
+        if sig == self._weights_sig and not _ALWAYS_REPACK:
             return
         for p in ps:
             if p.dtype != torch.float32 or not p.is_contiguous():
@@ -324,6 +340,26 @@ class BiologyAwareDiffusionModel(nn.Module):
         arr = (C.c_void_p * len(ps))(*[p.data_ptr() for p in ps])
         _lib.check(_lib.load().osteo_ddpm_set_weights(self._ctx, arr, len(ps), _lib.stream_handle()))
         self._weights_sig = sig
+
+    def invalidate_weights(self) -> None:
+        """Force the library to repack the parameters before the next compute call. The repack is normally triggered by the
+        parameters' (address, version) signature; in-place writes THROUGH `.data` (`p.data.copy_(ema)`, init code using `.data`)
+        bump a separate version counter torch does not expose on the Parameter, so after such writes call this (load_state_dict,
+        `.to()` / `.cuda()` / `.float()` and optimizer steps are detected automatically). Set OSTEO_DDPM_ALWAYS_REPACK=1 to repack
+        before every call instead (slower: ~30 small launches)."""
+        self._weights_sig = None
+        self._schedule_sig = None
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_weights()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self.__dict__["_plist"] = None
+        self.invalidate_weights()
+        return out
 
     def _destroy_ctx(self) -> None:
         ctx = self.__dict__.get("_ctx")
@@ -346,10 +382,20 @@ class BiologyAwareDiffusionModel(nn.Module):
         state.update(_ctx=None, _ctx_device=None, _weights_sig=None, _schedule_sig=None, _inject=None, _train_enabled=False, _grad_buf=None, _plist=None)
         return state
 
+    @_on_model_device
     def check_status(self) -> None:
         """Raise if any kernel pipeline reported a (bounded-wait) timeout. Synchronises the current stream."""
         if self._ctx is not None:
             _lib.check(_lib.load().osteo_ddpm_status(self._ctx, _lib.stream_handle()))
+
+    def sampling_mode(self) -> dict:
+        """How the last sample() ran: {'precision', 'fused' (the fused step kernel), 'graph_branches' (row branches of the replayed graph,
+        0 = launched eagerly)} -- lets tests and bench.py assert that the benchmarked configuration is the one that was exercised."""
+        lib = _lib.load()
+        if self._ctx is None:
+            return {"precision": self._precision, "fused": False, "graph_branches": 0}
+        return {"precision": self._precision, "fused": bool(lib.osteo_ddpm_step_is_fused(self._ctx)),
+                "graph_branches": int(lib.osteo_ddpm_graph_branches(self._ctx)) if self._use_graph else 0}
 
     def launch_count(self) -> int:
         return int(_lib.load().osteo_ddpm_launch_count(self._ctx)) if self._ctx is not None else 0
@@ -360,6 +406,7 @@ class BiologyAwareDiffusionModel(nn.Module):
 
     # ------------------------------------------------------------------ forward process (models/diffusion.py:328-342)
     @torch.no_grad()
+    @_on_model_device
     def q_sample(self, x_0, t, noise=None):
         dev = self._device()
         lib = self._ensure_ctx(1)
@@ -374,6 +421,7 @@ class BiologyAwareDiffusionModel(nn.Module):
         return x_t, noise_t
 
     # ------------------------------------------------------------------ training forward (models/diffusion.py:344-380)
+    @_on_model_device
     def forward(self, x_0, conditions, return_loss=True):
         dev = self._device()
         x_0 = self._as_f32(x_0, dev)
@@ -401,6 +449,7 @@ class BiologyAwareDiffusionModel(nn.Module):
             return inject["t"].to(self._device())
         return torch.randint(0, self.num_steps, (n,), device=self._device())   # models/diffusion.py:361
 
+    @_on_model_device
     def _run_train_step(self, x_0, conditions, inject, want_grads: bool, aux=None):
         """One C-ABI training step. `aux` (multitask.py) adds auxiliary losses on the predicted clean sample: the step then runs in
         two halves (osteo_ddpm_train_forward / _backward) with d(aux)/d(x0hat) injected between them."""
@@ -452,6 +501,7 @@ class BiologyAwareDiffusionModel(nn.Module):
 
     # ------------------------------------------------------------------ reverse process (models/diffusion.py:382-449)
     @torch.no_grad()
+    @_on_model_device
     def p_sample(self, x_t, t, conditions, noise=None, return_eps: bool = False, seed: Optional[int] = None):
         """Single reverse step.  `noise` injects z (parity); otherwise z comes from the in-kernel Philox stream."""
         dev = self._device()
@@ -471,9 +521,12 @@ class BiologyAwareDiffusionModel(nn.Module):
         return (out, eps) if return_eps else out
 
     @torch.no_grad()
+    @_on_model_device
     def sample(self, conditions, num_samples: int = 1, *, seed: Optional[int] = None, row_base: int = 0, x_T=None, noise=None,
                t_stop: int = 0, _components: Optional[str] = None):
-        """Generate samples via reverse diffusion (models/diffusion.py:427-449).
+        """Generate samples via reverse diffusion (models/diffusion.py:427-449). Sampling always runs the denoiser in inference form
+        (no dropout), whatever `self.training` says: every reference caller samples under `.eval()` (utils/generate.py:29,
+        models/diffusion.py:476), where the reference's Dropout is the identity too.
 
         Extra keyword-only arguments (all optional, defaults reproduce the reference call):
           seed / row_base  Philox key and global index of row 0: rows get the same noise however the cohort is
@@ -516,6 +569,7 @@ class BiologyAwareDiffusionModel(nn.Module):
         return out
 
     @torch.no_grad()
+    @_on_model_device
     def sample_components(self, conditions, num_samples: int = 1, *, pack_bits: bool = False, **kw):
         """sample() with the egress of SyntheticPatientGenerator.generate fused on the device (utils/generate.py:127-144): returns
         {'mutations': uint8 [n, mutation_dim] = samples[:, :mutation_dim] > 0.5, 'expression': fp32 [n, expression_dim],
@@ -524,6 +578,7 @@ class BiologyAwareDiffusionModel(nn.Module):
         return self.sample(conditions, num_samples, _components="bits" if pack_bits else "bytes", **kw)
 
     @torch.no_grad()
+    @_on_model_device
     def predict_noise(self, x_t, t, conditions):
         """eps_theta(x_t, t, c) for integer timesteps t [n] — the denoiser alone (DiffusionUNet.forward, :210-256)."""
         dev = self._device()

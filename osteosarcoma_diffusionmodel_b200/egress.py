@@ -11,7 +11,7 @@ conditions), so the reference's own `save_synthetic_data` can still write CSVs f
 from __future__ import annotations
 
 import json
-import threading
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
 from typing import Dict, List, Optional
 
@@ -32,7 +32,9 @@ def generate_to_shards(model, conditions: torch.Tensor, out_dir, shard_rows: int
     manifest = {"format": "osteo-ddpm-b200 shards v1", "rows": n, "shard_rows": int(shard_rows), "seed": int(seed), "row_base": int(row_base),
                 "mutation_dim": int(model.mutation_dim), "expression_dim": int(model.expression_dim), "pathway_dim": int(model.pathway_dim),
                 "mutations": "bits (LSB first, ceil(mutation_dim / 8) bytes per patient)" if pack_bits else "uint8 0/1", "shards": []}
-    writer: Optional[threading.Thread] = None
+    pool = ThreadPoolExecutor(max_workers=1)      # the writer: at most one shard in flight on the host
+    pending = None                                # (future, manifest entry) of the shard being written
+    pinned: List[Dict[str, torch.Tensor]] = [{}, {}]      # two sets of pinned staging buffers, reused shard after shard
 
     def write(idx: int, host: Dict[str, torch.Tensor], ready) -> None:
         if ready is not None:
@@ -40,31 +42,49 @@ def generate_to_shards(model, conditions: torch.Tensor, out_dir, shard_rows: int
         for k, t in host.items():
             np.save(out / f"shard_{idx:05d}_{k}.npy", t.numpy())
 
-    for idx, b in enumerate(range(0, n, shard_rows)):
-        e = min(b + shard_rows, n)
-        comp = model.sample_components(conditions[b:e], e - b, seed=seed, row_base=row_base + b, pack_bits=pack_bits)
-        keep = {"expression": comp["expression"], "pathways": comp["pathways"], "conditions": comp["conditions"],
-                ("mutation_bits" if pack_bits else "mutations"): comp["mutation_bits" if pack_bits else "mutations"]}
-        host, ready = {}, None
-        if on_gpu:
-            copy_stream.wait_stream(torch.cuda.current_stream(conditions.device))
-            with torch.cuda.stream(copy_stream):
-                for k, t in keep.items():
-                    t = t.contiguous()
-                    t.record_stream(copy_stream)
-                    host[k] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                    host[k].copy_(t, non_blocking=True)
-                ready = torch.cuda.Event()
-                ready.record(copy_stream)
-        else:
-            host = {k: t.contiguous() for k, t in keep.items()}
-        if writer is not None:
-            writer.join()                      # at most one shard in flight on the host: bounded pinned memory
-        writer = threading.Thread(target=write, args=(idx, host, ready))
-        writer.start()
-        manifest["shards"].append({"index": idx, "row_begin": row_base + b, "rows": e - b})
-    if writer is not None:
-        writer.join()
+    def finish(p) -> None:
+        """Wait for a shard's files; a failure in the writer thread (full disk, permissions, a CUDA error surfacing in
+        ready.synchronize()) is re-raised HERE, and only a completely written shard enters the manifest."""
+        fut, entry = p
+        fut.result()
+        manifest["shards"].append(entry)
+
+    def staging(slot: int, key: str, like: torch.Tensor) -> torch.Tensor:
+        buf = pinned[slot].get(key)
+        if buf is None or buf.dtype != like.dtype or buf.shape[1:] != like.shape[1:] or buf.shape[0] < like.shape[0]:
+            buf = torch.empty((max(like.shape[0], min(shard_rows, n)),) + tuple(like.shape[1:]), dtype=like.dtype, pin_memory=True)
+            pinned[slot][key] = buf
+        return buf[:like.shape[0]]
+
+    try:
+        for idx, b in enumerate(range(0, n, shard_rows)):
+            e = min(b + shard_rows, n)
+            comp = model.sample_components(conditions[b:e], e - b, seed=seed, row_base=row_base + b, pack_bits=pack_bits)
+            keep = {"expression": comp["expression"], "pathways": comp["pathways"], "conditions": comp["conditions"],
+                    ("mutation_bits" if pack_bits else "mutations"): comp["mutation_bits" if pack_bits else "mutations"]}
+            host, ready = {}, None
+            if on_gpu:
+                copy_stream.wait_stream(torch.cuda.current_stream(conditions.device))
+                with torch.cuda.stream(copy_stream):
+                    for k, t in keep.items():
+                        # the copy reads the SOURCE storage (expression / pathways are column views of one buffer) on copy_stream: tell the
+                        # caching allocator, or the storage could be handed out again while the copy is still in flight
+                        t.record_stream(copy_stream)
+                        # slot idx % 2 was last used by shard idx - 2, whose writer finished before shard idx - 1's writer started
+                        host[k] = staging(idx % 2, k, t)
+                        host[k].copy_(t, non_blocking=True)          # strided device view -> dense pinned rows in one 2-D copy
+                    ready = torch.cuda.Event()
+                    ready.record(copy_stream)
+            else:
+                host = {k: t.contiguous() for k, t in keep.items()}
+            if pending is not None:
+                finish(pending)
+            pending = (pool.submit(write, idx, host, ready), {"index": idx, "row_begin": row_base + b, "rows": e - b})
+        if pending is not None:
+            finish(pending)
+            pending = None
+    finally:
+        pool.shutdown(wait=True)
     (out / "manifest.json").write_text(json.dumps(manifest, indent=1))
     return manifest
 

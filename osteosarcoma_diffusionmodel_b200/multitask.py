@@ -48,6 +48,11 @@ class _CorrLoss(torch.autograd.Function):
         n, G = data.shape
         S = ci.shape[0]
         rank, ws = D.world()
+        with torch.cuda.device(data.device):
+            return _CorrLoss._forward_on_device(ctx, data, ci, modes, n_eff, lib, n, S, ws)
+
+    @staticmethod
+    def _forward_on_device(ctx, data, ci, modes, n_eff, lib, n, S, ws):
         # a shift near the column means conditions the fp64 moments; ranks must agree on it before their moments are summed
         if ws == 1 and n_eff is None:
             shift = data[0, ci.clamp(min=0).long()].contiguous()
@@ -70,8 +75,9 @@ class _CorrLoss(torch.autograd.Function):
         data, ci, coef = ctx.saved_tensors
         up = (grad_out.to(torch.float32) * ctx.scale).contiguous()
         grad = torch.zeros_like(data)
-        _lib.check(_lib.load().osteo_corr_loss_backward(data.data_ptr(), data.shape[0], data.shape[1], ci.data_ptr(), ci.shape[0], coef.data_ptr(), up.data_ptr(),
-                                                        grad.data_ptr(), _lib.stream_handle()))
+        with torch.cuda.device(data.device):
+            _lib.check(_lib.load().osteo_corr_loss_backward(data.data_ptr(), data.shape[0], data.shape[1], ci.data_ptr(), ci.shape[0], coef.data_ptr(), up.data_ptr(),
+                                                            grad.data_ptr(), _lib.stream_handle()))
         return grad, None, None, None
 
 

@@ -1,10 +1,17 @@
-"""GPU mirror of the three validators on the hot path: `BiologicalValidator.compute_mmd`,
-`.validate_pathway_coherence`, `.validate_mutation_expression_correlation`
-(utils/validation.py:273-298, :125-175, :177-223).  Same method names, argument meaning and return
-values as the reference; the arithmetic runs in the C-ABI library (RBF Gram tiles on tcgen05 with an
-exp/sum epilogue; column-gathered fp64 moment reduction for the Pearson correlations).  Under
-torch.distributed the Gram rows / cohort rows are sharded over ranks and only the partial sums are
-all-reduced.  No CPU fallback.
+"""GPU mirror of `BiologicalValidator` (utils/validation.py:18-387): the three validators on the hot path --
+`compute_mmd`, `validate_pathway_coherence`, `validate_mutation_expression_correlation` (:273-298, :125-175, :177-223) --
+and the rest of the class (`validate_mutation_cooccurrence` :27-123, `statistical_tests` :225-271, `validate_all` :300-387;
+SURVEY.md §8(f)#3) so that `main.py --steps validate` (main.py:322) runs against the drop-in.  Same method names, argument
+meaning, result keys and return values as the reference.
+
+The heavy arithmetic runs in the C-ABI library: RBF Gram tiles on tcgen05 with an exp/sum epilogue; column-gathered fp64
+moment reduction for the Pearson correlations; the 2x2 co-occurrence tables as ONE binary M^T M contraction on tcgen05
+(`osteo_wgrad_tc`: 0/1 is exact in bf16 and the fp32 accumulators count exactly up to 2^24 rows); the PCA scatter matrix as a
+split-bf16 (fp32x3) Gram.  What is left to torch on the device are library primitives outside the hot path: `sort` /
+`searchsorted` for the KS statistic and the 1-D Wasserstein distance, `linalg.eigh` for the 10 leading principal axes.  Scalar
+finishes (Pearson from moments, chi-square from four counts, KS p-value from D) run on the host in float64 like the reference.
+Under torch.distributed the Gram rows / cohort rows are sharded over ranks and only the partial sums are all-reduced
+(SURVEY.md §8e).  No CPU fallback.
 """
 from __future__ import annotations
 
@@ -71,8 +78,11 @@ def _corr_from_moments(mom: np.ndarray, k: int) -> np.ndarray:
         return cov / np.outer(sd, sd)
 
 
+_on_validator_device = _lib.on_device(lambda v: v.device)
+
+
 class BiologicalValidator:
-    """Validate synthetic patients against biological knowledge (GPU-resident hot-path subset)."""
+    """Validate synthetic patients against biological knowledge (GPU-resident)."""
 
     def __init__(self, config: dict, device: Optional[str] = None, precision: str = "fp32x3"):
         self.config = config
@@ -91,6 +101,7 @@ class BiologicalValidator:
             raise RuntimeError("BiologicalValidator (B200-native) computes only on a CUDA device; there is no CPU fallback")
 
     # ------------------------------------------------------------------ utils/validation.py:273-298
+    @_on_validator_device
     def compute_mmd(self, X, Y, kernel: str = "rbf", gamma: Optional[float] = None) -> float:
         """sqrt(max(mean Kxx + mean Kyy - 2 mean Kxy, 0)) with K = exp(-gamma ||a - b||^2), diagonals included; gamma
         defaults to 1 / n_features; `kernel` is ignored exactly as in the reference."""
@@ -165,6 +176,7 @@ class BiologicalValidator:
         flat = torch.cat([mr, ms]).cpu().numpy()
         return self._scores_from_moments(flat[:len(members_real)], members_real), self._scores_from_moments(flat[len(members_real):], members_syn)
 
+    @_on_validator_device
     def validate_pathway_coherence(self, real_data, synthetic_data, pathway_gene_matrix) -> Dict[str, float]:
         """Mean within-pathway pairwise Pearson correlation for the first 10 pathways (>= 3 member genes present), for the
         real and the synthetic cohort, and the correlation of the two score vectors.
@@ -197,6 +209,7 @@ class BiologicalValidator:
         logger.info("Coherence correlation: %.3f", results["pathway_coherence_correlation"])
         return results
 
+    @_on_validator_device
     def pathway_coherence_from_tensors(self, real: torch.Tensor, synthetic: torch.Tensor, members: Sequence[Sequence[int]]) -> Dict[str, float]:
         """Tensor entry point for large GPU-resident cohorts: `members[p]` = column indices of pathway p's genes."""
         self._require_cuda()
@@ -208,6 +221,7 @@ class BiologicalValidator:
                 "pathway_coherence_correlation": float(np.corrcoef(rs, ss)[0, 1])}
 
     # ------------------------------------------------------------------ utils/validation.py:177-223
+    @_on_validator_device
     def validate_mutation_expression_correlation(self, mutations, expression, pathway_scores) -> Dict[str, float]:
         """Sign check of corr(mutation status, pathway activity) for every rule of evaluation.required_correlations."""
         self._require_cuda()
@@ -231,3 +245,225 @@ class BiologicalValidator:
         if total > 0:
             results["mutation_expression_violation_rate"] = violations / total
         return results
+
+    # ------------------------------------------------------------------ utils/validation.py:27-123
+    def _binary_columns(self, df, cols: Sequence) -> torch.Tensor:
+        """fp32 device tensor [n, len(cols)] of the given DataFrame columns; raises unless every value is 0 or 1 (the co-occurrence
+        tables are counted by a binary Gram; the reference's crosstab would grow extra categories for other values)."""
+        t = _to_device(df[list(cols)], self.device)
+        if not bool(((t == 0) | (t == 1)).all()):
+            raise ValueError("mutation matrices must be binary (0 / 1)")
+        return t
+
+    def _cooccurrence_counts(self, m: torch.Tensor) -> np.ndarray:
+        """n11[i, j] = #rows with columns i and j both 1: M^T M on tcgen05 (exact for < 2^24 rows per call)."""
+        n, k = m.shape
+        out = torch.zeros((k, k), dtype=torch.float64, device=m.device)
+        lib = _lib.load()
+        step = 1 << 23
+        for r0 in range(0, n, step):
+            blk = m[r0:r0 + step].contiguous()
+            g = torch.empty((k, k), dtype=torch.float32, device=m.device)
+            _lib.check(lib.osteo_wgrad_tc(blk.data_ptr(), blk.data_ptr(), g.data_ptr(), blk.shape[0], k, k, _lib.PREC_BF16, _lib.stream_handle()))
+            out += g.double()
+        return out.cpu().numpy()
+
+    @staticmethod
+    def _chi2_2x2(n11: float, s_i: float, s_j: float, n: float) -> float:
+        """scipy.stats.chi2_contingency(pd.crosstab(a, b))[0] for two 0/1 columns from their counts: a constant column makes the
+        crosstab 1 x 2 (dof 0 -> 0.0); otherwise Pearson's statistic with Yates' continuity correction (dof 1)."""
+        if s_i in (0.0, n) or s_j in (0.0, n):
+            return 0.0
+        obs = np.array([[n - s_i - s_j + n11, s_j - n11], [s_i - n11, n11]], dtype=np.float64)
+        exp = np.outer(obs.sum(1), obs.sum(0)) / n
+        diff = exp - obs
+        obs = obs + np.minimum(0.5, np.abs(diff)) * np.sign(diff)
+        return float(((obs - exp) ** 2 / exp).sum())
+
+    @_on_validator_device
+    def validate_mutation_cooccurrence(self, real_mutations, synthetic_mutations) -> Dict[str, float]:
+        """Mutation-frequency correlation, driver-gene frequency difference, mutual-exclusivity violation rate and the correlation
+        of the pairwise chi-square scores of (up to) 50 randomly chosen genes -- drawn with the same `np.random.choice` call as the
+        reference, so a seeded numpy RNG picks the same genes."""
+        self._require_cuda()
+        results: Dict[str, float] = {}
+        real_t = _to_device(real_mutations, self.device)
+        syn_t = _to_device(synthetic_mutations, self.device)
+        real_cols, syn_cols = list(real_mutations.columns), list(synthetic_mutations.columns)
+        real_freq = (real_t.sum(0, dtype=torch.float64) / real_t.shape[0]).cpu().numpy()
+        syn_freq = (syn_t.sum(0, dtype=torch.float64) / syn_t.shape[0]).cpu().numpy()
+        ri = {g: i for i, g in enumerate(real_cols)}
+        si = {g: i for i, g in enumerate(syn_cols)}
+        common_genes = real_mutations.columns.intersection(synthetic_mutations.columns)
+        common = list(common_genes)
+        freq_corr = np.corrcoef(real_freq[[ri[g] for g in common]], syn_freq[[si[g] for g in common]])[0, 1]
+        results["mutation_frequency_correlation"] = freq_corr
+        logger.info("Mutation frequency correlation: %.3f", freq_corr)
+
+        drivers = [g for g in self.driver_genes if g in ri]
+        if drivers:
+            diff = np.abs(real_freq[[ri[g] for g in drivers]] - syn_freq[[si[g] for g in drivers]]).mean()      # KeyError like the reference
+            results["driver_gene_frequency_diff"] = diff
+            logger.info("Driver gene frequency difference: %.3f", diff)
+
+        if self.mutually_exclusive_pairs:
+            violations, total_pairs = 0, 0
+            for g1, g2 in self.mutually_exclusive_pairs:
+                if g1 in si and g2 in si:
+                    violations += int(((syn_t[:, si[g1]] == 1) & (syn_t[:, si[g2]] == 1)).sum())
+                    total_pairs += 1
+            if total_pairs > 0:
+                results["mutual_exclusivity_violation_rate"] = violations / (syn_t.shape[0] * total_pairs)
+                logger.info("Mutual exclusivity violation rate: %.3f", results["mutual_exclusivity_violation_rate"])
+
+        sample_genes = np.random.choice(common_genes, size=min(50, len(common_genes)), replace=False)
+        if len(sample_genes) >= 2:
+            chi = []
+            for t, index in ((real_t, ri), (syn_t, si)):
+                m = t[:, [index[g] for g in sample_genes]].contiguous()
+                if not bool(((m == 0) | (m == 1)).all()):
+                    raise ValueError("mutation matrices must be binary (0 / 1)")
+                n11 = self._cooccurrence_counts(m)
+                s, n = np.diag(n11), float(m.shape[0])
+                k = len(sample_genes)
+                chi.append([self._chi2_2x2(n11[i, j], s[i], s[j], n) for i in range(k) for j in range(i + 1, k)])
+            chi2_corr = np.corrcoef(chi[0], chi[1])[0, 1]
+            results["cooccurrence_pattern_correlation"] = chi2_corr
+            logger.info("Co-occurrence pattern correlation: %.3f", chi2_corr)
+        return results
+
+    # ------------------------------------------------------------------ utils/validation.py:225-271
+    @staticmethod
+    def _ks_pvalue(d: float, n1: int, n2: int) -> float:
+        """Two-sided p-value of scipy.stats.ks_2samp(method='auto') from the statistic: exact for max(n1, n2) <= 10 000 (scipy's own
+        lattice-path count, a scalar routine), asymptotic Kolmogorov distribution otherwise."""
+        from scipy.stats import distributions
+
+        if max(n1, n2) <= 10000:
+            try:
+                from scipy.stats._stats_py import _attempt_exact_2kssamp
+
+                ok, _, prob = _attempt_exact_2kssamp(n1, n2, int(np.gcd(n1, n2)), d, "two-sided")
+                if ok:
+                    return float(np.clip(prob, 0, 1))
+            except ImportError:      # private helper moved: fall through to the asymptotic form
+                pass
+        m, n = sorted([float(n1), float(n2)], reverse=True)
+        return float(np.clip(distributions.kstwo.sf(d, np.round(m * n / (m + n))), 0, 1))
+
+    @staticmethod
+    def _cdf_pair(a: torch.Tensor, b: torch.Tensor):
+        """Column-wise empirical CDFs of a [n1, k] and b [n2, k] evaluated at the pooled sorted sample: (all_sorted [n1+n2, k], F_a, F_b)."""
+        a_s = torch.sort(a.t().contiguous(), dim=1).values
+        b_s = torch.sort(b.t().contiguous(), dim=1).values
+        allv = torch.sort(torch.cat([a_s, b_s], dim=1), dim=1).values
+        fa = torch.searchsorted(a_s, allv, right=True).double() / a.shape[0]
+        fb = torch.searchsorted(b_s, allv, right=True).double() / b.shape[0]
+        return allv, fa, fb
+
+    def _ks_statistics(self, a: torch.Tensor, b: torch.Tensor) -> np.ndarray:
+        _, fa, fb = self._cdf_pair(a, b)
+        d = fa - fb
+        return torch.maximum(torch.clamp(-d.min(dim=1).values, 0, 1), d.max(dim=1).values).cpu().numpy()
+
+    def _wasserstein(self, a: torch.Tensor, b: torch.Tensor) -> np.ndarray:
+        """scipy.stats.wasserstein_distance per column: integral of |F_a - F_b| over the pooled sample."""
+        allv, fa, fb = self._cdf_pair(a.double(), b.double())
+        return ((fa - fb).abs()[:, :-1] * (allv[:, 1:] - allv[:, :-1])).sum(dim=1).cpu().numpy()
+
+    # tcgen05 contractions behind the PCA (split-bf16 = fp32x3: ~3e-6 relative per entry)
+    @staticmethod
+    def _gram_rows(x: torch.Tensor) -> torch.Tensor:
+        """x x^T, [n, n] fp32."""
+        n, d = x.shape
+        g = torch.empty((n, n), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().osteo_linear_tc(x.data_ptr(), x.data_ptr(), None, g.data_ptr(), n, n, d, _lib.PREC_FP32X3, _lib.stream_handle()))
+        return g
+
+    @staticmethod
+    def _gram_cols(x: torch.Tensor) -> torch.Tensor:
+        """x^T x, [d, d] fp32 (both operands MN-major, rows split over CTAs)."""
+        n, d = x.shape
+        g = torch.empty((d, d), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().osteo_wgrad_tc(x.data_ptr(), x.data_ptr(), g.data_ptr(), n, d, d, _lib.PREC_FP32X3, _lib.stream_handle()))
+        return g
+
+    @staticmethod
+    def _project(x: torch.Tensor, axes_t: torch.Tensor) -> torch.Tensor:
+        """x axes_t^T, [n, k] fp32."""
+        n, d = x.shape
+        k = axes_t.shape[0]
+        out = torch.empty((n, k), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.load().osteo_linear_tc(x.data_ptr(), axes_t.data_ptr(), None, out.data_ptr(), n, k, d, _lib.PREC_FP32X3, _lib.stream_handle()))
+        return out
+
+    def _pca_scores(self, real: torch.Tensor, synthetic: torch.Tensor, k: int = 10):
+        """Scores of both cohorts on the k leading principal axes of the REAL cohort (sklearn PCA.fit_transform / .transform: centre on
+        the real mean, project). The scatter matrix is a split-bf16 (fp32x3) Gram on tcgen05 -- rows x rows when there are fewer
+        patients than features, features x features otherwise -- its k leading eigenvectors come from linalg.eigh in float64."""
+        n, d = real.shape
+        mean = real.sum(0, dtype=torch.float64) / n
+        rc = (real.double() - mean).float().contiguous()
+        sc = (synthetic.double() - mean).float().contiguous()
+        k = min(k, n, d)
+        if n <= d:
+            g = self._gram_rows(rc).double()
+            w, u = torch.linalg.eigh((g + g.t()) / 2)
+            w, u = w[-k:].flip(0), u[:, -k:].flip(1)
+            axes = (rc.double().t() @ u) / torch.sqrt(w.clamp_min(1e-300))          # [d, k] unit vectors
+        else:
+            g = self._gram_cols(rc).double()
+            _, v = torch.linalg.eigh((g + g.t()) / 2)
+            axes = v[:, -k:].flip(1)
+        axes_t = axes.t().float().contiguous()                                        # [k, d]
+        return self._project(rc, axes_t), self._project(sc, axes_t)
+
+    @_on_validator_device
+    def statistical_tests(self, real_data, synthetic_data) -> Dict[str, float]:
+        """KS test on the first 100 features, RBF-MMD, mean 1-D Wasserstein distance over the 10 leading principal components."""
+        self._require_cuda()
+        results: Dict[str, float] = {}
+        real = _to_device(real_data, self.device)
+        syn = _to_device(synthetic_data, self.device)
+        nf = min(real.shape[1], 100)
+        d = self._ks_statistics(real[:, :nf], syn[:, :nf])
+        pvals = np.array([self._ks_pvalue(float(x), real.shape[0], syn.shape[0]) for x in d])
+        results["ks_test_mean_pvalue"] = np.mean(pvals)
+        results["ks_test_fraction_significant"] = (pvals < 0.05).mean()
+        logger.info("KS test mean p-value: %.3f", results["ks_test_mean_pvalue"])
+        logger.info("KS test fraction significant: %.3f", results["ks_test_fraction_significant"])
+        results["mmd"] = self.compute_mmd(real, syn)
+        logger.info("MMD: %.4f", results["mmd"])
+        real_pca, syn_pca = self._pca_scores(real, syn, 10)
+        results["wasserstein_distance_mean"] = np.mean(self._wasserstein(real_pca, syn_pca))
+        logger.info("Mean Wasserstein distance: %.3f", results["wasserstein_distance_mean"])
+        return results
+
+    # ------------------------------------------------------------------ utils/validation.py:300-387
+    @_on_validator_device
+    def validate_all(self, real_mutations, real_expression, real_pathways, synth_mutations, synth_expression, synth_pathways,
+                     pathway_gene_matrix=None) -> Dict[str, float]:
+        """Run all validation tests; same result keys and overall score as the reference."""
+        all_results: Dict[str, float] = {}
+        all_results.update(self.validate_mutation_cooccurrence(real_mutations, synth_mutations))
+        if pathway_gene_matrix is not None:
+            all_results.update(self.validate_pathway_coherence(real_expression, synth_expression, pathway_gene_matrix))
+        all_results.update(self.validate_mutation_expression_correlation(synth_mutations, synth_expression, synth_pathways))
+        real_all = torch.cat([_to_device(x, self.device) for x in (real_mutations, real_expression, real_pathways)], dim=1)
+        syn_all = torch.cat([_to_device(x, self.device) for x in (synth_mutations, synth_expression, synth_pathways)], dim=1)
+        all_results.update(self.statistical_tests(real_all, syn_all))
+        for key, value in all_results.items():
+            logger.info("%s: %.4f", key, value)
+        score = []
+        if "mutation_frequency_correlation" in all_results:
+            score.append(all_results["mutation_frequency_correlation"])
+        if "cooccurrence_pattern_correlation" in all_results:
+            score.append(all_results["cooccurrence_pattern_correlation"])
+        if "mutual_exclusivity_violation_rate" in all_results:
+            score.append(1 - all_results["mutual_exclusivity_violation_rate"])
+        if "mutation_expression_violation_rate" in all_results:
+            score.append(1 - all_results["mutation_expression_violation_rate"])
+        if score:
+            all_results["overall_biological_score"] = np.mean(score)
+            logger.info("Overall Biological Score: %.3f", all_results["overall_biological_score"])
+        return all_results

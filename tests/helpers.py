@@ -19,7 +19,12 @@ CASES = {
 
 # Stated tolerances (norm-wise relative Frobenius error against the reference's fp32 output)
 TOL_FP32X3 = 1e-4      # north_star: "stated fp32 tolerance (rel 1e-4)"
-TOL_BF16 = 2e-2        # bf16 operands vs the fp32 reference (SURVEY.md §7 "State precision": weights alone cost 1.8e-3)
+TOL_BF16 = 2e-2        # bf16 operands vs the fp32 reference, single calls (SURVEY.md §7 "State precision": weights alone cost 1.8e-3)
+# The benchmarked mode (bf16 operands, fused step kernel, replayed graphs) over the FULL 1000-step loop, final sample and every trajectory
+# checkpoint. Measured on B200 against the reference's goldens (scripts/measure_bf16_loop.py -> profiles/r2_bf16_loop_error.txt):
+# 3.4e-3 (smoke), 3.4e-3 (config.yaml dims), 2.8e-3 (linear schedule) -- the error is set in the first ~10 steps (c_x = 99.99 at t = 999
+# amplifies the bf16 rounding of eps) and does not grow afterwards. Stated tolerance = 3x the worst measurement.
+TOL_BF16_LOOP = 1e-2
 
 
 def rel(a, b) -> float:

@@ -38,3 +38,27 @@ def test_shards_round_trip_and_do_not_depend_on_the_shard_size(tmp_path):
         assert np.array_equal(g["conditions"], cond.numpy())
     part = load_shards(tmp_path / "s5", shards=[1, 3])
     assert part["expression"].shape == (10, 7) and part["expression"][0, 0] == 105 + 4
+
+
+def test_writer_failures_surface_and_the_manifest_lists_only_written_shards(tmp_path, monkeypatch):
+    """A failure in the writer thread (full disk, permissions) must not be swallowed: generate_to_shards raises and never writes a
+    manifest that advertises missing shards."""
+    import pytest
+
+    from osteosarcoma_diffusionmodel_b200 import egress
+
+    model, n = _FakeModel(), 20
+    cond = torch.zeros(n, 2)
+    real_save = np.save
+    calls = {"n": 0}
+
+    def flaky_save(path, arr):
+        calls["n"] += 1
+        if "shard_00002" in str(path):
+            raise OSError("No space left on device")
+        return real_save(path, arr)
+
+    monkeypatch.setattr(egress.np, "save", flaky_save)
+    with pytest.raises(OSError, match="No space left"):
+        generate_to_shards(model, cond, tmp_path / "x", shard_rows=5, pack_bits=False)
+    assert not (tmp_path / "x" / "manifest.json").exists()
