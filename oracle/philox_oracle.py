@@ -1,9 +1,11 @@
 """ORACLE — numpy restatement of the in-kernel counter RNG (csrc/philox.cuh); test infrastructure.
 
-Philox4x32-10 (Salmon et al., SC'11; same constants as Random123 / cuRAND) with
-counter = (col4 -- col8 for the packed reverse-noise stream --, row_lo, row_hi, stream << 16 | step), key = (seed_lo, seed_hi).  The reference has
-no counterpart (it calls torch.randn, models/diffusion.py:335,409,443); this is pinned by the
-Random123 known-answer vectors in tests/test_philox.py.
+Philox4x32 (Salmon et al., SC'11; same constants as Random123 / cuRAND) with
+counter = (col4 -- col8 for the packed reverse-noise stream --, row_lo, row_hi, stream << 16 | step), key = (seed_lo, seed_hi);
+10 rounds for every stream except the reverse-step noise (stream 0), which uses 7 (the paper's smallest BigCrush-clean round count;
+csrc/philox.cuh: philox_rounds).  The reference has no counterpart (it calls torch.randn, models/diffusion.py:335,409,443); the
+10-round form is pinned by the Random123 known-answer vectors in tests/test_philox.py and the 7-round form is the same loop run
+seven times (plus the algebraic check there that rounds compose).
 """
 from __future__ import annotations
 
@@ -14,13 +16,25 @@ W0, W1 = np.uint32(0x9E3779B9), np.uint32(0xBB67AE85)
 MASK = np.uint64(0xFFFFFFFF)
 
 
+ROUNDS, ROUNDS_REVERSE = 10, 7
+
+
+def rounds_of(stream: int) -> int:
+    return ROUNDS_REVERSE if stream == 0 else ROUNDS
+
+
 def philox4x32_10(ctr: np.ndarray, key: np.ndarray) -> np.ndarray:
-    """ctr [..., 4] uint32, key [..., 2] uint32 (broadcastable) -> [..., 4] uint32."""
+    return philox4x32(ctr, key, ROUNDS)
+
+
+def philox4x32(ctr: np.ndarray, key: np.ndarray, rounds: int = 10, first_round: int = 0) -> np.ndarray:
+    """ctr [..., 4] uint32, key [..., 2] uint32 (broadcastable) -> [..., 4] uint32 after `rounds` Philox rounds; `first_round` offsets
+    the key schedule (round r uses key + r * W), so philox(philox(c, k, a), k, b, first_round=a) == philox(c, k, a + b)."""
     c = [ctr[..., i].astype(np.uint64) for i in range(4)]
-    k0 = np.asarray(key[..., 0], dtype=np.uint32).copy()
-    k1 = np.asarray(key[..., 1], dtype=np.uint32).copy()
     with np.errstate(over="ignore"):
-        for _ in range(10):
+        k0 = (np.asarray(key[..., 0], dtype=np.uint32) + np.uint32((int(W0) * first_round) & 0xFFFFFFFF)).astype(np.uint32)
+        k1 = (np.asarray(key[..., 1], dtype=np.uint32) + np.uint32((int(W1) * first_round) & 0xFFFFFFFF)).astype(np.uint32)
+        for _ in range(rounds):
             p0 = M0 * c[0]
             p1 = M1 * c[2]
             hi0, lo0 = p0 >> np.uint64(32), p0 & MASK
@@ -41,7 +55,7 @@ def words(seed: int, rows: np.ndarray, ncol4: int, stream: int, step: int) -> np
     ctr[..., 2] = (rows >> np.uint64(32)).astype(np.uint32)[:, None]
     ctr[..., 3] = np.uint32(((stream & 0xFFFF) << 16) | (step & 0xFFFF))
     key = np.array([seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF], dtype=np.uint32)
-    return philox4x32_10(ctr, key)
+    return philox4x32(ctr, key, rounds_of(stream))
 
 
 def unit_1_2(w: np.ndarray) -> np.ndarray:

@@ -224,7 +224,7 @@ __global__ void philox_words_kernel(uint32_t* __restrict__ out, long long n, int
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total; i += static_cast<long long>(gridDim.x) * blockDim.x) {
         const long long r = i / ncol4;
         const int c4 = static_cast<int>(i % ncol4);
-        const uint4 w = philox_words(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), stream_id, step);
+        const uint4 w = philox_words_stream(seed, static_cast<uint64_t>(row_base + r), static_cast<uint32_t>(c4), stream_id, step);
         reinterpret_cast<uint4*>(out)[i] = w;
     }
 }

@@ -227,7 +227,7 @@ struct osteo_ddpm_ctx {
     int graph_precision = -1, graph_chunk = -1, graph_fused = -1, graph_branches = -1, graph_noise_t0 = 0;
     int graph_nb = 0;                    // row branches the cached sampling graph was captured with
     const float* graph_noise = nullptr;
-    unsigned long long graph_generation = ~0ull;
+    unsigned long long graph_generation = ~0ull, graph_weights_version = ~0ull;
     long long graph_launches_per_step = 0;
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every GEMM launch
     // graph caches of the training path (api_train.inl): weight repack after an optimizer step, forward + backward
@@ -238,8 +238,12 @@ struct osteo_ddpm_ctx {
     int train_graph_enable = 1;
     DevBuf seed_dev;                     // u64: Philox key of the graph-replayed training step
 
+    std::vector<float> h_bias_out;       // host copy of output_proj.bias (zero padded): the fused kernel takes it by value (FusedParams::bias_c)
+    bool h_bias_valid = false;
+    unsigned long long weights_version = 0;   // bumped by set_weights: part of the sampling-graph key (the graphs embed bias_c)
+
     bool x3() const { return precision == OSTEO_PREC_FP32X3; }
-    bool fused_ok() const { return fused_enable && precision == OSTEO_PREC_BF16 && hidden[0] <= 256; }
+    bool fused_ok() const { return fused_enable && precision == OSTEO_PREC_BF16 && hidden[0] <= 256 && DP <= F_BIAS_MAX; }
     int xs_nbox() const { return x_c8 ? DP / 8 : x_nbox; }
     int xs_shift() const { return x_c8 ? 3 : 5; }
     int h0() const { return hidden[0]; }
@@ -463,6 +467,8 @@ static int launch_fused(osteo_ddpm_ctx* c, long long row0, long long row1, const
     p.x = c->x.as<float>();
     p.x_c8 = c->DP / 8;
     p.bias_out = c->out_proj.bias.as<float>();
+    if (!c->h_bias_valid) return fail("internal: host copy of output_proj.bias is stale (ensure_host_bias must run before the fused step is enqueued)");
+    std::memcpy(p.bias_c, c->h_bias_out.data(), sizeof(float) * static_cast<size_t>(c->DP));
     p.noise = noise;
     p.noise_ld = c->D;
     p.noise_step_stride = noise ? c->noise_step_stride : 0;
@@ -470,6 +476,11 @@ static int launch_fused(osteo_ddpm_ctx* c, long long row0, long long row1, const
     p.eps_out = eps_out;
     p.eps_ld = c->D;
     p.seed = seed;
+    for (int r = 0; r < PHILOX_ROUNDS_REVERSE; ++r) {      // Philox key schedule, hoisted out of the kernel: round r uses key + r * (W0, W1)
+        p.rk[2 * r] = static_cast<uint32_t>(seed) + static_cast<uint32_t>(r) * 0x9E3779B9u;
+        p.rk[2 * r + 1] = static_cast<uint32_t>(seed >> 32) + static_cast<uint32_t>(r) * 0xBB67AE85u;
+    }
+    p.one_bits = 0x3f800000u;
     p.row_base = row_base;
     p.bias_in = c->in_proj.bias.as<float>();
     p.time_table = c->time_table.as<float>();
@@ -477,6 +488,8 @@ static int launch_fused(osteo_ddpm_ctx* c, long long row0, long long row1, const
     p.h0_out = c->acts[0]->ptr();
     p.h0_ld = 2 * c->h0();
     if (const char* e = getenv("OSTEO_DDPM_DBG")) p.dbg = atoi(e);
+    p.prefetch = F_PREFETCH;
+    if (const char* e = getenv("OSTEO_FUSED_PF")) p.prefetch = atoi(e);
     if (p.m_tiles <= 0) return 0;
     const bool want_trace = getenv("OSTEO_DDPM_TRACE") != nullptr;      // diagnostics: synchronises, prints CTA 0's event timeline
     if (want_trace) {
@@ -527,6 +540,19 @@ static int enqueue_reverse_step(osteo_ddpm_ctx* c, long long n, const float* noi
         if (c->x_c8) OSTEO_TRY(launch_fused(c, r0, r1, noise, eps_out, seed, row_base, s));
         else OSTEO_TRY(launch_output_ddpm(c, r0, r1, noise, eps_out, seed, row_base, s));
     }
+    return 0;
+}
+
+// The fused kernel takes output_proj.bias by value: refresh the host copy after a weight change. Synchronises `s` (once per
+// set_weights, and only when the fused path is used next); must not be called while `s` is capturing.
+static int ensure_host_bias(osteo_ddpm_ctx* c, cudaStream_t s) {
+    if (c->h_bias_valid || !c->fused_ok()) return 0;
+    c->h_bias_out.assign(F_BIAS_MAX, 0.0f);
+    const size_t n = static_cast<size_t>(c->out_proj.np) < static_cast<size_t>(F_BIAS_MAX) ? c->out_proj.np : F_BIAS_MAX;
+    OSTEO_CUDA(cudaMemcpyAsync(c->h_bias_out.data(), c->out_proj.bias.p, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    OSTEO_CUDA(cudaStreamSynchronize(s));
+    for (size_t i = static_cast<size_t>(c->D); i < static_cast<size_t>(F_BIAS_MAX); ++i) c->h_bias_out[i] = 0.0f;      // padding columns stay exact zeros
+    c->h_bias_valid = true;
     return 0;
 }
 
@@ -958,6 +984,8 @@ int osteo_ddpm_set_weights(osteo_ddpm_ctx* c, const float* const* w, int n_tenso
     const int rc = run_cached(c, c->weights_graph, key, s0, enqueue);
     if (rc != 0) c->have_weights = had;
     c->h0_primed = false;
+    c->h_bias_valid = false;
+    ++c->weights_version;
     return rc;
 }
 
@@ -1063,6 +1091,7 @@ int osteo_ddpm_reverse_step(osteo_ddpm_ctx* c, long long n, int t, const float* 
     set_int_kernel<<<1, MAX_BRANCHES, 0, s>>>(c->step_dev.as<int>(), t);
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
+    OSTEO_TRY(ensure_host_bias(c, s));
     OSTEO_TRY(ensure_primed(c, n, t, s));
     OSTEO_TRY(enqueue_reverse_step(c, n, noise_dev, eps_out_dev, seed, row_base, s));
     after_steps(c, t, 1);
@@ -1080,6 +1109,7 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
     OSTEO_CUDA(cudaGetLastError());
     ++c->launches;
     if (c->x_c8 != c->fused_ok()) return fail("the state was loaded under a different precision / fused setting: call load_state or init_noise again");
+    OSTEO_TRY(ensure_host_bias(c, s));
     OSTEO_TRY(ensure_primed(c, n, t_start, s));
     // Injected noise is a per-step stack [steps][n, D]: each kernel picks its slice from the device step word (noise_t0 - t), so the
     // replayed graphs below consume it exactly like the in-kernel Philox stream (parity runs of the benchmarked graph path).
@@ -1105,7 +1135,7 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
     const bool reuse = c->graph_exec && c->graph_n == n && c->graph_seed == seed && c->graph_row_base == row_base &&
                        c->graph_precision == c->precision && c->graph_chunk == c->chunk_rows && c->graph_fused == (c->x_c8 ? 1 : 0) &&
                        c->graph_branches == c->branches && c->graph_noise == noise_dev && c->graph_noise_t0 == (noise_dev ? t_start : 0) &&
-                       c->graph_generation == c->generation;
+                       c->graph_generation == c->generation && c->graph_weights_version == c->weights_version;
     if (!reuse) {
         for (cudaGraphExec_t* g : {&c->graph_exec, &c->graph_exec_multi}) {
             if (*g) cudaGraphExecDestroy(*g);
@@ -1130,6 +1160,7 @@ int osteo_ddpm_sample_loop(osteo_ddpm_ctx* c, long long n, int t_start, int t_en
         c->graph_noise = noise_dev;
         c->graph_noise_t0 = noise_dev ? t_start : 0;
         c->graph_generation = c->generation;
+        c->graph_weights_version = c->weights_version;
     }
     c->noise_step_stride = 0;
     int left = steps;
@@ -1200,6 +1231,7 @@ int osteo_ddpm_profile_step(osteo_ddpm_ctx* c, long long n, int t, uint64_t seed
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     set_int_kernel<<<1, MAX_BRANCHES, 0, s>>>(c->step_dev.as<int>(), t);
     OSTEO_CUDA(cudaGetLastError());
+    OSTEO_TRY(ensure_host_bias(c, s));
     OSTEO_TRY(ensure_primed(c, n, t, s));
     std::vector<cudaEvent_t> ev;
     cudaEvent_t e0;

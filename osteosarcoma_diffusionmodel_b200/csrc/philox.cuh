@@ -1,6 +1,9 @@
-// Counter-based RNG for the DDPM noise: Philox4x32-10 keyed by the sampling seed,
+// Counter-based RNG for the DDPM noise: Philox4x32 keyed by the sampling seed,
 // counter = (column/4, global_row_lo, global_row_hi, stream<<16 | step), so a
 // row's noise is independent of how rows are sharded over GPUs.
+// Rounds: 10 (the Random123 / cuRAND default) for everything drawn once per patient or training row; 7 -- the smallest round count
+// Salmon et al. (SC'11, table 2) report as passing BigCrush ("Crush-resistant"), 10 being 7 plus a safety margin -- for the
+// reverse-step noise stream, which is 5142 x 1000 normals per patient and the bulk of every integer instruction the sampling loop issues.
 // The numpy restatement lives in oracle/philox_oracle.py and is compared bit-exactly
 // (uint32 words) and within 2e-6 (Box-Muller normals) in tests/test_philox.py.
 //
@@ -25,10 +28,15 @@ enum PhiloxStream : uint32_t {
     STREAM_TIMESTEP = 16  // randint t (models/diffusion.py:361)
 };
 
-__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+constexpr int PHILOX_ROUNDS = 10;             // x_T, q_sample noise, dropout masks, timesteps
+constexpr int PHILOX_ROUNDS_REVERSE = 7;      // STREAM_REVERSE (the per-step z)
+__host__ __device__ constexpr int philox_rounds(uint32_t stream) { return stream == 0u /* STREAM_REVERSE */ ? PHILOX_ROUNDS_REVERSE : PHILOX_ROUNDS; }
+
+template <int R>
+__device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < R; ++r) {
         const uint32_t hi0 = __umulhi(M0, c.x), lo0 = M0 * c.x;
         const uint32_t hi1 = __umulhi(M1, c.z), lo1 = M1 * c.z;
         c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
@@ -37,11 +45,19 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     }
     return c;
 }
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) { return philox4x32<PHILOX_ROUNDS>(c, k); }
 
+// 10-round words of any stream but STREAM_REVERSE (dropout masks, timesteps, x_T, q_sample noise).
 __device__ __forceinline__ uint4 philox_words(uint64_t seed, uint64_t row, uint32_t col4, uint32_t stream, uint32_t step) {
     const uint4 ctr = make_uint4(col4, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), (stream << 16) | (step & 0xFFFFu));
     const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
     return philox4x32_10(ctr, key);
+}
+// Words of a stream with that stream's round count (philox_rounds): the generic form behind the test hook and philox_normal4.
+__device__ __forceinline__ uint4 philox_words_stream(uint64_t seed, uint64_t row, uint32_t col, uint32_t stream, uint32_t step) {
+    const uint4 ctr = make_uint4(col, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), (stream << 16) | (step & 0xFFFFu));
+    const uint2 key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    return stream == STREAM_REVERSE ? philox4x32<PHILOX_ROUNDS_REVERSE>(ctr, key) : philox4x32<PHILOX_ROUNDS>(ctr, key);
 }
 
 // 23-bit uniforms built with integer ops only (no I2F on the XU pipe): the mantissa trick gives f in [1, 2).
@@ -74,13 +90,13 @@ __device__ __forceinline__ void box_muller_packed(uint32_t w, float& z0, float& 
 }
 __device__ __forceinline__ bool stream_is_packed(uint32_t stream) { return stream == STREAM_REVERSE; }
 
-// N independent Philox4x32-10 blocks advanced round by round (round loop outermost): N independent dependency
+// N independent Philox4x32-R blocks advanced round by round (round loop outermost): N independent dependency
 // chains in flight instead of one, which is what keeps the integer pipes busy with few warps per scheduler.
-template <int N>
-__device__ __forceinline__ void philox4x32_10_batch(uint4 (&c)[N], uint2 k) {
+template <int N, int R>
+__device__ __forceinline__ void philox4x32_batch(uint4 (&c)[N], uint2 k) {
     constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < R; ++r) {
 #pragma unroll
         for (int i = 0; i < N; ++i) {
             const uint32_t hi0 = __umulhi(M0, c[i].x), lo0 = M0 * c[i].x;
@@ -99,7 +115,8 @@ __device__ __forceinline__ void philox_normal_row(uint64_t seed, uint64_t row, u
 #pragma unroll
     for (int i = 0; i < N; ++i)
         c[i] = make_uint4(col4_0 + i, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), (stream << 16) | (step & 0xFFFFu));
-    philox4x32_10_batch<N>(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    if (stream == STREAM_REVERSE) philox4x32_batch<N, PHILOX_ROUNDS_REVERSE>(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    else philox4x32_batch<N, PHILOX_ROUNDS>(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         box_muller(c[i].x, c[i].y, z[4 * i + 0], z[4 * i + 1]);
@@ -114,7 +131,8 @@ __device__ __forceinline__ void philox_normal_row_packed(uint64_t seed, uint64_t
 #pragma unroll
     for (int i = 0; i < N; ++i)
         c[i] = make_uint4(col8_0 + i, static_cast<uint32_t>(row), static_cast<uint32_t>(row >> 32), (stream << 16) | (step & 0xFFFFu));
-    philox4x32_10_batch<N>(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    if (stream == STREAM_REVERSE) philox4x32_batch<N, PHILOX_ROUNDS_REVERSE>(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
+    else philox4x32_batch<N, PHILOX_ROUNDS>(c, make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32)));
 #pragma unroll
     for (int i = 0; i < N; ++i) {
         box_muller_packed(c[i].x, z[8 * i + 0], z[8 * i + 1]);
@@ -128,12 +146,12 @@ __device__ __forceinline__ void philox_normal_row_packed(uint64_t seed, uint64_t
 __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t row, uint32_t col4, uint32_t stream, uint32_t step) {
     float4 z;
     if (stream_is_packed(stream)) {
-        const uint4 w = philox_words(seed, row, col4 >> 1, stream, step);
+        const uint4 w = philox_words_stream(seed, row, col4 >> 1, stream, step);
         box_muller_packed((col4 & 1u) ? w.z : w.x, z.x, z.y);
         box_muller_packed((col4 & 1u) ? w.w : w.y, z.z, z.w);
         return z;
     }
-    const uint4 w = philox_words(seed, row, col4, stream, step);
+    const uint4 w = philox_words_stream(seed, row, col4, stream, step);
     box_muller(w.x, w.y, z.x, z.y);
     box_muller(w.z, w.w, z.z, z.w);
     return z;

@@ -20,8 +20,15 @@ if os.environ.get("PROBE_TRACE"):
 fused = bool(lib.osteo_ddpm_step_is_fused(model._ctx))
 per_chunk = 11 if fused else 12
 buf = (C.c_float * 4096)()
-for t, dbg in [(500, int(d)) for d in os.environ.get('PROBE_DBG', '0').split(',')]:
+for t, dbg in [(500, d) for d in os.environ.get('PROBE_DBG', '0').split(',')]:
+    # an entry is 'dbg' or 'dbg:pf' (pf = L2 prefetch distance of the fused kernel, OSTEO_FUSED_PF)
+    dbg, _, pf = dbg.partition(':')
+    dbg = int(dbg)
     os.environ['OSTEO_DDPM_DBG'] = str(dbg)
+    if pf:
+        os.environ['OSTEO_FUSED_PF'] = pf
+    else:
+        os.environ.pop('OSTEO_FUSED_PF', None)
     acc = None
     for rep in range(4):
         n = lib.osteo_ddpm_profile_step(model._ctx, rows, t, 9, 0, buf, 4096, _lib.stream_handle())
@@ -32,4 +39,4 @@ for t, dbg in [(500, int(d)) for d in os.environ.get('PROBE_DBG', '0').split(','
     ddpm = sum(acc[per_chunk - 1::per_chunk])
     inp = 0.0 if fused else sum(acc[0::per_chunk])
     hid = sum(acc) - ddpm - inp
-    print(f"dbg={dbg:2d} t={t} fused={int(fused)}: step {sum(acc):.3f} ms  input_proj {inp:.3f}  hidden {hid:.3f}  output_proj+update {ddpm:.3f}", flush=True)
+    print(f"dbg={dbg:2d} pf={pf or '-'} t={t} fused={int(fused)}: step {sum(acc):.3f} ms  input_proj {inp:.3f}  hidden {hid:.3f}  output_proj+update {ddpm:.3f}", flush=True)

@@ -49,3 +49,26 @@ def test_packed_mapping_of_the_reverse_noise_stream():
     big = P.normals(3, np.arange(256, dtype=np.uint64), 4096, 0, 1)
     assert abs(big.mean()) < 4e-3 and abs(big.var() - 1.0) < 6e-3 and abs((big ** 4).mean() - 3.0) < 0.05
     assert np.abs(big).max() <= np.sqrt(2 * 20 * np.log(2)) + 1e-12
+
+
+def test_seven_round_stream_is_a_prefix_of_the_pinned_ten_round_function():
+    """The reverse-noise stream uses Philox4x32-7 (csrc/philox.cuh: philox_rounds). Random123's known answers pin the 10-round function;
+    rounds compose -- ten rounds == seven rounds followed by rounds 7..9 of the same key schedule -- so the 7-round words are pinned by
+    the same vectors, and they differ from the 10-round words."""
+    for ctr, key, out in KAT:
+        c, k = np.array(ctr, dtype=np.uint32), np.array(key, dtype=np.uint32)
+        seven = P.philox4x32(c, k, 7)
+        assert tuple(int(v) for v in P.philox4x32(seven, k, 3, first_round=7)) == out
+        assert tuple(int(v) for v in seven) != out
+    assert P.rounds_of(0) == 7 and all(P.rounds_of(s) == 10 for s in (1, 2, 3, 16))
+    w7 = P.words(5, np.arange(4, dtype=np.uint64), 3, 0, 17)
+    w10 = P.words(5, np.arange(4, dtype=np.uint64), 3, 1, 17)
+    assert not np.array_equal(w7, w10)
+    # avalanche sanity of the 7-round function: flipping one counter bit flips about half of the 128 output bits
+    base = np.array([[i, 7, 0, 99] for i in range(256)], dtype=np.uint32)
+    flipped = base.copy()
+    flipped[:, 0] ^= np.uint32(1)
+    k = np.array([123, 456], dtype=np.uint32)
+    d = P.philox4x32(base, k, 7) ^ P.philox4x32(flipped, k, 7)
+    bits = np.unpackbits(d.view(np.uint8)).reshape(256, 128).sum(1)
+    assert 56 < bits.mean() < 72
