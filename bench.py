@@ -715,7 +715,7 @@ def run_secondary_dp(model, dev, dist, rank, world, tf_peak):
     val = BiologicalValidator({"evaluation": {}}, precision="bf16")
     ms = timed(lambda: val.compute_mmd(X, Y), 1, 3)
     out["mmd_bf16_row_sharded"] = {"rows": n, "ms": ms, "kernel_pairs_per_s": 3.0 * n * n / (ms / 1e3), "value": val.compute_mmd(X, Y),
-                                   "note": "every rank holds X and Y and reduces its share of the Gram rows; full (not symmetric-half) Grams when sharded"}
+                                   "note": "every rank holds X and Y and reduces the Gram row blocks b % world == rank (block-cyclic), Kxx and Kyy as symmetric half-Grams"}
     # ---- correctness of every sharded path, outside any timed region, reported in the JSON line (secondary.checks)
     out["checks"] = multi_gpu_checks(model, dev, dist, rank, world, opt, X, Y)
     model.check_status()

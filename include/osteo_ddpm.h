@@ -238,6 +238,12 @@ int osteo_philox_words(uint32_t* out_dev, long long n, int ncol4, uint64_t seed,
 int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long long m, int d, float gamma,
                       const float* center_dev, long long row_begin, long long row_end,
                       long long yrow_begin, long long yrow_end, int precision, double* sums_dev, void* stream);
+/* Same reduction with the Gram rows sharded BLOCK-CYCLICALLY over `world` ranks (BASELINE.json configs[4]: Gram rows over 8 GPUs):
+ * this rank reduces the 128-row blocks b with b % world == rank of K(X,X), K(Y,Y) and K(X,Y), and K(X,X) / K(Y,Y) as symmetric
+ * half-Grams (tiles below the diagonal skipped, off-diagonal ones counted twice), so the triangular work is balanced over the ranks and
+ * the partial sums of all ranks add up (NCCL all-reduce of 3 fp64 on the caller's side) to the sums of the whole Grams. */
+int osteo_mmd_partial_cyclic(const float* x_dev, long long n, const float* y_dev, long long m, int d, float gamma,
+                             const float* center_dev, int rank, int world, int precision, double* sums_dev, void* stream);
 /* Column-gathered moment blocks for Pearson correlations: replaces DataFrame.corr / Series.corr
  * (utils/validation.py:152,156,206).  data_dev [n, ld] fp32; cols_dev [k] int32 column indices (k <= 32);
  * shift_dev [k] per-column shift (e.g. a first-row estimate; improves conditioning);

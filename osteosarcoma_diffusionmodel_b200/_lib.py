@@ -74,6 +74,7 @@ SIGNATURES = {
     "osteo_philox_normal": (_i, [_vp, _ll, _i, _u64, _ll, _u32, _u32, _vp]),
     "osteo_philox_words": (_i, [_vp, _ll, _i, _u64, _ll, _u32, _u32, _vp]),
     "osteo_mmd_partial": (_i, [_vp, _ll, _vp, _ll, _i, _f, _vp, _ll, _ll, _ll, _ll, _i, _vp, _vp]),
+    "osteo_mmd_partial_cyclic": (_i, [_vp, _ll, _vp, _ll, _i, _f, _vp, _i, _i, _i, _vp, _vp]),
     "osteo_corr_moments": (_i, [_vp, _ll, _i, _vp, _i, _vp, _ll, _ll, _vp, _vp]),
     "osteo_corr_moments_batched": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _ll, _ll, _vp, _vp]),
     "osteo_mixup_rows": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _f, _f, _vp, _vp]),

@@ -128,13 +128,18 @@ int osteo_philox_words(uint32_t* out_dev, long long n, int ncol4, uint64_t seed,
     return 0;
 }
 
-int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long long m, int d, float gamma, const float* center_dev, long long row_begin,
-                      long long row_end, long long yrow_begin, long long yrow_end, int precision, double* sums_dev, void* stream) {
+// Shared body of osteo_mmd_partial (contiguous Gram-row ranges) and osteo_mmd_partial_cyclic (cyc_world > 0: this rank owns the 128-row
+// blocks b with b % cyc_world == cyc_rank of every Gram, and K(X,X) / K(Y,Y) are reduced as symmetric half-Grams -- a row block's tiles
+// below the diagonal are skipped and the off-diagonal ones count twice, which is valid per row block, so the halves of all ranks add up
+// to the whole sum while the block-cyclic assignment keeps the triangular work balanced).
+static int mmd_partial_impl(const float* x_dev, long long n, const float* y_dev, long long m, int d, float gamma, const float* center_dev, long long row_begin,
+                            long long row_end, long long yrow_begin, long long yrow_end, int cyc_rank, int cyc_world, int precision, double* sums_dev, void* stream) {
     if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
     if (n <= 0 || m <= 0 || d <= 0) return fail("mmd_partial: bad shape");
     if (row_begin < 0 || row_end > n || row_begin > row_end || yrow_begin < 0 || yrow_end > m || yrow_begin > yrow_end) return fail("mmd_partial: bad row range");
     if ((row_begin < row_end && row_begin % BM != 0) || (yrow_begin < yrow_end && yrow_begin % BM != 0)) return fail("mmd_partial: shard starts must be multiples of %d", BM);
     if (n > 2000000000LL || m > 2000000000LL) return fail("mmd_partial: more than 2^31 rows");
+    if (cyc_world > 0 && (cyc_rank < 0 || cyc_rank >= cyc_world)) return fail("mmd_partial_cyclic: rank %d outside [0, %d)", cyc_rank, cyc_world);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int sms = current_sms();
     const bool x3 = precision == OSTEO_PREC_FP32X3;
@@ -189,6 +194,14 @@ int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long 
         p.N = static_cast<int>(cols);
         p.m_tile0 = static_cast<int>(rb / BM);
         p.m_tiles = static_cast<int>((re - rb + BM - 1) / BM);
+        p.m_stride = 1;
+        if (cyc_world > 0) {      // block-cyclic: row blocks cyc_rank, cyc_rank + cyc_world, ... of [rb, re) = [0, rows)
+            const int blocks = p.m_tiles;
+            p.m_tile0 = cyc_rank;
+            p.m_stride = cyc_world;
+            p.m_tiles = blocks > cyc_rank ? (blocks - cyc_rank + cyc_world - 1) / cyc_world : 0;
+            if (p.m_tiles == 0) return 0;
+        }
         p.n_tiles = static_cast<int>((cols + RB_BN - 1) / RB_BN);
         p.status = status.as<int>();
         p.norm_a = na;
@@ -198,15 +211,28 @@ int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long 
         p.acc = acc;
         return launch_rbf_gram(p, sms, s);
     };
-    // K(X,X) rows [row_begin,row_end): the symmetric half-Gram is only valid when this call owns every row
-    OSTEO_TRY(gram(tx, txb, nx.as<float>(), nx.as<float>(), row_begin, row_end, n, row_begin == 0 && row_end == n, sums_dev + 0));
-    OSTEO_TRY(gram(ty, tyb, ny.as<float>(), ny.as<float>(), yrow_begin, yrow_end, m, yrow_begin == 0 && yrow_end == m, sums_dev + 1));
+    // K(X,X) rows [row_begin,row_end): with contiguous ranges the symmetric half-Gram is used only when this call owns every row (a
+    // contiguous shard of a triangle is unbalanced); block-cyclic sharding always uses it
+    const bool cyc = cyc_world > 0;
+    OSTEO_TRY(gram(tx, txb, nx.as<float>(), nx.as<float>(), row_begin, row_end, n, cyc || (row_begin == 0 && row_end == n), sums_dev + 0));
+    OSTEO_TRY(gram(ty, tyb, ny.as<float>(), ny.as<float>(), yrow_begin, yrow_end, m, cyc || (yrow_begin == 0 && yrow_end == m), sums_dev + 1));
     OSTEO_TRY(gram(tx, tyb, nx.as<float>(), ny.as<float>(), row_begin, row_end, m, false, sums_dev + 2));
     int h = 0;
     OSTEO_CUDA(cudaMemcpyAsync(&h, status.p, sizeof(int), cudaMemcpyDeviceToHost, s));
     OSTEO_CUDA(cudaStreamSynchronize(s));
     if (h != 0) return fail("tcgen05 pipeline error %d in mmd_partial", h);
     return 0;
+}
+
+int osteo_mmd_partial(const float* x_dev, long long n, const float* y_dev, long long m, int d, float gamma, const float* center_dev, long long row_begin,
+                      long long row_end, long long yrow_begin, long long yrow_end, int precision, double* sums_dev, void* stream) {
+    return mmd_partial_impl(x_dev, n, y_dev, m, d, gamma, center_dev, row_begin, row_end, yrow_begin, yrow_end, 0, 0, precision, sums_dev, stream);
+}
+
+int osteo_mmd_partial_cyclic(const float* x_dev, long long n, const float* y_dev, long long m, int d, float gamma, const float* center_dev, int rank, int world,
+                             int precision, double* sums_dev, void* stream) {
+    if (world <= 0) return fail("mmd_partial_cyclic: world size must be positive");
+    return mmd_partial_impl(x_dev, n, y_dev, m, d, gamma, center_dev, 0, n, 0, m, rank, world, precision, sums_dev, stream);
 }
 
 int osteo_corr_moments(const float* data_dev, long long n, int ld, const int* cols_dev, int k, const float* shift_dev, long long row_begin, long long row_end,

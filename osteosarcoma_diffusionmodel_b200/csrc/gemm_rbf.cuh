@@ -28,7 +28,8 @@ struct RbfParams {
     CUtensorMap tma_a;        // rows of A: bf16 [rows_a, 2*kp] = [hi | lo], box 128 x 64
     CUtensorMap tma_b;        // rows of B: same layout, box 256 x 64
     int M, N;                 // valid rows of A (absolute) / valid rows of B
-    int m_tile0, m_tiles;     // 128-row blocks of A this call covers
+    int m_tile0, m_tiles;     // 128-row blocks of A this call covers: m_tile0 + i * m_stride, i < m_tiles
+    int m_stride;             // 1 = a contiguous range; world_size = block-cyclic sharding over ranks (balanced for the symmetric half-Gram)
     int n_tiles;              // 256-row blocks of B
     int nseg;
     KSeg seg[3];              // (a_col, b_col, nkb): hi.hi, and in split mode hi.lo, lo.hi
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rbf_gram_kernel(const __grid_co
 
     // tile -> (row block, 256-column block); a symmetric tile entirely below the diagonal is skipped by all three roles
     auto decode = [&](int tile, int& m_blk, int& n_blk) -> bool {
-        m_blk = p.m_tile0 + tile / p.n_tiles;
+        m_blk = p.m_tile0 + (tile / p.n_tiles) * p.m_stride;
         n_blk = tile % p.n_tiles;
         return !(p.symmetric && 2 * n_blk + 1 < m_blk);
     };

@@ -20,10 +20,12 @@ import torch
 
 
 def generate_to_shards(model, conditions: torch.Tensor, out_dir, shard_rows: int = 100_000, seed: int = 0, row_base: int = 0,
-                       pack_bits: bool = True) -> Dict:
+                       pack_bits: bool = True, on_shard=None) -> Dict:
     """Sample `conditions.shape[0]` patients shard by shard and write them under `out_dir`; returns the manifest.
     Rows keep their global Philox identity (row_base + index), so the files do not depend on the shard size or on how a cohort was
-    split over GPUs (each rank calls this with its own row range and directory)."""
+    split over GPUs (each rank calls this with its own row range and directory).
+    on_shard(entry, paths), if given, runs on the writer thread right after a shard's files are complete (e.g. to ship them off the box
+    and delete them: 10 M patients are 206 GB, more than a node's RAM-backed scratch)."""
     out = Path(out_dir)
     out.mkdir(parents=True, exist_ok=True)
     n = int(conditions.shape[0])
@@ -39,14 +41,19 @@ def generate_to_shards(model, conditions: torch.Tensor, out_dir, shard_rows: int
     def write(idx: int, host: Dict[str, torch.Tensor], ready) -> None:
         if ready is not None:
             ready.synchronize()
+        paths = []
         for k, t in host.items():
-            np.save(out / f"shard_{idx:05d}_{k}.npy", t.numpy())
+            paths.append(out / f"shard_{idx:05d}_{k}.npy")
+            np.save(paths[-1], t.numpy())
+        return paths
 
     def finish(p) -> None:
         """Wait for a shard's files; a failure in the writer thread (full disk, permissions, a CUDA error surfacing in
         ready.synchronize()) is re-raised HERE, and only a completely written shard enters the manifest."""
         fut, entry = p
-        fut.result()
+        paths = fut.result()
+        if on_shard is not None:
+            on_shard(entry, paths)
         manifest["shards"].append(entry)
 
     def staging(slot: int, key: str, like: torch.Tensor) -> torch.Tensor:

@@ -45,6 +45,14 @@ def _gram_partial_sums(X: torch.Tensor, Y: torch.Tensor, gamma: float, center: t
     return sums
 
 
+def _gram_partial_sums_cyclic(X: torch.Tensor, Y: torch.Tensor, gamma: float, center: torch.Tensor, rank: int, world: int, precision: int) -> torch.Tensor:
+    """This rank's share {sum Kxx, sum Kyy, sum Kxy} under block-cyclic Gram-row sharding (symmetric half-Grams for Kxx / Kyy)."""
+    sums = torch.zeros(3, dtype=torch.float64, device=X.device)
+    _lib.check(_lib.load().osteo_mmd_partial_cyclic(X.data_ptr(), X.shape[0], Y.data_ptr(), Y.shape[0], X.shape[1], float(gamma), center.data_ptr(),
+                                                    int(rank), int(world), precision, sums.data_ptr(), _lib.stream_handle()))
+    return sums
+
+
 def _moments(data: torch.Tensor, cols: Sequence[int], shift: torch.Tensor, rows) -> torch.Tensor:
     """fp64 [1 + k + k*k] = {count, sum (x - s), sum (x - s)(x - s)^T} of the gathered columns over rows [b, e)."""
     k = len(cols)
@@ -116,9 +124,11 @@ class BiologicalValidator:
         # RBF is translation invariant: centre on the pooled mean before the bf16 split (SURVEY.md §7 "MMD precision")
         center = ((X.sum(0, dtype=torch.float64) + Y.sum(0, dtype=torch.float64)) / (n + m)).float().contiguous()
         rank, ws = D.world()
-        rx = D.shard_rows(n, rank, ws, align=128)
-        ry = D.shard_rows(m, rank, ws, align=128)
-        sums = _gram_partial_sums(X, Y, gamma, center, rx, ry, _PRECISIONS[self.precision])
+        if ws > 1:
+            # Gram rows block-cyclic over the ranks, Kxx / Kyy as symmetric half-Grams: balanced, and 2/3 of the tiles of full Grams
+            sums = _gram_partial_sums_cyclic(X, Y, gamma, center, rank, ws, _PRECISIONS[self.precision])
+        else:
+            sums = _gram_partial_sums(X, Y, gamma, center, (0, n), (0, m), _PRECISIONS[self.precision])
         D.all_reduce_sum_(sums)
         sxx, syy, sxy = (float(v) for v in sums.cpu())
         mmd = sxx / (float(n) * n) + syy / (float(m) * m) - 2.0 * sxy / (float(n) * m)

@@ -110,6 +110,23 @@ def _worker_mmd(rank, ws, port, q):
         sxy = np.exp(-gamma * V.sqeuclidean(Xn[rx[0]:rx[1]], Yn)).sum() if rx[1] > rx[0] else 0.0
         return torch.tensor([sxx, syy, sxy], dtype=torch.float64)
 
+    def fake_partial_cyclic(Xt, Yt, gamma, center, rnk, world, precision):
+        """Host restatement of osteo_mmd_partial_cyclic: 128-row blocks b % world == rnk; Kxx / Kyy as symmetric half-Grams (128-column
+        halves below the diagonal skipped, above it counted twice)."""
+        Xn, Yn = Xt.numpy().astype(np.float64), Yt.numpy().astype(np.float64)
+
+        def half_gram(A):
+            nb, tot = -(-A.shape[0] // 128), 0.0
+            for b in range(rnk, nb, world):
+                K = np.exp(-gamma * V.sqeuclidean(A[128 * b:128 * b + 128], A))
+                for hb in range(nb):
+                    w = 2.0 if hb > b else (1.0 if hb == b else 0.0)
+                    tot += w * K[:, 128 * hb:128 * hb + 128].sum()
+            return tot
+
+        sxy = sum(np.exp(-gamma * V.sqeuclidean(Xn[128 * b:128 * b + 128], Yn)).sum() for b in range(rnk, -(-Xn.shape[0] // 128), world))
+        return torch.tensor([half_gram(Xn), half_gram(Yn), sxy], dtype=torch.float64)
+
     def fake_moments(data, cols, shift, rows):
         a = data.numpy().astype(np.float64)[rows[0]:rows[1]][:, list(cols)] - shift.numpy().astype(np.float64)
         k = len(cols)
@@ -129,6 +146,7 @@ def _worker_mmd(rank, ws, port, q):
         return torch.from_numpy(out)
 
     val._gram_partial_sums = fake_partial
+    val._gram_partial_sums_cyclic = fake_partial_cyclic
     val._moments = fake_moments
     val._moments_batched = fake_moments_batched
     v = val.BiologicalValidator({"evaluation": {}}, device="cpu")

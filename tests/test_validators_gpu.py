@@ -59,6 +59,25 @@ def test_mmd_row_sharding_sums_to_the_whole():
     assert torch.allclose(whole, parts, rtol=1e-6)
 
 
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_mmd_block_cyclic_symmetric_sharding_sums_to_the_whole(world):
+    """BASELINE.json configs[4] sharding, emulated on one GPU: rank r reduces the 128-row blocks b % world == r of each Gram, K(X,X) and
+    K(Y,Y) as symmetric half-Grams; the partial sums of all ranks equal the single-call sums (ragged last blocks, more ranks than blocks
+    of Y included)."""
+    from osteosarcoma_diffusionmodel_b200 import validation as val
+    rs = np.random.RandomState(17)
+    n, m, d = 1100, 300, 96
+    X = torch.from_numpy(rs.standard_normal((n, d)).astype(np.float32)).cuda()
+    Y = torch.from_numpy((rs.standard_normal((m, d)) + 0.2).astype(np.float32)).cuda()
+    center = ((X.sum(0) + Y.sum(0)) / (n + m)).contiguous()
+    for prec in (0, 1):
+        whole = val._gram_partial_sums(X, Y, 1.0 / d, center, (0, n), (0, m), prec)
+        parts = sum(val._gram_partial_sums_cyclic(X, Y, 1.0 / d, center, r, world, prec) for r in range(world))
+        assert torch.allclose(whole, parts, rtol=1e-6), (prec, whole, parts)
+    ref = np.array(V.rbf_sums(X.cpu().numpy().astype(np.float64), Y.cpu().numpy().astype(np.float64), 1.0 / d))
+    assert np.allclose(parts.cpu().numpy(), ref, rtol=2e-5)
+
+
 def test_pathway_coherence_matches_reference_golden(golden_dir):
     import pandas as pd
     g = np.load(golden_dir / "validators.npz")
