@@ -790,7 +790,7 @@ def multi_gpu_checks(model, dev, dist, rank, world, opt, X, Y):
     sharded = val._coherence_scores(cohort, members)
     packs_key = (str(cohort.device), tuple(tuple(c) for c in members))
     ci_t, gather_idx = val._index_cache[packs_key][0]
-    mom = Vm._moments_batched(cohort, ci_t, cohort[0, gather_idx].contiguous(), (0, cohort.shape[0])).cpu().numpy()
+    mom = Vm._moments_tiled(cohort, ci_t, (0, cohort.shape[0]), 15).cpu().numpy()      # the same kernel over ALL rows on this GPU alone
     whole = val._scores_from_moments(mom, members)
     checks["coherence_sharded_equals_unsharded"] = agree(max(abs(a - b) for a, b in zip(sharded, whole)) <= 1e-9)
     return checks

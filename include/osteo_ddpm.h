@@ -258,6 +258,16 @@ int osteo_corr_moments(const float* data_dev, long long n, int ld, const int* co
  * out_dev fp64 [n_sets, 1057] = per set {count, sum (x-s) [32], sum (x-s)(x-s)^T [32][32]} over rows [row_begin,row_end), overwritten. */
 int osteo_corr_moments_batched(const float* data_dev, long long n, int ld, int ncols, const int* cols_dev, int n_sets,
                                const float* shift_dev, long long row_begin, long long row_end, double* out_dev, void* stream);
+/* Same moment blocks (same output layout), register-tiled: the HBM-rate path behind validate_pathway_coherence
+ * (utils/validation.py:144-157). max_set_size = the largest number of columns in a set (<= 32; sets of <= 16 columns take the 10-block
+ * form, 25 sets per pass over the rows; larger ones the 36-block form, 7 sets per pass). shift_dev may be NULL: a column's shift is then
+ * its value in row 0 of data_dev (every rank holds the whole cohort). cols_dev int32 [n_sets, 32], -1 padded, valid entries first. */
+int osteo_corr_moments_tiled(const float* data_dev, long long n, int ld, int ncols, const int* cols_dev, int n_sets, int max_set_size,
+                             const float* shift_dev, long long row_begin, long long row_end, double* out_dev, void* stream);
+/* Per-set pathway-coherence score = mean over i < j of the Pearson correlation, float64, from moment blocks [n_sets, 1 + 32 + 32*32]
+ * (the upper-triangle mean of DataFrame.corr(), utils/validation.py:152-157) -> scores_dev fp64 [n_sets]. Moment blocks of several
+ * ranks are summed (all-reduced) BEFORE this call. */
+int osteo_coherence_finish(const double* moments_dev, const int* cols_dev, int n_sets, double* scores_dev, void* stream);
 
 /* ---- training ingress (utils/train.py:22-126, :204-227): one batch of a DEVICE-RESIDENT dataset, gathered by row index,
  * with MixupAugmentation fused in:  out[i, :] = lam * src[idx_a[i], :] + one_minus_lam * src[idx_b[i], :]   (src_dev [src_rows, d] fp32,

@@ -77,6 +77,8 @@ SIGNATURES = {
     "osteo_mmd_partial_cyclic": (_i, [_vp, _ll, _vp, _ll, _i, _f, _vp, _i, _i, _i, _vp, _vp]),
     "osteo_corr_moments": (_i, [_vp, _ll, _i, _vp, _i, _vp, _ll, _ll, _vp, _vp]),
     "osteo_corr_moments_batched": (_i, [_vp, _ll, _i, _i, _vp, _i, _vp, _ll, _ll, _vp, _vp]),
+    "osteo_corr_moments_tiled": (_i, [_vp, _ll, _i, _i, _vp, _i, _i, _vp, _ll, _ll, _vp, _vp]),
+    "osteo_coherence_finish": (_i, [_vp, _vp, _i, _vp, _vp]),
     "osteo_mixup_rows": (_i, [_vp, _ll, _i, _vp, _vp, _ll, _f, _f, _vp, _vp]),
     "osteo_corr_loss_finish": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "osteo_corr_loss_backward": (_i, [_vp, _ll, _i, _vp, _i, _vp, _vp, _vp, _vp]),

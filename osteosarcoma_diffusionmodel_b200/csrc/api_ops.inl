@@ -284,6 +284,40 @@ int osteo_corr_moments_batched(const float* data_dev, long long n, int ld, int n
     return 0;
 }
 
+int osteo_corr_moments_tiled(const float* data_dev, long long n, int ld, int ncols, const int* cols_dev, int n_sets, int max_set_size, const float* shift_dev,
+                             long long row_begin, long long row_end, double* out_dev, void* stream) {
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (n_sets <= 0 || n_sets > 32) return fail("corr_moments_tiled: %d column sets outside [1, 32]", n_sets);
+    if (max_set_size <= 0 || max_set_size > 32) return fail("corr_moments_tiled: sets of up to %d columns (limit 32)", max_set_size);
+    if (ncols <= 0 || ncols > ld) return fail("corr_moments_tiled: ncols=%d outside [1, ld=%d]", ncols, ld);
+    if (row_begin < 0 || row_end > n || row_begin > row_end) return fail("corr_moments_tiled: bad row range");
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    OSTEO_CUDA(cudaMemsetAsync(out_dev, 0, sizeof(double) * n_sets * CM_STRIDE, s));
+    if (row_end == row_begin) return 0;
+    // sets per launch: every (set, 4 x 4 block) pair needs a thread (51 sets of <= 16 columns, 14 of <= 32) and the launch has to fit its
+    // 226 KB of shared memory; more sets than that take several passes over the rows
+    const int W = max_set_size <= 16 ? 16 : 32;
+    int per = max_set_size <= 16 ? CT_THREADS / 10 : CT_THREADS / 36;
+    while (per > 1 && moments_tiled_smem(per, W, ncols, 2) > static_cast<size_t>(CT_SMEM_LIMIT)) --per;
+    for (int s0 = 0; s0 < n_sets; s0 += per) {
+        const int ns = n_sets - s0 < per ? n_sets - s0 : per;
+        const int* c0 = cols_dev + s0 * 32;
+        const float* sh0 = shift_dev ? shift_dev + s0 * 32 : nullptr;
+        double* o0 = out_dev + static_cast<size_t>(s0) * CM_STRIDE;
+        if (max_set_size <= 16) OSTEO_TRY(launch_moments_tiled<4>(data_dev, ld, ncols, c0, ns, sh0, row_begin, row_end, o0, current_sms(), s));
+        else OSTEO_TRY(launch_moments_tiled<8>(data_dev, ld, ncols, c0, ns, sh0, row_begin, row_end, o0, current_sms(), s));
+    }
+    return 0;
+}
+
+int osteo_coherence_finish(const double* moments_dev, const int* cols_dev, int n_sets, double* scores_dev, void* stream) {
+    if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");
+    if (n_sets <= 0) return fail("coherence_finish: no column sets");
+    coherence_finish_kernel<<<(n_sets * 32 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(moments_dev, cols_dev, n_sets, scores_dev);
+    OSTEO_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int osteo_corr_loss_finish(const double* moments_dev, const int* cols_dev, const float* shift_dev, const int* modes_dev, int n_sets, float* loss_out_dev,
                            float* coef_out_dev, void* stream) {
     if (osteo_device_count() <= 0) return fail("no CUDA device: this library has no CPU fallback");

@@ -167,6 +167,226 @@ __global__ void corr_moments_batched_kernel(const float* __restrict__ data, int 
     }
 }
 
+// Register-tiled form of the same reduction for sets of at most 16 columns (the Hallmark pathways of validate_pathway_coherence have
+// 11-19 member genes, 15 in the benchmark cohort): the warp <-> set kernel above spends 16 shuffles + 16 FMAs per row and set and is
+// shuffle-bound at 14 % of HBM. Here a set's 16 x 16 moment matrix is cut into 4 x 4 register blocks on or above the diagonal (10 per
+// set); thread <-> (set, block) reads two float4 per row from a compact copy of the gathered, shifted columns in shared memory and does
+// 16 FMAs -- no shuffles, and each loaded value feeds 4 FMAs. The block's threads form `groups` identical teams that take alternate
+// rows of a chunk; chunks of whole rows are staged with coalesced 128-bit loads, two CTAs per SM overlap one's staging with the
+// other's arithmetic. fp32 products over the rows of ONE chunk (shifted, O(1) values), fp64 across chunks; one shared-memory fp64
+// reduction per CTA, one set of global atomics per CTA.
+//   shift == nullptr: the shift of a column is its value in row 0 of `data` (every rank holds the whole cohort: all ranks agree).
+constexpr int CT_THREADS = 512;
+constexpr int CT_CHUNK = 32;                     // rows per chunk
+constexpr int CT_MAX_STAGES = 4;                 // row buffers (2..4, chosen by the launcher to fit shared memory): stages - 1 chunks in flight per SM
+constexpr int CT_SMEM_LIMIT = 226 * 1024;
+constexpr int CT_FLUSH = 4;                      // chunks between fp32 -> fp64 flushes of the register blocks
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// NB = 4 x 4 register blocks per dimension: 4 (sets of <= 16 columns, 10 blocks per set) or 8 (<= 32 columns, 36 blocks per set).
+// One CTA per SM; the rows of the next CT_STAGES - 1 chunks are in flight (cp.async, 16 bytes per request) while chunk c is gathered and
+// multiplied: with a single chunk ahead the loop ran at the latency of one 47 KB fetch per iteration (3.6 TB/s).
+template <int NB>
+__global__ void __launch_bounds__(CT_THREADS, 1) corr_moments_tiled_kernel(const float* __restrict__ data, int ld, int ncols, const int* __restrict__ cols, int P,
+                                                                            const float* __restrict__ shift, long long rb, long long re, int stages, double* __restrict__ out) {
+    constexpr int W = 4 * NB;                        // padded set width
+    constexpr int NBLK = NB * (NB + 1) / 2;          // blocks on or above the diagonal
+    constexpr int SET_STRIDE = 2 + W + W * W;        // shared-memory reduction block per set: count, s1[W], s2[W][W], one pad (keeps what follows 16-byte aligned)
+    extern __shared__ __align__(16) uint8_t ct_smem[];
+    double* red = reinterpret_cast<double*>(ct_smem);                                   // [P][SET_STRIDE]
+    float* rows_sm = reinterpret_cast<float*>(red + static_cast<size_t>(P) * SET_STRIDE);      // [stages][CT_CHUNK][ncols] (+ pad to 16 bytes per buffer)
+    const int buf_floats = (CT_CHUNK * ncols + 3) & ~3;
+    float* g_sm = rows_sm + stages * static_cast<size_t>(buf_floats);                     // [CT_CHUNK][P][W]
+    int* col_sm = reinterpret_cast<int*>(g_sm + static_cast<size_t>(CT_CHUNK) * P * W);   // [P][W]
+    float* shift_sm = reinterpret_cast<float*>(col_sm + P * W);                           // [P][W]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < P * SET_STRIDE; i += CT_THREADS) red[i] = 0.0;
+    for (int i = tid; i < P * W; i += CT_THREADS) {
+        const int c = cols[(i / W) * 32 + (i % W)];
+        col_sm[i] = c;
+        shift_sm[i] = c < 0 ? 0.0f : (shift ? shift[(i / W) * 32 + (i % W)] : data[c]);
+    }
+    const int items = P * NBLK;
+    const int groups = CT_THREADS / items;            // >= 1 (checked by the launcher)
+    const bool worker = tid < groups * items;
+    const int grp = tid / items, item = tid % items;
+    const int set = item / NBLK, blk = item % NBLK;
+    // block index -> (bi, bj), bi <= bj: row bi of the triangle holds NB - bi blocks
+    int bi = 0, rem = blk;
+    while (rem >= NB - bi) { rem -= NB - bi; ++bi; }
+    const int bj = bi + rem;
+    double d2[16], d1[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) d2[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d1[i] = 0.0;
+    // fp32 partial sums over up to CT_FLUSH chunks (<= 32 * CT_FLUSH / groups shifted O(1) products each), then one fp64 add: the
+    // fp32 -> fp64 conversions run on the 16-lane XU pipe
+    float a2[16], a1[4];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a2[i] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a1[i] = 0.0f;
+    int pending = 0;
+    long long count = 0;
+    const long long nchunks = (re - rb + CT_CHUNK - 1) / CT_CHUNK;
+    // gather roles (see the loop): SL slots per row, rlanes rows in flight
+    const int SL = P * W;
+    const int rlanes = CT_THREADS / SL > 0 ? CT_THREADS / SL : 1;
+    const int gslot = tid % SL, rlane = tid / SL;
+    __syncthreads();                                  // col_sm / shift_sm are complete
+    const int gcol = col_sm[gslot];
+    const float gshift = shift_sm[gslot];
+    // contiguous rows whose chunks start on 16-byte boundaries go through cp.async; anything else is copied synchronously
+    const bool async_ok = ld == ncols && ((reinterpret_cast<uintptr_t>(data + rb * ld) & 15) == 0) && ((static_cast<size_t>(CT_CHUNK) * ncols * 4) & 15) == 0;
+    auto stage = [&](int buf, long long c) {
+        if (c < nchunks) {
+            const long long r0 = rb + c * CT_CHUNK;
+            const int nr = static_cast<int>(re - r0 < CT_CHUNK ? re - r0 : CT_CHUNK);
+            float* dst = rows_sm + static_cast<size_t>(buf) * buf_floats;
+            if (async_ok) {
+                const float* src = data + r0 * ld;
+                const int n4 = (nr * ncols) >> 2;
+                for (int i = tid; i < n4; i += CT_THREADS) cp_async_16(dst + 4 * i, src + 4 * i);
+                for (int j = (n4 << 2) + tid; j < nr * ncols; j += CT_THREADS) dst[j] = src[j];
+            } else {
+                for (int i = tid; i < nr * ncols; i += CT_THREADS) dst[i] = data[(r0 + i / ncols) * ld + i % ncols];
+            }
+        }
+        cp_async_commit();                            // one group per call, empty past the end: the wait below counts groups
+    };
+    __syncthreads();
+    for (int st = 0; st < stages - 1; ++st) stage(st, blockIdx.x + static_cast<long long>(st) * gridDim.x);
+    int buf = 0;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x, buf = buf + 1 == stages ? 0 : buf + 1) {
+        const long long r0 = rb + c * CT_CHUNK;
+        const int nr = static_cast<int>(re - r0 < CT_CHUNK ? re - r0 : CT_CHUNK);
+        const float* cur = rows_sm + static_cast<size_t>(buf) * buf_floats;
+        // the buffer consumed in the previous iteration was released by the barrier that ended it: refill it with chunk c + (STAGES - 1) grid
+        stage((buf + stages - 1) % stages, c + static_cast<long long>(stages - 1) * gridDim.x);
+        // all but the newest stages - 1 groups have landed: chunk c is in `cur`
+        if (stages == 4) cp_async_wait<3>();
+        else if (stages == 3) cp_async_wait<2>();
+        else cp_async_wait<1>();
+        __syncthreads();
+        // ---- gather + shift into the compact set-major copy: thread <-> one (set, slot) of `rlanes` interleaved rows, its column index and
+        // shift in registers (a flat index over rows x slots costs two integer divisions per element)
+        if (tid < rlanes * SL) {
+            for (int r = rlane; r < nr; r += rlanes) g_sm[r * SL + gslot] = gcol < 0 ? 0.0f : cur[r * ncols + gcol] - gshift;
+        }
+        __syncthreads();
+        // ---- 4 x 4 register blocks
+        if (worker) {
+            for (int r = grp; r < nr; r += groups) {
+                const float4 a = *reinterpret_cast<const float4*>(g_sm + (r * P + set) * W + 4 * bi);
+                const float4 b = *reinterpret_cast<const float4*>(g_sm + (r * P + set) * W + 4 * bj);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    a1[i] += av[i];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) a2[4 * i + j] = fmaf(av[i], bv[j], a2[4 * i + j]);
+                }
+                if (blk == 0) ++count;
+            }
+            if (++pending == CT_FLUSH) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { d2[i] += static_cast<double>(a2[i]); a2[i] = 0.0f; }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { d1[i] += static_cast<double>(a1[i]); a1[i] = 0.0f; }
+                pending = 0;
+            }
+        }
+        // g_sm (and, after the next iteration's wait, this row buffer) is reused: every worker must be done with this chunk
+        __syncthreads();
+    }
+    if (worker) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) d2[i] += static_cast<double>(a2[i]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d1[i] += static_cast<double>(a1[i]);
+        double* rs = red + static_cast<size_t>(set) * SET_STRIDE;
+        if (blk == 0 && count) atomicAdd(rs, static_cast<double>(count));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (bi == bj) atomicAdd(rs + 1 + 4 * bi + i, d1[i]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) atomicAdd(rs + 1 + W + (4 * bi + i) * W + 4 * bj + j, d2[4 * i + j]);
+        }
+    }
+    __syncthreads();
+    // ---- one set of global atomics per CTA, into the [count, s1[32], s2[32][32]] layout of the batched kernel (both triangles)
+    for (int i = tid; i < P * SET_STRIDE; i += CT_THREADS) {
+        const int st = i / SET_STRIDE, e = i % SET_STRIDE;
+        const double v = red[i];
+        if (v == 0.0) continue;
+        double* o = out + static_cast<size_t>(st) * CM_STRIDE;
+        if (e == 0) atomicAdd(o, v);
+        else if (e < 1 + W) atomicAdd(o + 1 + (e - 1), v);
+        else if (e < 1 + W + W * W) {
+            const int a = (e - 1 - W) / W, b = (e - 1 - W) % W;
+            if ((a >> 2) > (b >> 2)) continue;            // blocks below the diagonal were never accumulated
+            atomicAdd(o + 33 + a * 32 + b, v);
+            if ((a >> 2) != (b >> 2)) atomicAdd(o + 33 + b * 32 + a, v);      // mirror an off-diagonal block
+        }
+    }
+}
+
+// Shared-memory bytes of one launch with n_sets sets of padded width W over `ncols`-column rows.
+inline size_t moments_tiled_smem(int n_sets, int W, int ncols, int stages) {
+    const size_t buf_floats = (static_cast<size_t>(CT_CHUNK) * ncols + 3) & ~static_cast<size_t>(3);
+    return static_cast<size_t>(n_sets) * (2 + W + W * W) * sizeof(double) + static_cast<size_t>(stages) * buf_floats * 4 + static_cast<size_t>(CT_CHUNK) * n_sets * W * 4 +
+           static_cast<size_t>(n_sets) * W * 8;
+}
+
+template <int NB>
+inline int launch_moments_tiled(const float* data_dev, int ld, int ncols, const int* cols_dev, int n_sets, const float* shift_dev, long long row_begin, long long row_end,
+                                double* out_dev, int sms, cudaStream_t s) {
+    int stages = CT_MAX_STAGES;
+    while (stages > 2 && moments_tiled_smem(n_sets, 4 * NB, ncols, stages) > static_cast<size_t>(CT_SMEM_LIMIT)) --stages;
+    const size_t smem = moments_tiled_smem(n_sets, 4 * NB, ncols, stages);
+    if (smem > CT_SMEM_LIMIT) return fail("corr_moments_tiled: %d columns x %d sets need %zu bytes of shared memory per block (limit %d)", ncols, n_sets, smem, CT_SMEM_LIMIT);
+    static bool configured = false;
+    if (!configured) {
+        OSTEO_CUDA(cudaFuncSetAttribute(corr_moments_tiled_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_LIMIT));
+        configured = true;
+    }
+    const long long nchunks = (row_end - row_begin + CT_CHUNK - 1) / CT_CHUNK;
+    const long long blocks = nchunks < sms ? nchunks : sms;
+    corr_moments_tiled_kernel<NB><<<static_cast<unsigned>(blocks), CT_THREADS, smem, s>>>(data_dev, ld, ncols, cols_dev, n_sets, shift_dev, row_begin, row_end, stages, out_dev);
+    OSTEO_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Per-set coherence score from the (all-reduced) moment blocks: mean over i < j of the Pearson correlation, float64, the same algebra as
+// DataFrame.corr() followed by the upper-triangle mean (utils/validation.py:152-157): cov = S2 - S1 S1^T / n, R = cov / (sd sd^T),
+// IEEE semantics for constant columns (0 / 0 -> NaN, as pandas reports). One warp per set.
+__global__ void coherence_finish_kernel(const double* __restrict__ mom, const int* __restrict__ cols, int n_sets, double* __restrict__ scores) {
+    const int lane = threadIdx.x & 31;
+    const int set = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (set >= n_sets) return;
+    const double* m = mom + static_cast<size_t>(set) * CM_STRIDE;
+    const bool has = cols[set * 32 + lane] >= 0;
+    const int k = __popc(__ballot_sync(0xffffffffu, has));
+    const double n = m[0];
+    const double s1 = has ? m[1 + lane] : 0.0;
+    const double var = has ? m[33 + lane * 32 + lane] - s1 * s1 / n : 1.0;
+    const double sd = sqrt(var);
+    double sum = 0.0;
+    for (int j = 0; j < k; ++j) {
+        const double s1j = __shfl_sync(0xffffffffu, s1, j), sdj = __shfl_sync(0xffffffffu, sd, j);
+        if (has && j > lane) sum += (m[33 + lane * 32 + j] - s1 * s1j / n) / (sd * sdj);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) scores[set] = sum / (0.5 * k * (k - 1));
+}
+
 // ---------------------------------------------------------------------------------------------------------------------------
 // Differentiable forms of the two correlation validators (the reference only has stubs, models/cvae.py:262-302;
 // the forward values are tied to validate_pathway_coherence / validate_mutation_expression_correlation, utils/validation.py:125-223).

@@ -75,6 +75,24 @@ def _moments_batched(data: torch.Tensor, ci_t: torch.Tensor, shift: torch.Tensor
     return out
 
 
+def _moments_tiled(data: torch.Tensor, ci_t: torch.Tensor, rows, max_set_size: int = 32, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp64 [n_sets, _CM_STRIDE] like _moments_batched by the register-tiled kernel (osteo_corr_moments_tiled); the shift of a column is
+    its value in row 0 of `data` (taken inside the kernel). max_set_size: the largest set (<= 16 selects the 10-block form).
+    `out`: an existing contiguous [n_sets, _CM_STRIDE] fp64 view to fill (no allocation, no later concatenation)."""
+    if out is None:
+        out = torch.empty((ci_t.shape[0], _CM_STRIDE), dtype=torch.float64, device=data.device)
+    _lib.check(_lib.load().osteo_corr_moments_tiled(data.data_ptr(), data.shape[0], data.stride(0), data.shape[1], ci_t.data_ptr(), ci_t.shape[0],
+                                                    int(max_set_size), None, rows[0], rows[1], out.data_ptr(), _lib.stream_handle()))
+    return out
+
+
+def _coherence_finish(mom: torch.Tensor, ci_t: torch.Tensor) -> torch.Tensor:
+    """fp64 [n_sets] device tensor: mean upper-triangle Pearson correlation per set from (all-reduced) moment blocks."""
+    scores = torch.empty(mom.shape[0], dtype=torch.float64, device=mom.device)
+    _lib.check(_lib.load().osteo_coherence_finish(mom.data_ptr(), ci_t.data_ptr(), mom.shape[0], scores.data_ptr(), _lib.stream_handle()))
+    return scores
+
+
 def _corr_from_moments(mom: np.ndarray, k: int) -> np.ndarray:
     """Pearson correlation matrix from shifted moments (float64, host; k <= 32)."""
     n = mom[0]
@@ -135,15 +153,11 @@ class BiologicalValidator:
         return float(np.sqrt(max(mmd, 0.0)))
 
     # ------------------------------------------------------------------ utils/validation.py:125-175
-    def _coherence_moments(self, data: torch.Tensor, member_cols: List[List[int]]) -> torch.Tensor:
-        """Device tensor [n_sets, _CM_STRIDE] of all-reduced moment blocks: all pathways in one pass over the cohort
-        (osteo_corr_moments_batched: warp p owns pathway p, whole rows are streamed through shared memory). Nothing here waits for the
-        device: the index tensors are cached per (device, column sets) and the result stays in HBM."""
-        rank, ws = D.world()
-        rows = D.shard_rows(data.shape[0], rank, ws)
+    def _index_packs(self, device, member_cols: List[List[int]]):
+        """Cached device index tensors of the column sets: [(int32 [<= 32 sets, 32], -1 padded), ...]."""
         if any(len(c) > 32 for c in member_cols):
             raise ValueError("a pathway with more than 32 member genes is not supported by the moment kernel")
-        key = (str(data.device), tuple(tuple(c) for c in member_cols))
+        key = (str(device), tuple(tuple(c) for c in member_cols))
         packs = self._index_cache.get(key)
         if packs is None:
             packs = []
@@ -152,18 +166,29 @@ class BiologicalValidator:
                 ci = np.full((len(sets), 32), -1, dtype=np.int32)
                 for i, cols in enumerate(sets):
                     ci[i, :len(cols)] = cols
-                ci_t = torch.from_numpy(ci).to(data.device)
+                ci_t = torch.from_numpy(ci).to(device)
                 packs.append((ci_t, ci_t.clamp(min=0).long()))
             if len(self._index_cache) > 16:
                 self._index_cache.clear()
             self._index_cache[key] = packs
-        parts = []
-        for ci_t, gather_idx in packs:
-            # any value near the column mean conditions the fp64 moments: the first row's (every rank holds the whole cohort and reduces its
-            # share of the rows, so all ranks pick the same shift)
-            shift = data[0, gather_idx].contiguous()
-            parts.append(_moments_batched(data, ci_t, shift, rows))
-        return D.all_reduce_sum_(torch.cat(parts))
+        return packs
+
+    def _coherence_moments(self, data: torch.Tensor, member_cols: List[List[int]], out: Optional[torch.Tensor] = None, reduce: bool = True) -> torch.Tensor:
+        """Device tensor [n_sets, _CM_STRIDE] of moment blocks (all-reduced over the ranks unless reduce=False): all pathways in one pass
+        over the cohort by the register-tiled kernel (osteo_corr_moments_tiled). Nothing here waits for the device: the index tensors
+        are cached per (device, column sets) and the result stays in HBM. The shift that conditions the fp64 moments is row 0 of the
+        cohort, read inside the kernel (every rank holds the whole cohort and reduces its share of the rows: same shift everywhere)."""
+        rank, ws = D.world()
+        rows = D.shard_rows(data.shape[0], rank, ws)
+        packs = self._index_packs(data.device, member_cols)
+        kmax = max(len(c) for c in member_cols)
+        if out is None:
+            out = torch.empty((len(member_cols), _CM_STRIDE), dtype=torch.float64, device=data.device)
+        s0 = 0
+        for ci_t, _ in packs:
+            _moments_tiled(data, ci_t, rows, kmax, out=out[s0:s0 + ci_t.shape[0]])
+            s0 += ci_t.shape[0]
+        return D.all_reduce_sum_(out) if reduce else out
 
     @staticmethod
     def _scores_from_moments(flat: np.ndarray, member_cols: List[List[int]]) -> List[float]:
@@ -179,12 +204,25 @@ class BiologicalValidator:
     def _coherence_scores(self, data: torch.Tensor, member_cols: List[List[int]]) -> List[float]:
         return self._scores_from_moments(self._coherence_moments(data, member_cols).cpu().numpy(), member_cols)
 
+    def _index_tensor(self, device, member_cols: List[List[int]]) -> torch.Tensor:
+        packs = self._index_packs(device, member_cols)
+        return packs[0][0] if len(packs) == 1 else torch.cat([ci for ci, _ in packs])
+
     def _coherence_scores_pair(self, real: torch.Tensor, members_real, synthetic: torch.Tensor, members_syn):
-        """Both cohorts enqueued back to back, ONE device-to-host copy for the pair."""
-        mr = self._coherence_moments(real, members_real)
-        ms = self._coherence_moments(synthetic, members_syn)
-        flat = torch.cat([mr, ms]).cpu().numpy()
-        return self._scores_from_moments(flat[:len(members_real)], members_real), self._scores_from_moments(flat[len(members_real):], members_syn)
+        """Both cohorts enqueued back to back into ONE moment buffer -- two moment kernels, one all-reduce (if sharded), one Pearson
+        finish on the device -- and ONE device-to-host copy of the float64 scores of the pair."""
+        nr, ns = len(members_real), len(members_syn)
+        key = ("pair", str(real.device), tuple(tuple(c) for c in members_real), tuple(tuple(c) for c in members_syn))
+        ci_all = self._index_cache.get(key)
+        if ci_all is None:
+            ci_all = torch.cat([self._index_tensor(real.device, members_real), self._index_tensor(synthetic.device, members_syn)])
+            self._index_cache[key] = ci_all
+        mom = torch.empty((nr + ns, _CM_STRIDE), dtype=torch.float64, device=real.device)
+        self._coherence_moments(real, members_real, out=mom[:nr], reduce=False)
+        self._coherence_moments(synthetic, members_syn, out=mom[nr:], reduce=False)
+        D.all_reduce_sum_(mom)
+        flat = _coherence_finish(mom, ci_all).cpu().numpy()
+        return [float(v) for v in flat[:nr]], [float(v) for v in flat[nr:]]
 
     @_on_validator_device
     def validate_pathway_coherence(self, real_data, synthetic_data, pathway_gene_matrix) -> Dict[str, float]:

@@ -145,10 +145,27 @@ def _worker_mmd(rank, ws, port, q):
             out[p, 33:] = s2.reshape(-1)
         return torch.from_numpy(out)
 
+    def fake_moments_tiled(data, ci_t, rows, max_set_size=32, out=None):
+        res = fake_moments_batched(data, ci_t, data[0, ci_t.clamp(min=0).long()], rows)
+        if out is None:
+            return res
+        out.copy_(res)
+        return out
+
+    def fake_finish(mom, ci_t):
+        out = []
+        for blk, ci in zip(mom.numpy(), ci_t.numpy()):
+            k = int((ci >= 0).sum())
+            m = np.concatenate([blk[:1], blk[1:1 + k], blk[33:].reshape(32, 32)[:k, :k].reshape(-1)])
+            out.append(val._corr_from_moments(m, k)[np.triu_indices(k, k=1)].mean())
+        return torch.tensor(out, dtype=torch.float64)
+
     val._gram_partial_sums = fake_partial
     val._gram_partial_sums_cyclic = fake_partial_cyclic
     val._moments = fake_moments
     val._moments_batched = fake_moments_batched
+    val._moments_tiled = fake_moments_tiled
+    val._coherence_finish = fake_finish
     v = val.BiologicalValidator({"evaluation": {}}, device="cpu")
     v._require_cuda = lambda: None
     got = v.compute_mmd(X, Y)

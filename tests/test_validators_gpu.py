@@ -162,3 +162,40 @@ def test_batched_moments_match_numpy_and_the_single_set_kernel(n, ncols, pitch):
             corr = val._corr_from_moments(mom, k)
             ref = np.corrcoef(full[:, cols].astype(np.float64), rowvar=False)
             assert np.abs(corr - ref).max() < 1e-6
+
+
+@pytest.mark.parametrize("n,ncols,pitch,sizes", [(1000, 64, 64, [3, 15, 16, 1, 7]), (50_001, 371, 371, [15] * 10), (4099, 371, 371, [11, 19, 17, 16, 32, 3, 12]),
+                                                 (777, 40, 56, [9, 32]), (31, 20, 20, [5, 17])])
+def test_tiled_moments_and_device_finish_match_numpy(n, ncols, pitch, sizes):
+    """osteo_corr_moments_tiled (4 x 4 register blocks; the 10-block form for sets <= 16 columns, the 36-block form up to 32, several
+    passes when the sets do not fit one launch) + osteo_coherence_finish against float64 numpy: moment blocks, Pearson matrices and the
+    per-set coherence score; ragged last chunk, row pitch > columns, a row sub-range."""
+    from osteosarcoma_diffusionmodel_b200 import validation as val
+    rs = np.random.RandomState(n + ncols)
+    base = rs.standard_normal((n, 4)) @ rs.standard_normal((4, ncols)) * 0.5 + rs.standard_normal((n, ncols)) + 3.0
+    buf = np.zeros((n, pitch), dtype=np.float32)
+    buf[:, :ncols] = base.astype(np.float32)
+    t = torch.from_numpy(buf).cuda()[:, :ncols]
+    sets = [sorted(rs.choice(ncols, k, replace=False).tolist()) for k in sizes]
+    ci = np.full((len(sets), 32), -1, dtype=np.int32)
+    for i, c in enumerate(sets):
+        ci[i, :len(c)] = c
+    ci_t = torch.from_numpy(ci).cuda()
+    rb, re = (0, n) if n < 1000 else (7, n - 5)
+    mom = val._moments_tiled(t, ci_t, (rb, re), max(sizes))
+    scores = val._coherence_finish(mom, ci_t).cpu().numpy()
+    mom = mom.cpu().numpy()
+    x64 = buf[:, :ncols].astype(np.float64)
+    for i, c in enumerate(sets):
+        k = len(c)
+        g = x64[rb:re][:, c] - x64[0, c]
+        assert mom[i, 0] == re - rb
+        assert np.allclose(mom[i, 1:1 + k], g.sum(0), rtol=1e-6, atol=1e-3)
+        s2 = mom[i, 33:].reshape(32, 32)[:k, :k]
+        assert np.allclose(s2, g.T @ g, rtol=2e-6, atol=1e-3)
+        assert np.array_equal(s2, s2.T)
+        if k >= 2:
+            ref = np.corrcoef(x64[rb:re][:, c], rowvar=False)
+            got = val._corr_from_moments(np.concatenate([mom[i, :1], mom[i, 1:1 + k], s2.reshape(-1)]), k)
+            assert np.abs(got - ref).max() < 1e-6
+            assert abs(scores[i] - ref[np.triu_indices(k, k=1)].mean()) < 1e-6
