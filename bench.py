@@ -707,6 +707,14 @@ def run_secondary_dp(model, dev, dist, rank, world, tf_peak):
     ms = timed(lambda: Dm.dp_train_step(model, opt, x0, cond), 4, 10)
     out["dp_train_step"] = {"batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms, "samples_per_s": B * world / (ms / 1e3),
                             "allreduce": "one NCCL all-reduce of the flat fp32 gradient buffer per step, after the graph-replayed backward"}
+    try:      # the same step with the library's fused clip + AdamW (two launches; the torch optimiser's host enqueue bounds the step above)
+        from osteosarcoma_diffusionmodel_b200.optim import FusedAdamW
+        fopt = FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, max_grad_norm=1.0)
+        ms_f = timed(lambda: Dm.dp_train_step(model, fopt, x0, cond), 4, 10)
+        out["dp_train_step"]["fused_optimizer_ms_per_step"] = ms_f
+        del fopt
+    except Exception as e:
+        out["dp_train_step"]["fused_optimizer_error"] = repr(e)
     model.eval()
     n = 32768
     g = torch.Generator(device=dev).manual_seed(1)
@@ -727,7 +735,7 @@ def multi_gpu_checks(model, dev, dist, rank, world, opt, X, Y):
       sampling_shards_equal_single_gpu   rows sampled by rank r inside its shard == the same GLOBAL rows sampled by rank 0 alone (bit-equal)
       dp_replicas_bit_identical          parameters (and AdamW moments) identical on all ranks after data-parallel optimiser steps
       mmd_sharded_equals_unsharded       row-sharded RBF-MMD == the single-GPU reduction of the same X, Y (relative 1e-6)
-      coherence_sharded_equals_unsharded row-sharded pathway-coherence scores == the single-GPU ones (absolute 1e-9)"""
+      coherence_sharded_equals_unsharded row-sharded pathway-coherence scores == the single-GPU ones (absolute 1e-7)"""
     import torch
     from osteosarcoma_diffusionmodel_b200 import distributed as Dm
     from osteosarcoma_diffusionmodel_b200 import synthetic as synth
@@ -792,7 +800,11 @@ def multi_gpu_checks(model, dev, dist, rank, world, opt, X, Y):
     ci_t, gather_idx = val._index_cache[packs_key][0]
     mom = Vm._moments_tiled(cohort, ci_t, (0, cohort.shape[0]), 15).cpu().numpy()      # the same kernel over ALL rows on this GPU alone
     whole = val._scores_from_moments(mom, members)
-    checks["coherence_sharded_equals_unsharded"] = agree(max(abs(a - b) for a, b in zip(sharded, whole)) <= 1e-9)
+    # fp32 partial sums over <= 4 chunks of 32 rows, fp64 across chunks: a different row partition changes the fp32 roundings -- scores
+    # agree to ~1e-8; the validators' stated tolerance is 1e-6 absolute (tests/test_validators_gpu.py)
+    diff = max(abs(a - b) for a, b in zip(sharded, whole))
+    checks["coherence_sharded_equals_unsharded"] = agree(diff <= 1e-7)
+    checks["coherence_max_abs_diff"] = diff
     return checks
 
 

@@ -20,6 +20,7 @@ constexpr int RB_STAGES = 4;
 constexpr int RB_B_BYTES = RB_BN * BK * 2;                       // 32 KB
 constexpr int RB_STAGE_BYTES = A_TILE_BYTES + RB_B_BYTES;        // 48 KB
 constexpr int RB_ACC = 2;
+constexpr int RB_GROUP_M = 16;                                   // row blocks per tile group (L2 reuse of the B operand, see decode)
 constexpr int RB_EPI_WARPS = 8;
 constexpr int RB_THREADS = 32 * (RB_EPI_WARPS + 4);
 constexpr int RB_SMEM_BYTES = RB_STAGES * RB_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -81,9 +82,19 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rbf_gram_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_slot;
 
     // tile -> (row block, 256-column block); a symmetric tile entirely below the diagonal is skipped by all three roles
+    // Tiles are walked in groups of RB_GROUP_M row blocks: consecutive tile indices (= the CTAs of one wave) go DOWN the group's row
+    // blocks for one 256-column block, then to the next column block. A wave of 148 CTAs then shares 16 A row blocks and ~9 B column
+    // blocks (45 MB of operands for 148 tiles at K = 5184) instead of one A row block and 148 different B blocks (390 MB): at 1 M x 1 M
+    // the B operand (10 GB) is far beyond the L2 and the row-major walk was HBM-bound at 49 % of the tensor peak
+    // (profiles/r2_config4_n8.json).
     auto decode = [&](int tile, int& m_blk, int& n_blk) -> bool {
-        m_blk = p.m_tile0 + (tile / p.n_tiles) * p.m_stride;
-        n_blk = tile % p.n_tiles;
+        const int per_group = RB_GROUP_M * p.n_tiles;
+        const int group = tile / per_group, in_group = tile - group * per_group;
+        const int first = group * RB_GROUP_M;
+        const int rows_here = p.m_tiles - first < RB_GROUP_M ? p.m_tiles - first : RB_GROUP_M;
+        const int mi = first + in_group % rows_here;
+        n_blk = in_group / rows_here;
+        m_blk = p.m_tile0 + mi * p.m_stride;
         return !(p.symmetric && 2 * n_blk + 1 < m_blk);
     };
 

@@ -102,7 +102,9 @@ def dp_train_step(model, optimizer, x0: torch.Tensor, conditions: torch.Tensor, 
             model._flat_allreduce = False
     if not flat:
         allreduce_gradients(model.parameters(), bucket_bytes)
-    torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
+    # optim.FusedAdamW(max_grad_norm=...) clips inside its own two-launch step (global norm on the device, after the reduce): no torch clip then
+    if getattr(optimizer, "defaults", {}).get("max_grad_norm") is None:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_grad_norm)
     optimizer.step()
     return loss.detach()
 
