@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (warp_phys == 0) WS_TRACE(2, it, 2);
-            Epilogue<EPI_GN_SILU>::template run32<GW>(p, row, col, v, gn_par, gn_xch, q, part, lane);
+            if (!(p.dbg & 64)) Epilogue<EPI_GN_SILU>::template run32<GW>(p, row, col, v, gn_par, gn_xch, q, part, lane);      // bit 6: timing probe, no epilogue
             if (warp_phys == 0) WS_TRACE(2, it, 3);
         }
         if (!ok && lane == 0) atomicExch(p.status, ERR_EPI_TIMEOUT);

@@ -11,6 +11,7 @@
 #include "fused_step.cuh"
 #include "gemm_host.cuh"
 #include "gemm_ws.cuh"
+#include "gemm_ws2.cuh"
 #include "gemm_rbf.cuh"
 #include "train_kernels.cuh"
 #include "validators.cuh"
@@ -204,6 +205,7 @@ struct osteo_ddpm_ctx {
     CUtensorMap wout_tmap64, win_tmap;   // W_out as [64 x 64] boxes, W_in as [h0 x 64] boxes
     int fused_enable = 1;
     int ws_enable = getenv("OSTEO_DDPM_NO_WS") ? 0 : 1;
+    int ws2_enable = getenv("OSTEO_WS2") ? atoi(getenv("OSTEO_WS2")) : 0;      // CTA-pair block GEMMs (gemm_ws2.cuh): opt-in until measured
     DevBuf fused_trace;
     bool x_c8 = false;                   // layout the state was loaded in: c8 (fused path) or 32-column boxes (TMA-staged path)
     bool shadow_valid = false;           // xb == bf16(x)? (the fused step does not maintain the shadow)
@@ -377,6 +379,12 @@ static int launch_half(osteo_ddpm_ctx* c, int hi, long long row0, long long row1
         p.rstd_out = c->train.rstd[hi]->as<float>();
     }
     // bf16 mode, K <= 512: weight-stationary kernel (the column slice of W stays in shared memory, only A streams: half the L2 traffic)
+    if (const char* e = getenv("OSTEO_DDPM_DBG")) p.dbg = atoi(e);
+    // ... as a CTA pair (cta_group::2, M = 256 x N = 256) where the layer is a whole number of 256-column slices: half the per-SM operand traffic
+    if (c->ws2_enable && c->ws_enable && gemm_ws2_eligible(p)) {
+        const int rc = launch_gemm_ws2(hb.gw, p, c->sms, s);
+        if (rc != -2) return after_launch(c, rc, s);
+    }
     if (c->ws_enable && gemm_ws_eligible(p)) {
         const int rc = launch_gemm_ws(hb.gw, p, c->sms, s);
         if (rc != -2) return after_launch(c, rc, s);
