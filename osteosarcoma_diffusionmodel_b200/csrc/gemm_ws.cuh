@@ -117,6 +117,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
                     const CUtensorMap* ta = &p.tma_a[sg.a_sel];
                     for (int kb = 0; kb < sg.nkb; ++kb) {
                         if (!mbar_wait_relaxed(&empty_bar[stage], phase ^ 1u)) { ok = false; break; }
+                        if (p.dbg & 128) {      // timing probe: no A traffic, no MMAs (the epilogue alone; results are wrong)
+                            mbar_arrive(&full_bar[stage]);
+                            if (++stage == stages) { stage = 0; phase ^= 1u; }
+                            continue;
+                        }
                         mbar_arrive_expect_tx(&full_bar[stage], A_TILE_BYTES);
                         if constexpr (CS > 1) {
                             if (gstage % CS == crank) tma_load_2d_multicast(ta, s_a + stage * A_TILE_BYTES, &full_bar[stage], sg.a_col + kb * BK, m_blk * BM, CMASK);
@@ -155,7 +160,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
                     const uint64_t adesc = adesc0 + static_cast<uint64_t>((stage * A_TILE_BYTES) >> 4);
                     const uint64_t bdesc = wdesc0 + static_cast<uint64_t>((idx * B_TILE_BYTES) >> 4);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (idx | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; ++k)
+                        if (!(p.dbg & 128)) umma_bf16(d_tmem, adesc + 2u * k, bdesc + 2u * k, idesc, (idx | k) != 0 ? 1u : 0u);
                     if constexpr (CS > 1) umma_commit_multicast(&empty_bar[stage], CMASK);
                     else umma_commit(&empty_bar[stage]);
                 }
