@@ -632,7 +632,7 @@ def run_secondary(model, dev, hbm_peak, tf_peak):
     ms = timed(lambda: val.pathway_coherence_from_tensors(cohort[: rows // 2], cohort[rows // 2:], members), 1, 3)
     out["coherence"] = {"rows": rows, "genes": 371, "pathways": 10, "ms": ms, "gathered_gb_per_s": rows * 150 * 4 / (ms / 1e3) / 1e9,
                         "streamed_gb_per_s": rows * 371 * 4 / (ms / 1e3) / 1e9, "hbm_frac": rows * 371 * 4 / (ms / 1e3) / 1e9 / hbm_peak,
-                        "note": "one pass over whole rows for all pathways (osteo_corr_moments_batched); includes the host-side finish of both cohorts"}
+                        "note": "both cohorts: register-tiled moment kernel (osteo_corr_moments_tiled, one pass over whole rows for all pathways) + Pearson finish on the device + one 20-double D2H; the time is the whole public call"}
     del cohort, X, Y
 
     # -------- fp32x3 (split-bf16, fp32-tolerance) sampling throughput beside the bf16 headline: same workload, one full loop
