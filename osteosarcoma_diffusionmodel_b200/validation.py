@@ -139,6 +139,10 @@ class BiologicalValidator:
         n, m, d = X.shape[0], Y.shape[0], X.shape[1]
         if gamma is None:
             gamma = 1.0 / d
+        # identical cohorts: the reference's three Grams are then the same float64 numbers and cancel to exactly 0.0; here K(X,X) is a
+        # symmetric half-Gram and K(X,Y) a full one, whose fp32 tile sums would leave sqrt(1e-8). One O(n d) comparison settles it.
+        if n == m and (X.data_ptr() == Y.data_ptr() or bool(torch.equal(X, Y))):
+            return 0.0
         # RBF is translation invariant: centre on the pooled mean before the bf16 split (SURVEY.md §7 "MMD precision")
         center = ((X.sum(0, dtype=torch.float64) + Y.sum(0, dtype=torch.float64)) / (n + m)).float().contiguous()
         rank, ws = D.world()

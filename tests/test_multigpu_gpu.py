@@ -118,3 +118,32 @@ def test_two_rank_paths():
     for k in ref:
         assert abs(res["coh"][k] - ref[k]) < 1e-6
     assert res["corr_loss_err"] < 5e-6 and res["corr_grad_err"] < 5e-5
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_a_non_current_device():
+    """a model on cuda:1 while the process's current device is cuda:0 -- every C-ABI call runs under a device guard and on the
+    MODEL device's current stream; the current device is unchanged afterwards (construction, sampling, training, garbage collection)."""
+    import gc
+    from oracle import synth
+    from tests.helpers import build_model, load_case
+
+    torch.cuda.set_device(0)
+    case = load_case("linear3")
+    ref_model = build_model(case, "bf16", device="cuda:0")
+    model = build_model(case, "bf16", device="cuda:1")
+    n = 200
+    _, cond = synth.make_cohort(n, 20, 90, 10, 2, seed=4)
+    a = ref_model.sample(cond.to("cuda:0"), n, seed=5, t_stop=990)
+    b = model.sample(cond.to("cuda:1"), n, seed=5, t_stop=990)
+    assert torch.cuda.current_device() == 0
+    assert b.device == torch.device("cuda", 1) and torch.equal(a.cpu(), b.cpu())
+    model.train()
+    x0, c = synth.make_cohort(64, 20, 90, 10, 2, seed=2)
+    loss = model(x0.to("cuda:1"), c.to("cuda:1"))
+    loss.backward()
+    assert torch.isfinite(loss).item() and torch.cuda.current_device() == 0
+    model.check_status()
+    del model
+    gc.collect()
+    assert torch.cuda.current_device() == 0

@@ -164,3 +164,25 @@ def test_multitask_wrapper_trains_under_the_reference_recipe_in_bf16():
     assert model.sample(cond[:8], 8, t_stop=990).shape == (8, case["D"])
     assert not hasattr(model, "vae")          # utils/train.py:233 dispatches on that attribute
     model.diffusion.check_status()
+
+
+def test_correlation_losses_of_an_empty_selection_are_finite():
+    """Every row filtered out (n_eff = 0: all timesteps too noisy for the auxiliary terms): the moment blocks are empty; the losses must be
+    0 with zero gradient, not 0 / 0 (corr_loss_finish_kernel)."""
+    import ctypes as C
+    from osteosarcoma_diffusionmodel_b200 import _lib
+    from osteosarcoma_diffusionmodel_b200.validation import _CM_STRIDE
+    S = 3
+    mom = torch.zeros((S, _CM_STRIDE), dtype=torch.float64, device="cuda")
+    ci = torch.full((S, 32), -1, dtype=torch.int32, device="cuda")
+    ci[0, :4] = torch.arange(4)
+    ci[1, :2] = torch.tensor([0, 5])
+    ci[2, :2] = torch.tensor([1, 6])
+    shift = torch.zeros((S, 32), device="cuda")
+    modes = torch.tensor([0, 1, -1], dtype=torch.int32, device="cuda")
+    losses = torch.full((S,), float("nan"), device="cuda")
+    coef = torch.full((S * 32 * 4,), float("nan"), device="cuda")
+    _lib.check(_lib.load().osteo_corr_loss_finish(mom.data_ptr(), ci.data_ptr(), shift.data_ptr(), modes.data_ptr(), S, losses.data_ptr(), coef.data_ptr(), _lib.stream_handle()))
+    assert torch.isfinite(losses).all() and float(losses.abs().sum()) == 0.0
+    assert torch.isfinite(coef).all()
+    assert float(coef.view(S, 32, 4)[:, :, 2].abs().sum()) == 0.0        # d loss / dS coefficients: no gradient flows

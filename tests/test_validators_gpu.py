@@ -23,7 +23,7 @@ def test_mmd_matches_reference_golden(golden_dir):
         X, Y = _mmd_inputs(n, m, d, rs)
         assert abs(val.compute_mmd(X, Y) - float(g[f"mmd_{tag}"])) < 1e-4 * float(g[f"mmd_{tag}"])          # fp32 tolerance: rel 1e-4
         assert abs(val.compute_mmd(X, Y, gamma=0.5 / d) - float(g[f"mmd_{tag}_gamma2"])) < 1e-4 * float(g[f"mmd_{tag}_gamma2"])
-        assert val.compute_mmd(X, X) < 2e-4        # reference: exactly 0.0; ours: sqrt of an O(1e-8) cancellation residue
+        assert val.compute_mmd(X, X) == 0.0 and val.compute_mmd(X, X.copy()) == 0.0      # exactly 0.0, like the reference (identical cohorts are detected)
     bf = BiologicalValidator(CONFIG, precision="bf16")
     X, Y = _mmd_inputs(150, 120, 64, np.random.RandomState(11))
     assert abs(bf.compute_mmd(X, Y) - float(g["mmd_small"])) < 2e-2 * float(g["mmd_small"])
