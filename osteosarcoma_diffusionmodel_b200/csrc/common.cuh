@@ -52,6 +52,9 @@ struct DeviceGuard {
 // 128-byte swizzle (matches make_kmajor_sw128_desc). Out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
+// bf16 row-major [rows, cols]; box = 32 rows x 32 columns (64-byte rows), 64-byte swizzle: the per-warp TMA-store box of gemm_ws.cuh.
+int make_tmap_bf16_st32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld);
+
 // fp32 row-major [rows, cols] (ld in elements); box = box_rows x 32 columns (128-byte rows), 128-byte swizzle.
 int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 

@@ -87,6 +87,8 @@ struct GemmParams {
     int a_resident;           // EPI_DDPM, single K segment of <= 4 k-blocks: keep the A tile in shared memory across the n-tiles of an m-block
     int n_chunks;             //   ... and split each m-block's n-tiles into this many work units (load balance)
     int dbg;                  // diagnostic switches (0 in production; scripts/ddpm_probe.py)
+    CUtensorMap tma_out;      // gemm_ws: output view (box 32 rows x 32 columns) for the per-warp TMA stores
+    int out_tma;              // != 0: the weight-stationary kernel stores its bf16 output through tma_out
     int a_blocked_nbox;       // > 0: tma_a[0] views a BLOCKED operand [m_tile][nbox][128 rows][64 cols] (16 KB contiguous per k-block)
     int* status;              // sticky error word (device)
     long long row_base;       // global row index of row 0 (RNG keying under row sharding)
@@ -797,7 +799,9 @@ struct Epilogue<EPI_GN_SILU> {
                 }
             }
             GN_STAMP(2);
-            store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + col, v, 0);
+            if (!(p.dbg & 256)) {      // bit 8: timing probe, no output store
+                store_row32_bf16(p.out_bf + static_cast<size_t>(row) * p.out_bf_ld + col, v, 0);
+            }
             GN_STAMP(3);
             return;
         }

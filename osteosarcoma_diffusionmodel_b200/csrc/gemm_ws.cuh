@@ -27,6 +27,69 @@ __device__ long long g_ws_trace[3 * 32 * 4];      // [role][tile < 32][event] cl
 #define WS_TRACE(role, tile, ev) do { } while (0)
 #endif
 
+// Lean GroupNorm + SiLU for the bf16 inference case of the weight-stationary kernel (no dropout, no saved x-hat / rstd): this thread owns 32
+// consecutive columns of one row; `par` points at those columns' parameters in shared memory, stored by the kernel prologue as
+// [bias | 0.5 gamma | 0.5 beta] (the 0.5 is the tanh form of SiLU: silu(y) = h + h tanh(h), h = y / 2). Per element: bias FADD, sum FADD, sum
+// of squares FFMA, normalise FFMA (u = x rstd - mean rstd), affine FFMA (h = u g' + b'), MUFU.TANH, FFMA, half a pack = 7.5 instructions
+// (the shared run32 spends 9.8 on it: it folds 0.5 into gamma / beta and builds a per-element scale and offset at run time). One-pass
+// moments: the outputs are bf16 (2^-9), the one-pass variance moves them by ~1e-6. out[16] = the row's 32 outputs as packed bf16 pairs.
+template <int GW>
+__device__ __forceinline__ void ws_gn_silu_lean(float (&v)[32], const float* par, float* xch, int me, int other, int bar_id, float eps, uint32_t (&out)[16]) {
+    constexpr int NG = GW >= 32 ? 1 : 32 / GW;
+    constexpr int W = GW >= 32 ? 32 : GW;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 b = reinterpret_cast<const float4*>(par)[j];
+        v[4 * j + 0] += b.x;
+        v[4 * j + 1] += b.y;
+        v[4 * j + 2] += b.z;
+        v[4 * j + 3] += b.w;
+    }
+    float rstd[NG], nm[NG];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+        float s = 0.0f, ss = 0.0f;
+#pragma unroll
+        for (int j = 0; j < W; ++j) {
+            s += v[g * W + j];
+            ss = fmaf(v[g * W + j], v[g * W + j], ss);
+        }
+        if constexpr (GW == 64) {
+            xch[me] = s;
+            xch[512 + me] = ss;
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");
+            s += xch[other];
+            ss += xch[512 + other];
+            asm volatile("bar.sync %0, 64;" ::"r"(bar_id) : "memory");      // the partner has read before the next tile overwrites
+        }
+        const float mu = s * (1.0f / GW);
+        rstd[g] = rsqrtf(fmaxf(fmaf(-mu, mu, ss * (1.0f / GW)), 0.0f) + eps);
+        nm[g] = -mu * rstd[g];
+    }
+    const float4* g2 = reinterpret_cast<const float4*>(par + GN_PAR_MAX);
+    const float4* b2 = reinterpret_cast<const float4*>(par + 2 * GN_PAR_MAX);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 g = g2[j], b = b2[j];
+        const float gg[4] = {g.x, g.y, g.z, g.w}, bb[4] = {b.x, b.y, b.z, b.w};
+        float y[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = 4 * j + e;
+            const float h = fmaf(fmaf(v[i], rstd[i / W], nm[i / W]), gg[e], bb[e]);
+            float t;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+            y[e] = fmaf(h, t, h);
+        }
+        out[2 * j] = pack_bf16x2(y[0], y[1]);
+        out[2 * j + 1] = pack_bf16x2(y[2], y[3]);
+    }
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // CS = 2: the kernel is launched in clusters of two CTAs that own ADJACENT column slices and therefore walk the same row blocks: every A
 // stage is fetched from the L2 once, by one of the two in turn, and multicast into both shared memories; a stage is recycled when BOTH
 // CTAs' MMAs have consumed it (multicast tcgen05.commit onto both "empty" barriers). Without it every A tile crosses the L2 -> SM fabric
@@ -39,9 +102,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     int total_kb = 0;
     for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
-    const int stages = WS_RING_PLUS_RES - total_kb;     // 5 (K = 512) .. 9 (K = 256)
+    // fast path = bf16 inference (what run32 takes the one-pass route for): its output leaves through per-warp TMA stores staged in the last
+    // 16 KB slots (2 KB per warp), so the epilogue registers are free the moment the values are in shared memory -- with st.global the next
+    // tile's first register write waited for the previous tile's stores to drain (19 % of the block GEMMs, probe bit 8). K <= 384 gives up
+    // two ring slots (all 16 warps staged, 7+ stages left); K = 512 cannot (3 stages starve the MMAs: measured 20 % slower): with
+    // out_tma >= 2 it gives up one slot and stages the warps of column parts 0 and 1 only.
+    const bool lean = p.out_lo_off == 0 && !p.xhat_bf && !p.rstd_out && p.drop_p == 0.0f && p.out_bf && !(p.dbg & (64 | 256 | 512));
+    const bool tma_ok = CS == 1 && p.out_tma && lean;
+    const int out_slots = !tma_ok ? 0 : total_kb <= 6 ? 2 : p.out_tma >= 2 ? 1 : 0;
+    const int stages = WS_RING_PLUS_RES - total_kb - out_slots;     // 5 (K = 512) .. 9 (K = 256) without the staging
     uint8_t* s_w = smem;                                // resident W slice, k-block major
     uint8_t* s_a = smem + total_kb * B_TILE_BYTES;      // A ring
+    uint8_t* s_out = smem + (WS_RING_PLUS_RES - out_slots) * A_TILE_BYTES;      // [8 * out_slots warps][32 rows][64 bytes]
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WS_RING_PLUS_RES * A_TILE_BYTES);
     uint64_t* empty_bar = full_bar + WS_MAX_STAGES;
     uint64_t* tfull_bar = empty_bar + WS_MAX_STAGES;
@@ -65,6 +137,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
         tma_prefetch_desc(&p.tma_a[0]);
         tma_prefetch_desc(&p.tma_a[1]);
         tma_prefetch_desc(&p.tma_b[0]);
+        if (out_slots) tma_prefetch_desc(&p.tma_out);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < stages; ++i) {
@@ -81,9 +154,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
     if (warp == 2) tmem_alloc(tmem_slot, 512);
     if (warp >= 4) {
         for (int i = threadIdx.x; i < p.N && i < GN_PAR_MAX; i += NUM_EPI_WARPS * 32) {
+            const float sc = lean ? 0.5f : 1.0f;      // ws_gn_silu_lean wants 0.5 gamma, 0.5 beta
             gn_par[i] = p.bias[i];
-            gn_par[GN_PAR_MAX + i] = p.gamma[i];
-            gn_par[2 * GN_PAR_MAX + i] = p.beta[i];
+            gn_par[GN_PAR_MAX + i] = sc * p.gamma[i];
+            gn_par[2 * GN_PAR_MAX + i] = sc * p.beta[i];
         }
     }
     tc_fence_before_sync();
@@ -177,8 +251,52 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
         // ---------------------------------------------------------------- epilogue (the generic kernel's 32-column GroupNorm epilogue)
         const int q = warp_phys & 3;
         const int part = warp_phys >> 2;
+        const bool tma_out = warp_phys < 8 * out_slots;
         bool ok = true;
         int it = 0;
+        if (lean) {
+            // ---- bf16 inference: everything tile-invariant is hoisted, the epilogue is ws_gn_silu_lean, the output goes to the warp's staging
+            // box + one TMA store (tma_out) or straight to global memory
+            const float* par = gn_par + n_blk * BN + part * 32;
+            const int me = (q * 4 + part) * 32 + lane, other = (q * 4 + (part ^ 1)) * 32 + lane;
+            const int bar_id = 1 + q * 2 + (part >> 1);
+            const uint32_t stage_warp = smem_u32(s_out + warp_phys * 2048);
+            const uint32_t stage_row = stage_warp + lane * 64;
+            const int sw = (lane >> 1) & 3;      // 64-byte swizzle of the staging box: a quarter warp's 16-byte chunks cover all 32 banks
+            const float eps = p.gn_eps;
+            const int col = n_blk * BN + part * 32;
+            const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(part * 32);
+            for (int m = m_first; m < p.m_tiles; m += m_step, ++it) {
+                const int acc = it % NUM_ACC;
+                const int row0 = (p.m_tile0 + m) * BM + q * 32;
+                if (!mbar_wait(&tfull_bar[acc], static_cast<uint32_t>(it / NUM_ACC) & 1u)) { ok = false; break; }
+                tc_fence_after_sync();
+                float v[32];
+                tmem_ld_32(tcol + static_cast<uint32_t>(acc * BN), v);
+                tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                uint32_t o[16];
+                ws_gn_silu_lean<GW>(v, par, gn_xch, me, other, bar_id, eps, o);
+                if (tma_out) {
+                    // the bulk store of this warp's previous tile (issued a whole tile ago) has read the staging box
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) st_shared_v4(stage_row + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&p.tma_out, s_out + warp_phys * 2048, col, row0);
+                        tma_store_commit();
+                    }
+                } else if (row0 + lane < p.M) {
+                    __nv_bfloat16* dst = p.out_bf + static_cast<size_t>(row0 + lane) * p.out_bf_ld + col;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) st_global_v8(dst + 16 * j, *reinterpret_cast<const uint32_t(*)[8]>(&o[8 * j]));
+                }
+            }
+        } else
         for (int m = m_first; ok && m < p.m_tiles; m += m_step, ++it) {
             const int acc = it % NUM_ACC;
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BN + part * 32);
@@ -197,6 +315,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
             if (!(p.dbg & 64)) Epilogue<EPI_GN_SILU>::template run32<GW>(p, row, col, v, gn_par, gn_xch, q, part, lane);      // bit 6: timing probe, no epilogue
             if (warp_phys == 0) WS_TRACE(2, it, 3);
         }
+        if (tma_out && lane == 0) tma_store_wait_all<0>();      // all bulk stores complete before the CTA (and its shared memory) goes away
         if (!ok && lane == 0) atomicExch(p.status, ERR_EPI_TIMEOUT);
     }
 

@@ -64,6 +64,23 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t c
     return 0;
 }
 
+// bf16 row-major [rows, cols], box = 32 rows x 32 columns (64-byte rows, 64-byte swizzle: 16-byte chunk index XOR ((row >> 1) & 3), so the
+// 32 lanes of a warp, one row each, write a chunk without bank conflicts): the per-warp output box of the TMA-store epilogue.
+int make_tmap_bf16_st32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return fail("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+    if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0) return fail("tensor map operand not 16-byte aligned");
+    cuuint64_t gdim[2] = {cols, rows};
+    cuuint64_t gstride[1] = {ld * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled (store box) failed with CUresult %d", static_cast<int>(r));
+    return 0;
+}
+
 int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return fail("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
@@ -134,11 +151,13 @@ struct PackedLinear {
 struct ActBuf {
     int width = 0;
     DevBuf buf;
-    CUtensorMap tmap;
+    CUtensorMap tmap;          // A-operand view: box 128 rows x 64 columns, 128-byte swizzle
+    CUtensorMap tmap_st;       // output view of the TMA-store epilogue: box 32 rows x 32 columns, 64-byte swizzle
     int init(long long cap, int width_) {
         width = width_;
         OSTEO_TRY(buf.alloc(static_cast<size_t>(cap) * 2 * width * 2));
         OSTEO_TRY(make_tmap_bf16(&tmap, buf.p, cap, 2 * width, 2 * width, BM));
+        OSTEO_TRY(make_tmap_bf16_st32(&tmap_st, buf.p, cap, 2 * width, 2 * width));
         return 0;
     }
     __nv_bfloat16* ptr() const { return buf.as<__nv_bfloat16>(); }
@@ -205,6 +224,7 @@ struct osteo_ddpm_ctx {
     CUtensorMap wout_tmap64, win_tmap;   // W_out as [64 x 64] boxes, W_in as [h0 x 64] boxes
     int fused_enable = 1;
     int ws_enable = getenv("OSTEO_DDPM_NO_WS") ? 0 : 1;
+    int ws_tma_store = getenv("OSTEO_WS_TMA_STORE") ? atoi(getenv("OSTEO_WS_TMA_STORE")) : 1;      // block GEMMs write their output through per-warp TMA stores
     int ws2_enable = getenv("OSTEO_WS2") ? atoi(getenv("OSTEO_WS2")) : 0;      // CTA-pair block GEMMs (gemm_ws2.cuh): opt-in until measured
     DevBuf fused_trace;
     bool x_c8 = false;                   // layout the state was loaded in: c8 (fused path) or 32-column boxes (TMA-staged path)
@@ -378,6 +398,8 @@ static int launch_half(osteo_ddpm_ctx* c, int hi, long long row0, long long row1
         p.xhat_bf = c->train.xhat[hi]->as<__nv_bfloat16>();
         p.rstd_out = c->train.rstd[hi]->as<float>();
     }
+    p.tma_out = dst.tmap_st;
+    p.out_tma = c->ws_tma_store;
     // bf16 mode, K <= 512: weight-stationary kernel (the column slice of W stays in shared memory, only A streams: half the L2 traffic)
     if (const char* e = getenv("OSTEO_DDPM_DBG")) p.dbg = atoi(e);
     // ... as a CTA pair (cta_group::2, M = 256 x N = 256) where the layer is a whole number of 256-column slices: half the per-SM operand traffic

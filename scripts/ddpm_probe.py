@@ -39,4 +39,6 @@ for t, dbg in [(500, d) for d in os.environ.get('PROBE_DBG', '0').split(',')]:
     ddpm = sum(acc[per_chunk - 1::per_chunk])
     inp = 0.0 if fused else sum(acc[0::per_chunk])
     hid = sum(acc) - ddpm - inp
+    if os.environ.get("PROBE_KERNELS"):
+        print("  per launch (ms): " + " ".join(f"{a:.4f}" for a in acc[:per_chunk]), flush=True)
     print(f"dbg={dbg:2d} pf={pf or '-'} t={t} fused={int(fused)}: step {sum(acc):.3f} ms  input_proj {inp:.3f}  hidden {hid:.3f}  output_proj+update {ddpm:.3f}", flush=True)
