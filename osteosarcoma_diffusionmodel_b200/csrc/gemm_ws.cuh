@@ -34,7 +34,7 @@ __device__ long long g_ws_trace[3 * 32 * 4];      // [role][tile < 32][event] cl
 // (the shared run32 spends 9.8 on it: it folds 0.5 into gamma / beta and builds a per-element scale and offset at run time). One-pass
 // moments: the outputs are bf16 (2^-9), the one-pass variance moves them by ~1e-6. out[16] = the row's 32 outputs as packed bf16 pairs.
 template <int GW>
-__device__ __forceinline__ void ws_gn_silu_lean(float (&v)[32], const float* par, float* xch, int me, int other, int bar_id, float eps, uint32_t (&out)[16]) {
+__device__ __forceinline__ void ws_gn_silu_lean(float (&v)[32], const float* __restrict__ par, float* xch, int me, int other, int bar_id, float eps, uint32_t (&out)[16]) {
     constexpr int NG = GW >= 32 ? 1 : 32 / GW;
     constexpr int W = GW >= 32 ? 32 : GW;
 #pragma unroll
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
     // tile's first register write waited for the previous tile's stores to drain (19 % of the block GEMMs, probe bit 8). K <= 384 gives up
     // two ring slots (all 16 warps staged, 7+ stages left); K = 512 cannot (3 stages starve the MMAs: measured 20 % slower): with
     // out_tma >= 2 it gives up one slot and stages the warps of column parts 0 and 1 only.
-    const bool lean = p.out_lo_off == 0 && !p.xhat_bf && !p.rstd_out && p.drop_p == 0.0f && p.out_bf && !(p.dbg & (64 | 256 | 512));
+    const bool lean = p.out_lo_off == 0 && !p.xhat_bf && !p.rstd_out && p.drop_p == 0.0f && p.out_bf && !(p.dbg & 256);
     const bool tma_ok = CS == 1 && p.out_tma && lean;
     const int out_slots = !tma_ok ? 0 : total_kb <= 6 ? 2 : p.out_tma >= 2 ? 1 : 0;
     const int stages = WS_RING_PLUS_RES - total_kb - out_slots;     // 5 (K = 512) .. 9 (K = 256) without the staging
@@ -269,15 +269,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
             for (int m = m_first; m < p.m_tiles; m += m_step, ++it) {
                 const int acc = it % NUM_ACC;
                 const int row0 = (p.m_tile0 + m) * BM + q * 32;
+                if (warp_phys == 0) WS_TRACE(2, it, 0);
                 if (!mbar_wait(&tfull_bar[acc], static_cast<uint32_t>(it / NUM_ACC) & 1u)) { ok = false; break; }
                 tc_fence_after_sync();
+                if (warp_phys == 0) WS_TRACE(2, it, 1);
                 float v[32];
                 tmem_ld_32(tcol + static_cast<uint32_t>(acc * BN), v);
                 tc_fence_before_sync();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (warp_phys == 0) WS_TRACE(2, it, 2);
                 uint32_t o[16];
-                ws_gn_silu_lean<GW>(v, par, gn_xch, me, other, bar_id, eps, o);
+                if (p.dbg & 64) {      // bit 6: timing probe, no epilogue math
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(v[2 * j]);
+                } else {
+                    ws_gn_silu_lean<GW>(v, par, gn_xch, me, other, bar_id, eps, o);
+                }
                 if (tma_out) {
                     // the bulk store of this warp's previous tile (issued a whole tile ago) has read the staging box
                     if (lane == 0) tma_store_wait_read<0>();
@@ -295,6 +303,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws_gn_silu_kernel(const __
 #pragma unroll
                     for (int j = 0; j < 2; ++j) st_global_v8(dst + 16 * j, *reinterpret_cast<const uint32_t(*)[8]>(&o[8 * j]));
                 }
+                if (warp_phys == 0) WS_TRACE(2, it, 3);
             }
         } else
         for (int m = m_first; ok && m < p.m_tiles; m += m_step, ++it) {
