@@ -65,7 +65,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws2_gn_silu_kernel(const _
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     int total_kb = 0;
     for (int s = 0; s < p.nseg; ++s) total_kb += p.seg[s].nkb;
-    const int stages = WS_RING_PLUS_RES - total_kb;     // 5 (K = 512) .. 9 (K = 256)
+    // bf16 inference: the lean epilogue of gemm_ws.cuh (ws_gn_silu_lean) + per-warp TMA stores staged in the last two 16 KB slots. The pair
+    // streams HALF the A bytes per output column of the single-CTA kernel, so K = 512 can afford the two slots too (3 ring stages left).
+    const bool lean = p.out_lo_off == 0 && !p.xhat_bf && !p.rstd_out && p.drop_p == 0.0f && p.out_bf && !(p.dbg & 256);
+    const int out_slots = (lean && p.out_tma) ? 2 : 0;
+    const int stages = WS_RING_PLUS_RES - total_kb - out_slots;     // 5 (K = 512) .. 9 (K = 256) without the staging
+    uint8_t* s_out = smem + (WS_RING_PLUS_RES - 2) * A_TILE_BYTES;  // [16 warps][32 rows][64 bytes, 64-byte swizzle] when out_slots
     uint8_t* s_w = smem;                                // resident W half: 128 rows, k-block major
     uint8_t* s_a = smem + total_kb * B_TILE_BYTES;      // A ring (this CTA's 128 rows)
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + WS_RING_PLUS_RES * A_TILE_BYTES);
@@ -96,6 +101,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws2_gn_silu_kernel(const _
         tma_prefetch_desc(&p.tma_a[0]);
         tma_prefetch_desc(&p.tma_a[1]);
         tma_prefetch_desc(&p.tma_b[0]);
+        if (out_slots) tma_prefetch_desc(&p.tma_out);
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < stages; ++i) {
@@ -111,9 +117,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws2_gn_silu_kernel(const _
     }
     if (warp >= 4) {
         for (int i = threadIdx.x; i < p.N && i < GN_PAR_MAX; i += NUM_EPI_WARPS * 32) {
+            const float sc = lean ? 0.5f : 1.0f;      // ws_gn_silu_lean wants 0.5 gamma, 0.5 beta
             gn_par[i] = p.bias[i];
-            gn_par[GN_PAR_MAX + i] = p.gamma[i];
-            gn_par[2 * GN_PAR_MAX + i] = p.beta[i];
+            gn_par[GN_PAR_MAX + i] = sc * p.gamma[i];
+            gn_par[2 * GN_PAR_MAX + i] = sc * p.beta[i];
         }
     }
     __syncthreads();
@@ -192,6 +199,51 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_ws2_gn_silu_kernel(const _
         const int part = warp_phys >> 2;
         bool ok = true;
         int it = 0;
+        if (lean) {
+            const int me = (q * 4 + part) * 32 + lane, other = (q * 4 + (part ^ 1)) * 32 + lane;
+            const int bar_id = 1 + q * 2 + (part >> 1);
+            const uint32_t stage_row = smem_u32(s_out + warp_phys * 2048) + lane * 64;
+            const int sw = (lane >> 1) & 3;
+            const float eps = p.gn_eps;
+            const uint32_t tcol = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(part * 32);
+            for (int mp = mp_first; mp < mp_tiles; mp += mp_step, ++it) {
+                const int acc = it & (WS2_ACC - 1);
+                const int row0 = (p.m_tile0 + 2 * mp + static_cast<int>(crank)) * BM + q * 32;
+                if (!mbar_wait(&tfull_bar[acc], static_cast<uint32_t>(it / WS2_ACC) & 1u)) { ok = false; break; }
+                tc_fence_after_sync();
+#pragma unroll 1
+                for (int half = 0; half < 2; ++half) {
+                    const int col = n_pair * WS2_BN + half * BN + part * 32;
+                    float v[32];
+                    tmem_ld_32(tcol + static_cast<uint32_t>(acc * WS2_BN + half * BN), v);
+                    if (half == 1) {      // the whole accumulator stage has been read by this warp: hand it back to the leader's MMA warp
+                        tc_fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_leader(&tempty_bar[acc]);
+                    }
+                    uint32_t o[16];
+                    ws_gn_silu_lean<GW>(v, gn_par + col, gn_xch, me, other, bar_id, eps, o);
+                    if (out_slots) {
+                        if (lane == 0) tma_store_wait_read<0>();      // the previous bulk store has read the staging box
+                        __syncwarp();
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) st_shared_v4(stage_row + ((j ^ sw) << 4), o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                        fence_proxy_async_smem();
+                        __syncwarp();
+                        // an odd number of row blocks leaves the last pair's rank 1 without a block of its own: those rows belong to someone else
+                        if (lane == 0 && row0 < p.M) {
+                            tma_store_2d(&p.tma_out, s_out + warp_phys * 2048, col, row0);
+                            tma_store_commit();
+                        }
+                    } else if (row0 + lane < p.M) {
+                        __nv_bfloat16* dst = p.out_bf + static_cast<size_t>(row0 + lane) * p.out_bf_ld + col;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) st_global_v8(dst + 16 * j, *reinterpret_cast<const uint32_t(*)[8]>(&o[8 * j]));
+                    }
+                }
+            }
+            if (out_slots && lane == 0) tma_store_wait_all<0>();      // all bulk stores complete before the CTA (and its shared memory) goes away
+        } else
         for (int mp = mp_first; ok && mp < mp_tiles; mp += mp_step, ++it) {
             const int acc = it & (WS2_ACC - 1);
             const int row = (p.m_tile0 + 2 * mp + static_cast<int>(crank)) * BM + q * 32 + lane;

@@ -225,7 +225,7 @@ struct osteo_ddpm_ctx {
     int fused_enable = 1;
     int ws_enable = getenv("OSTEO_DDPM_NO_WS") ? 0 : 1;
     int ws_tma_store = getenv("OSTEO_WS_TMA_STORE") ? atoi(getenv("OSTEO_WS_TMA_STORE")) : 1;      // block GEMMs write their output through per-warp TMA stores
-    int ws2_enable = getenv("OSTEO_WS2") ? atoi(getenv("OSTEO_WS2")) : 0;      // CTA-pair block GEMMs (gemm_ws2.cuh): opt-in until measured
+    int ws2_enable = getenv("OSTEO_WS2") ? atoi(getenv("OSTEO_WS2")) : 1;      // 1: CTA-pair kernel for the K = 512, N >= 512 block GEMMs (measured faster there only); 2: wherever eligible; 0: never
     DevBuf fused_trace;
     bool x_c8 = false;                   // layout the state was loaded in: c8 (fused path) or 32-column boxes (TMA-staged path)
     bool shadow_valid = false;           // xb == bf16(x)? (the fused step does not maintain the shadow)
@@ -402,10 +402,15 @@ static int launch_half(osteo_ddpm_ctx* c, int hi, long long row0, long long row1
     p.out_tma = c->ws_tma_store;
     // bf16 mode, K <= 512: weight-stationary kernel (the column slice of W stays in shared memory, only A streams: half the L2 traffic)
     if (const char* e = getenv("OSTEO_DDPM_DBG")) p.dbg = atoi(e);
-    // ... as a CTA pair (cta_group::2, M = 256 x N = 256) where the layer is a whole number of 256-column slices: half the per-SM operand traffic
+    // ... as a CTA pair (cta_group::2, M = 256 x N = 256) for the K = 512, N >= 512 layers: half the per-SM operand and A-ring traffic, which is what
+    // bounds them (0.077 -> 0.066 ms per 100k rows); the K = 256 layers are epilogue-bound and lose with the pair (0.027 -> 0.033 ms)
     if (c->ws2_enable && c->ws_enable && gemm_ws2_eligible(p)) {
-        const int rc = launch_gemm_ws2(hb.gw, p, c->sms, s);
-        if (rc != -2) return after_launch(c, rc, s);
+        int total_kb = 0;
+        for (int sg = 0; sg < p.nseg; ++sg) total_kb += p.seg[sg].nkb;
+        if (c->ws2_enable >= 2 || (total_kb >= 7 && p.n_tiles >= 4)) {
+            const int rc = launch_gemm_ws2(hb.gw, p, c->sms, s);
+            if (rc != -2) return after_launch(c, rc, s);
+        }
     }
     if (c->ws_enable && gemm_ws_eligible(p)) {
         const int rc = launch_gemm_ws(hb.gw, p, c->sms, s);
