@@ -187,10 +187,18 @@ __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// One bulk copy (TMA engine, no tensor map) of `bytes` contiguous bytes global -> shared, completion on `bar` (complete_tx). 16-byte aligned
+// source, destination and size.
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 // NB = 4 x 4 register blocks per dimension: 4 (sets of <= 16 columns, 10 blocks per set) or 8 (<= 32 columns, 36 blocks per set).
-// One CTA per SM; the rows of the next CT_STAGES - 1 chunks are in flight (cp.async, 16 bytes per request) while chunk c is gathered and
-// multiplied: with a single chunk ahead the loop ran at the latency of one 47 KB fetch per iteration (3.6 TB/s).
+// One CTA per SM; the rows of the next CT_STAGES - 1 chunks are in flight while chunk c is gathered and multiplied (with a single chunk
+// ahead the loop ran at the latency of one 47 KB fetch per iteration). A chunk of whole contiguous rows is ONE bulk copy issued by one
+// thread (cp.async.bulk + mbarrier): as 2 968 per-thread 16-byte cp.async requests the staging alone kept the LSU busy for a large part
+// of the 3 800 cycles an iteration took.
 template <int NB>
 __global__ void __launch_bounds__(CT_THREADS, 1) corr_moments_tiled_kernel(const float* __restrict__ data, int ld, int ncols, const int* __restrict__ cols, int P,
                                                                             const float* __restrict__ shift, long long rb, long long re, int stages, double* __restrict__ out) {
@@ -198,13 +206,18 @@ __global__ void __launch_bounds__(CT_THREADS, 1) corr_moments_tiled_kernel(const
     constexpr int NBLK = NB * (NB + 1) / 2;          // blocks on or above the diagonal
     constexpr int SET_STRIDE = 2 + W + W * W;        // shared-memory reduction block per set: count, s1[W], s2[W][W], one pad (keeps what follows 16-byte aligned)
     extern __shared__ __align__(16) uint8_t ct_smem[];
-    double* red = reinterpret_cast<double*>(ct_smem);                                   // [P][SET_STRIDE]
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ct_smem);                          // [CT_MAX_STAGES] row buffer landed
+    double* red = reinterpret_cast<double*>(ct_smem + 64);                              // [P][SET_STRIDE]
     float* rows_sm = reinterpret_cast<float*>(red + static_cast<size_t>(P) * SET_STRIDE);      // [stages][CT_CHUNK][ncols] (+ pad to 16 bytes per buffer)
     const int buf_floats = (CT_CHUNK * ncols + 3) & ~3;
     float* g_sm = rows_sm + stages * static_cast<size_t>(buf_floats);                     // [CT_CHUNK][P][W]
     int* col_sm = reinterpret_cast<int*>(g_sm + static_cast<size_t>(CT_CHUNK) * P * W);   // [P][W]
     float* shift_sm = reinterpret_cast<float*>(col_sm + P * W);                           // [P][W]
     const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int i = 0; i < CT_MAX_STAGES; ++i) mbar_init(&full_bar[i], 1);
+        fence_mbar_init();
+    }
     for (int i = tid; i < P * SET_STRIDE; i += CT_THREADS) red[i] = 0.0;
     for (int i = tid; i < P * W; i += CT_THREADS) {
         const int c = cols[(i / W) * 32 + (i % W)];
@@ -242,38 +255,37 @@ __global__ void __launch_bounds__(CT_THREADS, 1) corr_moments_tiled_kernel(const
     __syncthreads();                                  // col_sm / shift_sm are complete
     const int gcol = col_sm[gslot];
     const float gshift = shift_sm[gslot];
-    // contiguous rows whose chunks start on 16-byte boundaries go through cp.async; anything else is copied synchronously
+    // contiguous rows whose chunks start on 16-byte boundaries are one bulk copy per chunk; anything else (and a last chunk whose size is not
+    // a multiple of 16 bytes) is copied by the threads, and thread 0 completes the barrier phase by hand
     const bool async_ok = ld == ncols && ((reinterpret_cast<uintptr_t>(data + rb * ld) & 15) == 0) && ((static_cast<size_t>(CT_CHUNK) * ncols * 4) & 15) == 0;
     auto stage = [&](int buf, long long c) {
-        if (c < nchunks) {
-            const long long r0 = rb + c * CT_CHUNK;
-            const int nr = static_cast<int>(re - r0 < CT_CHUNK ? re - r0 : CT_CHUNK);
-            float* dst = rows_sm + static_cast<size_t>(buf) * buf_floats;
-            if (async_ok) {
-                const float* src = data + r0 * ld;
-                const int n4 = (nr * ncols) >> 2;
-                for (int i = tid; i < n4; i += CT_THREADS) cp_async_16(dst + 4 * i, src + 4 * i);
-                for (int j = (n4 << 2) + tid; j < nr * ncols; j += CT_THREADS) dst[j] = src[j];
-            } else {
-                for (int i = tid; i < nr * ncols; i += CT_THREADS) dst[i] = data[(r0 + i / ncols) * ld + i % ncols];
+        if (c >= nchunks) return;
+        const long long r0 = rb + c * CT_CHUNK;
+        const int nr = static_cast<int>(re - r0 < CT_CHUNK ? re - r0 : CT_CHUNK);
+        float* dst = rows_sm + static_cast<size_t>(buf) * buf_floats;
+        const uint32_t bytes = static_cast<uint32_t>(nr) * static_cast<uint32_t>(ncols) * 4u;
+        if (async_ok && (bytes & 15u) == 0) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&full_bar[buf], bytes);
+                bulk_load(dst, data + r0 * ld, bytes, &full_bar[buf]);
             }
+        } else {
+            for (int i = tid; i < nr * ncols; i += CT_THREADS) dst[i] = data[(r0 + i / ncols) * ld + i % ncols];
+            __syncthreads();                          // (block-uniform branch) the copy is complete before the phase is
+            if (tid == 0) mbar_arrive(&full_bar[buf]);
         }
-        cp_async_commit();                            // one group per call, empty past the end: the wait below counts groups
     };
     __syncthreads();
     for (int st = 0; st < stages - 1; ++st) stage(st, blockIdx.x + static_cast<long long>(st) * gridDim.x);
     int buf = 0;
-    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x, buf = buf + 1 == stages ? 0 : buf + 1) {
+    uint32_t use = 0;                                 // iteration counter: buffer = use % stages, barrier parity = (use / stages) & 1
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x, buf = buf + 1 == stages ? 0 : buf + 1, ++use) {
         const long long r0 = rb + c * CT_CHUNK;
         const int nr = static_cast<int>(re - r0 < CT_CHUNK ? re - r0 : CT_CHUNK);
         const float* cur = rows_sm + static_cast<size_t>(buf) * buf_floats;
         // the buffer consumed in the previous iteration was released by the barrier that ended it: refill it with chunk c + (STAGES - 1) grid
         stage((buf + stages - 1) % stages, c + static_cast<long long>(stages - 1) * gridDim.x);
-        // all but the newest stages - 1 groups have landed: chunk c is in `cur`
-        if (stages == 4) cp_async_wait<3>();
-        else if (stages == 3) cp_async_wait<2>();
-        else cp_async_wait<1>();
-        __syncthreads();
+        if (!mbar_wait(&full_bar[buf], (use / static_cast<uint32_t>(stages)) & 1u)) __trap();      // chunk c is in `cur`
         // ---- gather + shift into the compact set-major copy: thread <-> one (set, slot) of `rlanes` interleaved rows, its column index and
         // shift in registers (a flat index over rows x slots costs two integer divisions per element)
         if (tid < rlanes * SL) {
@@ -340,7 +352,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) corr_moments_tiled_kernel(const
 // Shared-memory bytes of one launch with n_sets sets of padded width W over `ncols`-column rows.
 inline size_t moments_tiled_smem(int n_sets, int W, int ncols, int stages) {
     const size_t buf_floats = (static_cast<size_t>(CT_CHUNK) * ncols + 3) & ~static_cast<size_t>(3);
-    return static_cast<size_t>(n_sets) * (2 + W + W * W) * sizeof(double) + static_cast<size_t>(stages) * buf_floats * 4 + static_cast<size_t>(CT_CHUNK) * n_sets * W * 4 +
+    return 64 /*barriers*/ + static_cast<size_t>(n_sets) * (2 + W + W * W) * sizeof(double) + static_cast<size_t>(stages) * buf_floats * 4 + static_cast<size_t>(CT_CHUNK) * n_sets * W * 4 +
            static_cast<size_t>(n_sets) * W * 8;
 }
 
