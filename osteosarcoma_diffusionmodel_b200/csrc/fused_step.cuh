@@ -50,7 +50,7 @@ constexpr int F_XBF_STAGE = BM * BK * 2;                // 16 KB: [128 x 64]
 constexpr int F_STAGES = 2;
 constexpr int F_EPS_ACC = 4;
 constexpr int F_BIAS_MAX = 6144;                        // b_out travels in the kernel parameters (constant bank): DP <= F_BIAS_MAX on the fused path
-constexpr int F_PREFETCH = 2;                           // state tiles prefetched into L2 ahead of the next-step MMA position
+constexpr int F_PREFETCH = 6;                           // state tiles prefetched into L2 ahead of the next-step MMA position (sweep 2..16: 6 is best, -1.5 % eager, -0.5 % in the loop; >= 10 re-reads evicted lines)
 constexpr int F_LAG = 2;                                // the next-step contraction trails the eps GEMM by two tiles
 constexpr int F_TMEM_EPS0 = 256;                        // first TMEM column of the eps stages
 constexpr int F_SMEM_BYTES = F_ARES_BYTES + F_STAGES * (F_WOUT_STAGE + F_WIN_STAGE + F_XBF_STAGE) + 1024 /*align*/ + 256 /*barriers*/;
