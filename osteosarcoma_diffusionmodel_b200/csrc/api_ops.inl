@@ -266,10 +266,10 @@ int osteo_corr_moments_batched(const float* data_dev, long long n, int ld, int n
     if (chunk_rows > 64) chunk_rows = 64;
     if (chunk_rows < 1) return fail("corr_moments_batched: a row of %d columns does not fit the 96 KB staging buffer", ncols);
     const size_t smem = static_cast<size_t>(chunk_rows) * ncols * 4;
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice dev_state;
+    if (!dev_state.configured()) {
         OSTEO_CUDA(cudaFuncSetAttribute(corr_moments_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-        configured = true;
+        dev_state.set_configured();
     }
     const long long nchunks = (row_end - row_begin + chunk_rows - 1) / chunk_rows;
     const int sms = current_sms();

@@ -78,10 +78,10 @@ static int finish_partials(osteo_ddpm_ctx* c, const float* partials, long long n
 
 static int outer_accum(osteo_ddpm_ctx* c, const float* G, int gm, const float* X, int xk, const int* idx, long long n, float* dW, cudaStream_t s) {
     const size_t smem = static_cast<size_t>(64) * (gm + xk) * sizeof(float);
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice dev_state;
+    if (!dev_state.configured()) {
         OSTEO_CUDA(cudaFuncSetAttribute(outer_accum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
+        dev_state.set_configured();
     }
     if (smem > 160 * 1024) return fail("outer_accum: tile does not fit shared memory (gm=%d xk=%d)", gm, xk);
     outer_accum_kernel<<<static_cast<unsigned>((n + 63) / 64), 256, smem, s>>>(G, gm, X, xk, idx, n, dW);

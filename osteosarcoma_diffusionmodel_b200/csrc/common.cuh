@@ -48,6 +48,23 @@ struct DeviceGuard {
     OSTEO_TRY(::osteo::check_ctx(c));  \
     ::osteo::DeviceGuard _osteo_device_guard((c)->device)
 
+// cudaFuncSetAttribute (the opt-in to > 48 KB of dynamic shared memory) and occupancy queries are PER DEVICE: a launcher keeps one of
+// these per kernel instead of a process-wide `static bool configured`, or a model on cuda:1 launches an unconfigured kernel
+// ("invalid argument") after a model on cuda:0 configured it. `value` carries a per-device result (e.g. co-resident cluster count).
+struct PerDevice {
+    static constexpr int MAX_DEVICES = 64;
+    bool done[MAX_DEVICES] = {};
+    int value[MAX_DEVICES] = {};
+    static int current() {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+        return d;
+    }
+    bool configured() const { return done[current()]; }
+    void set_configured() { done[current()] = true; }
+    int& val() { return value[current()]; }
+};
+
 // bf16 row-major [rows, cols] with leading dimension ld (elements); box = box_rows x 64 columns,
 // 128-byte swizzle (matches make_kmajor_sw128_desc). Out-of-bounds elements read as zero.
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);

@@ -7,10 +7,10 @@ namespace osteo {
 
 template <int EPI, int GW, bool MN = false>
 int launch_gemm_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice dev_state;
+    if (!dev_state.configured()) {
         OSTEO_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<EPI, GW, MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem_bytes<EPI>()));
-        configured = true;
+        dev_state.set_configured();
     }
     int tiles = (MN ? p.splits : 1) * p.m_tiles * p.n_tiles;
     if (tiles <= 0) return 0;

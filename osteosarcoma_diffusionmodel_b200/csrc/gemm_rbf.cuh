@@ -212,10 +212,10 @@ __global__ void __launch_bounds__(RB_THREADS, 1) rbf_gram_kernel(const __grid_co
 }
 
 inline int launch_rbf_gram(const RbfParams& p, int num_sms, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice dev_state;
+    if (!dev_state.configured()) {
         OSTEO_CUDA(cudaFuncSetAttribute(rbf_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RB_SMEM_BYTES));
-        configured = true;
+        dev_state.set_configured();
     }
     const int tiles = p.m_tiles * p.n_tiles;
     if (tiles <= 0) return 0;

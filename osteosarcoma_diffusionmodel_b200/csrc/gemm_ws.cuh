@@ -343,10 +343,9 @@ inline bool gemm_ws_eligible(const GemmParams& p) {
 
 template <int GW>
 int launch_gemm_ws_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
-    static bool configured = false;
-    static int max_pairs = 0;               // co-resident 2-CTA clusters (1 CTA / SM, both SMs in one GPC); 0 = clusters unavailable
+    static PerDevice dev_state;
     static const bool want_cluster = getenv("OSTEO_WS_CLUSTER") && atoi(getenv("OSTEO_WS_CLUSTER")) != 0;      // opt-in until measured
-    if (!configured) {
+    if (!dev_state.configured()) {
         OSTEO_CUDA(cudaFuncSetAttribute(gemm_ws_gn_silu_kernel<GW, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
         OSTEO_CUDA(cudaFuncSetAttribute(gemm_ws_gn_silu_kernel<GW, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
         if (want_cluster) {
@@ -362,11 +361,12 @@ int launch_gemm_ws_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
             qc.attrs = qa;
             qc.numAttrs = 1;
             int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, gemm_ws_gn_silu_kernel<GW, 2>, &qc) == cudaSuccess) max_pairs = n;
+            if (cudaOccupancyMaxActiveClusters(&n, gemm_ws_gn_silu_kernel<GW, 2>, &qc) == cudaSuccess) dev_state.val() = n;
             else cudaGetLastError();
         }
-        configured = true;
+        dev_state.set_configured();
     }
+    const int max_pairs = dev_state.val();      // co-resident 2-CTA clusters on this device (0 = clusters unavailable / not queried)
     if (p.m_tiles <= 0) return 0;
     int per_slice = num_sms / p.n_tiles;                // CTAs per column slice
     if (per_slice > p.m_tiles) per_slice = p.m_tiles;

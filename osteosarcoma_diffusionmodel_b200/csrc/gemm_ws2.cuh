@@ -279,9 +279,8 @@ inline bool gemm_ws2_eligible(const GemmParams& p) {
 
 template <int GW>
 int launch_gemm_ws2_inst(const GemmParams& p, int num_sms, cudaStream_t stream) {
-    static bool configured = false;
-    static int max_pairs = 0;               // co-resident 2-CTA clusters (1 CTA / SM, both SMs in one TPC)
-    if (!configured) {
+    static PerDevice dev_state;
+    if (!dev_state.configured()) {
         OSTEO_CUDA(cudaFuncSetAttribute(gemm_ws2_gn_silu_kernel<GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM_BYTES));
         cudaLaunchConfig_t qc = {};
         qc.gridDim = dim3(static_cast<unsigned>(num_sms & ~1), 1, 1);
@@ -295,10 +294,11 @@ int launch_gemm_ws2_inst(const GemmParams& p, int num_sms, cudaStream_t stream) 
         qc.attrs = qa;
         qc.numAttrs = 1;
         int n = 0;
-        if (cudaOccupancyMaxActiveClusters(&n, gemm_ws2_gn_silu_kernel<GW>, &qc) == cudaSuccess) max_pairs = n;
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_ws2_gn_silu_kernel<GW>, &qc) == cudaSuccess) dev_state.val() = n;
         else cudaGetLastError();
-        configured = true;
+        dev_state.set_configured();
     }
+    const int max_pairs = dev_state.val();      // co-resident 2-CTA clusters on this device (0 = clusters unavailable / not queried)
     if (p.m_tiles <= 0) return 0;
     const int n_pairs = p.n_tiles / 2;
     if (max_pairs < n_pairs) return -2;

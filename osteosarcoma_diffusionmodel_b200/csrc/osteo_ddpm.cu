@@ -476,11 +476,11 @@ static int launch_output_eps(osteo_ddpm_ctx* c, long long row0, long long row1, 
 // Fused tail of a bf16 reverse step: output_proj + reverse update + next step's input_proj (fused_step.cuh).
 static int launch_fused(osteo_ddpm_ctx* c, long long row0, long long row1, const float* noise, float* eps_out, unsigned long long seed, long long row_base,
                         cudaStream_t s) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice dev_state;
+    if (!dev_state.configured()) {
         OSTEO_CUDA(cudaFuncSetAttribute(ddpm_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
         OSTEO_CUDA(cudaFuncSetAttribute(ddpm_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
-        configured = true;
+        dev_state.set_configured();
     }
     FusedParams p;
     std::memset(&p, 0, sizeof p);

@@ -363,10 +363,10 @@ inline int launch_moments_tiled(const float* data_dev, int ld, int ncols, const 
     while (stages > 2 && moments_tiled_smem(n_sets, 4 * NB, ncols, stages) > static_cast<size_t>(CT_SMEM_LIMIT)) --stages;
     const size_t smem = moments_tiled_smem(n_sets, 4 * NB, ncols, stages);
     if (smem > CT_SMEM_LIMIT) return fail("corr_moments_tiled: %d columns x %d sets need %zu bytes of shared memory per block (limit %d)", ncols, n_sets, smem, CT_SMEM_LIMIT);
-    static bool configured = false;
-    if (!configured) {
+    static PerDevice dev_state;
+    if (!dev_state.configured()) {
         OSTEO_CUDA(cudaFuncSetAttribute(corr_moments_tiled_kernel<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_LIMIT));
-        configured = true;
+        dev_state.set_configured();
     }
     const long long nchunks = (row_end - row_begin + CT_CHUNK - 1) / CT_CHUNK;
     const long long blocks = nchunks < sms ? nchunks : sms;

@@ -144,6 +144,24 @@ def test_model_on_a_non_current_device():
     loss.backward()
     assert torch.isfinite(loss).item() and torch.cuda.current_device() == 0
     model.check_status()
+    # the optimiser step and the validators too: their kernels opt in to large shared memory PER DEVICE (a process-wide "configured" flag
+    # made the first launch on cuda:1 fail with "invalid argument" after cuda:0 had been used)
+    from osteosarcoma_diffusionmodel_b200.optim import FusedAdamW
+    from osteosarcoma_diffusionmodel_b200.validation import BiologicalValidator
+    opt = FusedAdamW(model.parameters(), lr=1e-3, weight_decay=0.01, max_grad_norm=1.0)
+    opt.step()
+    assert torch.cuda.current_device() == 0
+    g = torch.Generator().manual_seed(3)
+    X, Y = torch.randn(300, 120, generator=g), torch.randn(260, 120, generator=g) + 0.1
+    members = [list(range(12 * i, 12 * i + 12)) for i in range(4)]
+    res = {}
+    for dev in ("cuda:0", "cuda:1"):
+        val = BiologicalValidator({"evaluation": {}}, device=dev)
+        res[dev] = (val.compute_mmd(X.to(dev), Y.to(dev)), val.pathway_coherence_from_tensors(X.to(dev), Y[:, :120].to(dev), members))
+        assert torch.cuda.current_device() == 0
+    assert res["cuda:0"][0] == res["cuda:1"][0]
+    for k, v in res["cuda:0"][1].items():
+        assert abs(v - res["cuda:1"][1][k]) < 1e-9
     del model
     gc.collect()
     assert torch.cuda.current_device() == 0
