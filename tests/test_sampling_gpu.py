@@ -283,3 +283,31 @@ def test_shard_writer_matches_sample_components(tmp_path):
         assert np.array_equal(got["pathways"], whole["pathways"].cpu().numpy())
         assert np.array_equal(got["conditions"], cond.cpu().numpy())
     model.check_status()
+
+
+def test_block_gemm_kernel_variants_agree(monkeypatch):
+    """The Linear+GroupNorm+SiLU layers of the bf16 mode run on three kernels -- the generic streaming kernel, the weight-stationary kernel
+    (lean epilogue, per-warp TMA stores for K <= 384, st.global otherwise) and the CTA-pair (cta_group::2) kernel for the 512 x 512 layers.
+    Same inputs through every combination, at a row count that is neither a whole number of 128-row blocks nor an even number of them (the
+    last pair of the CTA-pair kernel has one live block): they may differ by bf16 rounding of the activations only, and each stays within
+    the single-call bf16 tolerance of the fp32x3 result."""
+    case = load_case("config")
+    n = 5 * 128 - 17
+    rs = np.random.RandomState(11)
+    x_t = torch.from_numpy(rs.standard_normal((n, case["D"])).astype(np.float32)).cuda()
+    t = torch.from_numpy(rs.randint(0, case["T"], size=n).astype(np.int64)).cuda()
+    cond = synth.scenario_conditions(n, 3).cuda()
+    ref = build_model(case, "fp32x3").predict_noise(x_t, t, cond)
+    outs = {}
+    for name, env in {"default": {}, "one_cta_only": {"OSTEO_WS2": "0"}, "pairs_everywhere": {"OSTEO_WS2": "2"}, "st_global": {"OSTEO_WS_TMA_STORE": "0"},
+                      "generic": {"OSTEO_DDPM_NO_WS": "1"}}.items():
+        for k in ("OSTEO_WS2", "OSTEO_WS_TMA_STORE", "OSTEO_DDPM_NO_WS"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        model = build_model(case, "bf16")          # the switches are read when the context is created
+        outs[name] = model.predict_noise(x_t, t, cond)
+        model.check_status()
+        assert rel(outs[name], ref) < TOL_BF16, name
+    for name, o in outs.items():
+        assert rel(o, outs["generic"]) < 5e-3, name
