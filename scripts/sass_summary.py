@@ -4,7 +4,7 @@
 import collections, re, subprocess, sys
 so = sys.argv[1] if len(sys.argv) > 1 else "osteosarcoma_diffusionmodel_b200/libosteo_ddpm.so"
 sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
-keys = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKPF", "UTMAPF", "UTCBAR", "SYNCS", "LDGSTS", "HMMA", "MUFU", "FFMA"]
+keys = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKPF", "UTMAPF", "UTCBAR", "SYNCS", "LDGSTS", "HMMA", "MUFU", "FFMA"]
 cur, counts = None, collections.OrderedDict()
 for line in sass.splitlines():
     m = re.search(r"Function : (\S+)", line)
@@ -23,7 +23,7 @@ for line in sass.splitlines():
                 counts[cur][k] += 1
 demangle = subprocess.run(["c++filt"], input="\n".join(counts), capture_output=True, text=True).stdout.splitlines()
 print(f"# cuobjdump -sass {so}: SASS instruction counts per kernel (static), sm_100a")
-print("# tcgen05.mma -> UTCHMMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG (tensor loads) / UBLKPF (bulk L2 prefetch), cp.async -> LDGSTS; HMMA (mma.sync) must be 0")
+print("# tcgen05.mma -> UTCHMMA, tcgen05.ld/st -> LDTM/STTM, TMA -> UTMALDG (tensor loads) / UBLKCP (bulk copy global -> shared) / UBLKPF (bulk L2 prefetch), cp.async -> LDGSTS; HMMA (mma.sync) must be 0")
 print("kernel," + ",".join(keys) + ",total_sass")
 for (mangled, c), name in zip(counts.items(), demangle):
     if c["_total"] == 0:
