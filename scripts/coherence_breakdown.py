@@ -7,7 +7,7 @@ import torch
 from osteosarcoma_diffusionmodel_b200.validation import BiologicalValidator, _coherence_finish, _CM_STRIDE
 
 dev = torch.device("cuda")
-rows = 1_000_000
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
 cohort = torch.randn(rows, 371, device=dev)
 members = [list(range(15 * p, 15 * p + 15)) for p in range(10)]
 val = BiologicalValidator({"evaluation": {}})
