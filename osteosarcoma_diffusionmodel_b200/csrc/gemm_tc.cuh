@@ -88,7 +88,8 @@ struct GemmParams {
     int n_chunks;             //   ... and split each m-block's n-tiles into this many work units (load balance)
     int dbg;                  // diagnostic switches (0 in production; scripts/ddpm_probe.py)
     CUtensorMap tma_out;      // gemm_ws: output view (box 32 rows x 32 columns) for the per-warp TMA stores
-    int out_tma;              // != 0: the weight-stationary kernel stores its bf16 output through tma_out
+    int out_tma;              // != 0: the weight-stationary kernels store their bf16 output through tma_out (OSTEO_WS_TMA_STORE; 2 = also the
+                              // single-CTA kernel at K = 512 with half the warps staged, an experiment that measured slower)
     int a_blocked_nbox;       // > 0: tma_a[0] views a BLOCKED operand [m_tile][nbox][128 rows][64 cols] (16 KB contiguous per k-block)
     int* status;              // sticky error word (device)
     long long row_base;       // global row index of row 0 (RNG keying under row sharding)
