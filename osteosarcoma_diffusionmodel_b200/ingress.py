@@ -8,6 +8,8 @@ Here the dataset lives in HBM once and a batch is ONE kernel per tensor: gather 
 
   GpuResidentDataset   the tensors of OsteosarcomaDataset (`data` = [mutations | expression | pathways], `conditions`,
                        `survival_days`; utils/train.py:52-68) moved to the device once; `batches()` = DataLoader(shuffle, drop_last).
+                       `from_frames()` builds them from the four aligned tables `prepare_data` reads (utils/train.py:342-409): the
+                       z-scoring of the pathway scores and of the survival time, the index alignment and the NaN rules included.
   MixupAugmentation    same constructor and call signature as utils/train.py:85-126 for already-gathered batches, plus
                        `gather(dataset, index)` which fuses the gather and the mix.
 There is no CPU fallback.
@@ -57,6 +59,65 @@ class GpuResidentDataset:
             base, idx = dataset.dataset, torch.as_tensor(list(dataset.indices), dtype=torch.long)
         pick = (lambda t: t[idx]) if idx is not None else (lambda t: t)
         return cls(pick(base.data), pick(base.conditions), pick(base.survival_days), device=device)
+
+    @classmethod
+    def from_frames(cls, mutation_matrix, expression_matrix, pathway_scores, clinical_data, condition_features=None, normalize: bool = True,
+                    device="cuda") -> "GpuResidentDataset":
+        """From the four tables of `prepare_data` (utils/train.py:349-363: patients x genes / pathways DataFrames indexed by submitter id, and
+        the clinical table with a `submitter_id` column), doing what prepare_data + OsteosarcomaDataset do between the CSVs and the tensors:
+          * pathway scores z-scored per column over ALL their rows, `(x - mean) / (std + 1e-8)`, sample std (ddof = 1, NaN skipped) like
+            pandas (utils/train.py:387); `survival_days_norm` the same way from `survival_days` (:390-392); expression stays as it is (:384);
+          * condition features = those of [survival_days_norm, event_occurred, age_years, metastasis_at_diagnosis] present (:395-398),
+            unless given;
+          * rows = the ids common to all four tables, in the mutation table's order (utils/train.py:38-43); NaN conditions -> 0, NaN
+            survival -> 0 (:60-66); `data` = [mutations | expression | pathways] fp32 (:46-56).
+        The statistics are taken in float64 on the device (the tables can be millions of rows) and the result is rounded to fp32 once, as
+        pandas' float64 arithmetic followed by `.astype(np.float32)` does. `normalize=False` skips the two z-scorings (tables that
+        prepare_data has already normalised). `.config_dims()` gives the four sizes prepare_data stores in config['model'] (:439-442)."""
+        import pandas as pd
+
+        dev = torch.device(device)
+        clinical = clinical_data.set_index("submitter_id")
+        common = mutation_matrix.index.intersection(expression_matrix.index).intersection(pathway_scores.index).intersection(clinical.index)
+
+        def zscore(t: torch.Tensor) -> torch.Tensor:          # float64 [n, k] on the device, NaN-skipping, ddof = 1
+            ok = ~torch.isnan(t)
+            cnt = ok.sum(0).to(torch.float64)
+            x = torch.where(ok, t, torch.zeros_like(t))
+            mean = x.sum(0) / cnt
+            var = (torch.where(ok, t - mean, torch.zeros_like(t)) ** 2).sum(0) / (cnt - 1.0)
+            return (t - mean) / (var.sqrt() + 1e-8)
+
+        def dev64(frame_or_series) -> torch.Tensor:
+            a = np.array(frame_or_series.to_numpy(dtype=np.float64), copy=True, order="C")          # pandas may hand out a read-only view
+            return torch.from_numpy(a).to(dev)
+
+        paths = dev64(pathway_scores)
+        if normalize:
+            paths = zscore(paths)
+        pos = torch.as_tensor(pathway_scores.index.get_indexer(common), device=dev)
+        paths = paths[pos]
+        clin = clinical.copy()
+        if normalize and "survival_days" in clin.columns:
+            sd = zscore(dev64(clinical_data["survival_days"]).reshape(-1, 1)).reshape(-1)
+            clin["survival_days_norm"] = sd.cpu().numpy()
+        if condition_features is None:
+            condition_features = [f for f in ("survival_days_norm", "event_occurred", "age_years", "metastasis_at_diagnosis") if f in clin.columns]
+        clin = clin.loc[common]
+        cond = torch.nan_to_num(dev64(clin[list(condition_features)]).to(torch.float32), nan=0.0)
+        surv = dev64(clin["survival_days"].fillna(0)).to(torch.float32)
+        mut = torch.from_numpy(np.array(mutation_matrix.loc[common].to_numpy(dtype=np.float32), copy=True, order="C")).to(dev)
+        expr = torch.from_numpy(np.array(expression_matrix.loc[common].to_numpy(dtype=np.float32), copy=True, order="C")).to(dev)
+        out = cls(torch.cat([mut, expr, paths.to(torch.float32)], dim=1), cond, surv, device=dev)
+        out.condition_features = list(condition_features)
+        out._dims = {"n_genes_mutation": int(mut.shape[1]), "n_genes_expression": int(expr.shape[1]), "n_pathways": int(paths.shape[1]),
+                     "n_conditions": len(condition_features)}
+        out.index = pd.Index(common)
+        return out
+
+    def config_dims(self) -> Dict[str, int]:
+        """The sizes prepare_data writes into config['model'] (utils/train.py:439-442); only for datasets built by from_frames()."""
+        return dict(self._dims)
 
     def __len__(self) -> int:
         return self.data.shape[0]
