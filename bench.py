@@ -720,12 +720,19 @@ def run_secondary_dp(model, dev, dist, rank, world, tf_peak):
     opt = torch.optim.AdamW(model.parameters(), lr=1e-4, weight_decay=1e-5)
     ms = timed(lambda: Dm.dp_train_step(model, opt, x0, cond), 4, 10)
     out["dp_train_step"] = {"batch_per_gpu": B, "global_batch": B * world, "ms_per_step": ms, "samples_per_s": B * world / (ms / 1e3),
-                            "allreduce": "one NCCL all-reduce of the flat fp32 gradient buffer per step, after the graph-replayed backward"}
+                            "allreduce": "one NCCL all-reduce of the flat fp32 gradient buffer per step, after the graph-replayed backward; *_overlap = the "
+                                         "backward pass cut in two graph launches with the all-reduce of the first part's gradients (output_proj + decoder, "
+                                         "about half of the 17 MB) running beside the second part (model._dp_overlap / OSTEO_DP_OVERLAP=1)"}
     try:      # the same step with the library's fused clip + AdamW (two launches; the torch optimiser's host enqueue bounds the step above)
         from osteosarcoma_diffusionmodel_b200.optim import FusedAdamW
         fopt = FusedAdamW(model.parameters(), lr=1e-4, weight_decay=1e-5, max_grad_norm=1.0)
         ms_f = timed(lambda: Dm.dp_train_step(model, fopt, x0, cond), 4, 10)
         out["dp_train_step"]["fused_optimizer_ms_per_step"] = ms_f
+        # configs[3]: "report step time with and without allreduce overlap"
+        keep = model._dp_overlap
+        model._dp_overlap = True
+        out["dp_train_step"]["fused_optimizer_ms_per_step_overlap"] = timed(lambda: Dm.dp_train_step(model, fopt, x0, cond), 4, 10)
+        model._dp_overlap = keep
         del fopt
     except Exception as e:
         out["dp_train_step"]["fused_optimizer_error"] = repr(e)

@@ -175,6 +175,14 @@ int osteo_ddpm_train_backward(osteo_ddpm_ctx* ctx, const float* cond_dev, long l
                               const uint8_t* const* drop_masks_dev, int train, uint64_t seed, long long row_base,
                               float* const* grads_dev, int n_tensors, void* stream);
 
+/* The backward pass cut in two launches, so that a data-parallel caller can all-reduce the gradients of the first part while the second
+ * runs (the reference has one loss.backward() and no data parallelism: utils/train.py:236-244). part 1: loss gradient, output_proj and
+ * the Linear+GroupNorm half blocks j >= cut = the gradient tensors [10 + 4 * cut, n_tensors); part 2: the rest. Both after
+ * osteo_ddpm_train_forward, part 1 first; together they enqueue the kernels of osteo_ddpm_train_backward in the same order. */
+int osteo_ddpm_train_backward_part(osteo_ddpm_ctx* ctx, const float* cond_dev, long long n, const int* t_idx_dev,
+                                   const uint8_t* const* drop_masks_dev, int train, uint64_t seed, long long row_base,
+                                   float* const* grads_dev, int n_tensors, int part, int cut, void* stream);
+
 /* With nothing injected (noise_dev == NULL, drop_masks_dev == NULL) and gradients requested, everything of the step after the two
  * kernels that read x0_dev / cond_dev is replayed as ONE executable graph from the second call with the same n and gradient
  * addresses on (keep the gradient tensors persistent to benefit); enable = 0 keeps every call eager. Default 1. */

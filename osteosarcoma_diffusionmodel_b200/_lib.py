@@ -61,6 +61,7 @@ SIGNATURES = {
     "osteo_ddpm_train_x0hat": (_i, [_vp, _vp, _vp, _ll, _vp, _i, _vp, _vp]),
     "osteo_ddpm_train_inject": (_i, [_vp, _vp, _ll, _vp, _i, _vp, _vp]),
     "osteo_ddpm_train_backward": (_i, [_vp, _vp, _ll, _vp, C.POINTER(_vp), _i, _u64, _ll, C.POINTER(_vp), _i, _vp]),
+    "osteo_ddpm_train_backward_part": (_i, [_vp, _vp, _ll, _vp, C.POINTER(_vp), _i, _u64, _ll, C.POINTER(_vp), _i, _i, _i, _vp]),
     "osteo_ddpm_enable_training": (_i, [_vp, _i]),
     "osteo_adamw_create": (_i, [C.POINTER(_vp), _i, C.POINTER(_ll)]),
     "osteo_adamw_destroy": (_i, [_vp]),

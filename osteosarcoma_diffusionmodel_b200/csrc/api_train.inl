@@ -56,6 +56,8 @@ static int ensure_train_ws(osteo_ddpm_ctx* c) {
     c->train_graph.reset();
     c->train_fwd_graph.reset();
     c->train_bwd_graph.reset();
+    c->train_bwd_part_graph[0].reset();
+    c->train_bwd_part_graph[1].reset();
     for (int i = 0; i < 2; ++i) {
         OSTEO_CUDA(cudaStreamCreateWithFlags(&w.side[i], cudaStreamNonBlocking));
         OSTEO_CUDA(cudaEventCreateWithFlags(&w.ev_join[i], cudaEventDisableTiming));
@@ -200,8 +202,11 @@ __global__ void x0hat_inject_kernel(const int* __restrict__ t_idx, const float* 
 // Philox key of the dropout masks.
 static int train_body(osteo_ddpm_ctx* c, const float* cond_dev, long long n, const int* t_idx_dev, const uint8_t* const* drop_masks_dev, int train,
                       unsigned long long seed, const unsigned long long* seed_dev, long long row_base, float* loss_dev, float* const* grads_dev, int n_tensors,
-                      cudaStream_t s, int phase = 0) {
+                      cudaStream_t s, int phase = 0, int bwd_part = 0, int cut = 0) {
     // phase 0: forward + backward; 1: forward only, with the statistics the backward needs; 2: backward only (after a phase-1 call)
+    // bwd_part (phase 2 only) cuts the backward pass in two launches so that a data-parallel caller can all-reduce the gradients of the
+    // first part while the second runs: 1 = loss gradient, output_proj and the half blocks j >= cut (the TAIL of the gradient list),
+    // 2 = the half blocks j < cut, input_proj and the embedding paths (the head); 0 = everything
     const bool want_grads = grads_dev != nullptr || phase == 1;
     const int H = static_cast<int>(c->halves.size());
     TrainWorkspace& w = c->train;
@@ -262,7 +267,7 @@ static int train_body(osteo_ddpm_ctx* c, const float* cond_dev, long long n, con
         }
         return (j - 4 * H == 0) ? static_cast<size_t>(D) * h0 : static_cast<size_t>(D);
     };
-    {
+    if (bwd_part != 2) {
         // weight gradients accumulate atomically (split-batch wgrad): zero them; contiguous tensors share one memset
         int i = 0;
         while (i < n_tensors) {
@@ -289,12 +294,14 @@ static int train_body(osteo_ddpm_ctx* c, const float* cond_dev, long long n, con
     };
 
     // output_proj: bias gradient from the MSE epilogue's column partials, weight gradient = deps^T . act_last
+    if (bwd_part != 2) {
     OSTEO_TRY(fork_to(s1));
     OSTEO_TRY(finish_partials(c, w.partials[0]->as<float>(), n, 1, D, grads_dev[gi_out_b], nullptr, nullptr, s1));
     {
         const ActBuf& a = *c->acts.back();
         OSTEO_TRY(after_launch(c, launch_wgrad(w.deps.as<__nv_bfloat16>(), 2 * DP, DP, D, a.ptr(), 2 * a.width, 0, a.width, a.width, grads_dev[gi_out_w], a.width, n, x3,
                                                c->status_dev.as<int>(), c->sms, s1), s1));
+    }
     }
 
     // consumers of an activation: (half index, first input column of that activation inside the consumer's Linear)
@@ -307,7 +314,8 @@ static int train_body(osteo_ddpm_ctx* c, const float* cond_dev, long long n, con
         }
     };
     std::vector<std::pair<int, int>> cons;
-    for (int j = H - 1; j >= -1; --j) {
+    const int j_hi = bwd_part == 2 ? cut - 1 : H - 1, j_lo = bwd_part == 1 ? cut : -1;
+    for (int j = j_hi; j >= j_lo; --j) {
         // d(activation j+1) summed over its consumers, then this half's GroupNorm/SiLU/Dropout backward (j >= 0)
         GemmParams p;
         base_params(c, p);
@@ -382,6 +390,7 @@ static int train_body(osteo_ddpm_ctx* c, const float* cond_dev, long long n, con
             OSTEO_TRY(after_launch(c, launch_gemm(EPI_LINEAR, 64, p, c->sms, s), s));
         }
     }
+    if (bwd_part != 1) {
     // Everything below needs only d(h0). Side stream 1: input_proj weight gradient (dh0^T . x_t, the largest wgrad); side stream 2: the
     // three bias gradients that equal colsum(d(h0)) and the time_proj / cond_proj weight gradients; `s`: the ConditionalEmbedding chain.
     OSTEO_TRY(fork_to(s1));
@@ -427,6 +436,7 @@ static int train_body(osteo_ddpm_ctx* c, const float* cond_dev, long long n, con
     }
     OSTEO_TRY(outer_accum(c, w.dcemb.as<float>(), E, w.h1.as<float>(), E, nullptr, n, grads_dev[2], s));
     OSTEO_TRY(outer_accum(c, w.dpre0.as<float>(), E, cond_dev, c->C, nullptr, n, grads_dev[0], s));
+    }
     for (int i = 0; i < 2 && overlap; ++i) {
         OSTEO_CUDA(cudaEventRecord(w.ev_join[i], w.side[i]));
         OSTEO_CUDA(cudaStreamWaitEvent(s, w.ev_join[i], 0));
@@ -459,6 +469,10 @@ int osteo_ddpm_set_train_graph(osteo_ddpm_ctx* c, int enable) {
         c->train_graph.reset();
         c->train_fwd_graph.reset();
         c->train_bwd_graph.reset();
+        c->train_bwd_part_graph[0].reset();
+        c->train_bwd_part_graph[1].reset();
+    c->train_bwd_part_graph[0].reset();
+    c->train_bwd_part_graph[1].reset();
     }
     return 0;
 }
@@ -582,6 +596,37 @@ int osteo_ddpm_train_backward(osteo_ddpm_ctx* c, const float* cond_dev, long lon
         }));
     }
     w.fwd_n = -1;
+    return 0;
+}
+
+
+// The backward pass in two launches (after osteo_ddpm_train_forward): part 1 = loss gradient, output_proj and the half blocks j >= cut,
+// i.e. the gradient tensors [10 + 4 cut, n_tensors) -- the TAIL of the list; part 2 = the rest. A data-parallel caller starts the
+// all-reduce of the tail while part 2 runs (utils/train.py:236-244 has one backward() and no overlap). Parts 1 and 2 together enqueue
+// exactly the kernels of osteo_ddpm_train_backward, in the same order: the gradients are the same bits.
+int osteo_ddpm_train_backward_part(osteo_ddpm_ctx* c, const float* cond_dev, long long n, const int* t_idx_dev, const uint8_t* const* drop_masks_dev, int train,
+                                   uint64_t seed, long long row_base, float* const* grads_dev, int n_tensors, int part, int cut, void* stream) {
+    if (!grads_dev) return fail("train_backward_part: grads_dev is required");
+    OSTEO_TRY(train_check(c, n, t_idx_dev, grads_dev, n_tensors, true));
+    if (part != 1 && part != 2) return fail("train_backward_part: part %d outside {1, 2}", part);
+    if (cut < 0 || cut > static_cast<int>(c->halves.size())) return fail("train_backward_part: cut %d outside [0, %d]", cut, static_cast<int>(c->halves.size()));
+    if (c->train.fwd_n != n) return fail("train_backward_part: no forward pass of %lld rows is pending (osteo_ddpm_train_forward)", n);
+    TrainWorkspace& w = c->train;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!w.fwd_graphed || drop_masks_dev) {
+        OSTEO_TRY(train_body(c, cond_dev, n, t_idx_dev, drop_masks_dev, train, seed, nullptr, row_base, nullptr, grads_dev, n_tensors, s, /*phase=*/2, part, cut));
+    } else {
+        std::vector<unsigned long long> key{static_cast<unsigned long long>(n), static_cast<unsigned long long>(train != 0), static_cast<unsigned long long>(row_base),
+                                            static_cast<unsigned long long>(c->precision), static_cast<unsigned long long>(c->ws_enable),
+                                            reinterpret_cast<unsigned long long>(c->acts[0]->ptr()), reinterpret_cast<unsigned long long>(w.deps.p),
+                                            reinterpret_cast<unsigned long long>(c->out_proj.wt.p), c->generation, static_cast<unsigned long long>(cut)};
+        for (int i = 0; i < n_tensors; ++i) key.push_back(reinterpret_cast<unsigned long long>(grads_dev[i]));
+        OSTEO_TRY(run_cached(c, c->train_bwd_part_graph[part - 1], key, s, [&](cudaStream_t q) {
+            return train_body(c, w.cond_copy.as<float>(), n, w.t_copy.as<int>(), nullptr, train, seed, c->seed_dev.as<unsigned long long>(), row_base, nullptr,
+                              grads_dev, n_tensors, q, /*phase=*/2, part, cut);
+        }));
+    }
+    if (part == 2) w.fwd_n = -1;
     return 0;
 }
 

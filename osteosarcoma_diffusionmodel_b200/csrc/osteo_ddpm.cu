@@ -254,6 +254,7 @@ struct osteo_ddpm_ctx {
     std::vector<cudaEvent_t>* prof = nullptr;   // when set, an event is recorded after every GEMM launch
     // graph caches of the training path (api_train.inl): weight repack after an optimizer step, forward + backward
     GraphSlot weights_graph, train_graph, train_fwd_graph, train_bwd_graph;      // the last two: the halves of the two-phase step
+    GraphSlot train_bwd_part_graph[2];   // the backward pass cut in two (osteo_ddpm_train_backward_part: gradient all-reduce overlap)
     unsigned long long generation = 0;   // bumped by every (re)allocation of device buffers: part of every graph key (an address can be reused)
     cudaStream_t aux[3] = {nullptr, nullptr, nullptr};      // lanes of the weight repack
     cudaEvent_t aux_fork = nullptr, aux_join[3] = {nullptr, nullptr, nullptr};

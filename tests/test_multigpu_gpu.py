@@ -52,6 +52,7 @@ def _worker(rank, ws, port, q):
     lo, hi = D.shard_rows(B, rank, ws)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-3)
     model._inject = {"t": t[lo:hi], "noise": noise[lo:hi], "masks": [m[lo:hi] for m in masks]}
+    model._dp_overlap = True          # the two-piece all-reduce with the backward pass cut in between (opt-in): same result
     D.dp_train_step(model, opt, x0[lo:hi].to(dev), c[lo:hi].to(dev))
     ropt = torch.optim.AdamW(ref.parameters(), lr=1e-3)
     ref._inject = {"t": t, "noise": noise, "masks": masks}
