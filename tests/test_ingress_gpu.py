@@ -75,3 +75,24 @@ def test_argument_checks():
         ds.gather(torch.arange(4, dtype=torch.int32, device="cuda"))
     with pytest.raises(ValueError):
         ds.gather(torch.arange(4))                # index on the host
+
+
+def test_from_frames_on_the_device_feeds_the_batch_kernel():
+    """The table preparation (prepare_data's normalisation + the dataset's alignment) done on the GPU equals the same on the CPU to fp32
+    rounding, and its tensors go straight into the gather + mixup kernel."""
+    import numpy as np
+    from tests.test_ingress_frames_cpu import _tables
+    from osteosarcoma_diffusionmodel_b200.ingress import GpuResidentDataset, MixupAugmentation
+
+    mut, expr, path, clin = _tables(n=300, seed=8)
+    gpu = GpuResidentDataset.from_frames(mut, expr, path, clin, device="cuda")
+    cpu = GpuResidentDataset.from_frames(mut, expr, path, clin, device="cpu")
+    assert gpu.data.is_cuda and len(gpu) == len(cpu) == 299
+    np.testing.assert_allclose(gpu.data.cpu().numpy(), cpu.data.numpy(), rtol=2e-7, atol=1e-7)
+    np.testing.assert_allclose(gpu.conditions.cpu().numpy(), cpu.conditions.numpy(), rtol=2e-7, atol=1e-7)
+    assert torch.equal(gpu.survival_days.cpu(), cpu.survival_days)
+    seen = 0
+    for batch in gpu.batches(64, shuffle=True, drop_last=True, mixup=MixupAugmentation(0.2), generator=torch.Generator(device="cuda").manual_seed(1)):
+        assert batch["data"].shape == (64, 7 + 11 + 5) and batch["conditions"].shape == (64, 3) and torch.isfinite(batch["data"]).all()
+        seen += 1
+    assert seen == 299 // 64
