@@ -81,3 +81,20 @@ def test_optimizer_and_clip_see_the_parameters():
     m = make(dims=synth.SMOKE_DIMS)
     opt = torch.optim.AdamW(m.parameters(), lr=1e-4, weight_decay=1e-5)   # utils/train.py:169-173
     assert sum(len(g["params"]) for g in opt.param_groups) == 52
+
+
+@pytest.mark.parametrize("hidden", [(256, 512, 256), (128, 256), (512, 512, 512, 256)])
+def test_data_parallel_cut_is_a_half_block_boundary_near_the_middle(hidden):
+    """model._dp_cut: the backward pass is cut before half block `cut`; the gradients finished by then are the tensors [10 + 4 cut, end)
+    of the C-ABI order = elements [offset, total) of the flat gradient buffer -- a contiguous tail, about half of the bytes, that always
+    contains output_proj (the first gradients the backward pass produces)."""
+    m = make(hidden_dims=hidden)
+    ps = m._param_list()
+    sizes = [p.numel() for p in ps]
+    cut, off = m._dp_cut(ps)
+    n_halves = (len(ps) - 12) // 4
+    assert len(ps) == 12 + 4 * n_halves and 1 <= cut <= n_halves
+    assert off == sum(sizes[:10 + 4 * cut])
+    total = sum(sizes)
+    assert off + sizes[-1] + sizes[-2] <= total                 # output_proj (weight, bias) is in the tail
+    assert 0.2 < off / total < 0.8
